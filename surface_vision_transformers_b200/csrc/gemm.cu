@@ -1,0 +1,600 @@
+// gemm.cu -- warp-specialised TMA -> smem -> tcgen05.mma -> TMEM -> epilogue GEMM kernels for sm_100a.
+//
+// Hot path reference (what these kernels replace): every nn.Linear of the SiT encoder
+// (/root/reference/models/sit.py:45-64 and the vit_pytorch Transformer it constructs at sit.py:57),
+// forward and backward.  See gemm.cuh for the two entry points.
+#include "gemm.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+
+#include <cuda_bf16.h>
+#include <cstring>
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace svit {
+
+static thread_local char g_last_error[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_last_error; }
+
+// ------------------------------------------------------------------------------------------------
+// exact (erf) GELU, as nn.GELU() in the reference FeedForward
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TN GEMM
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int EPI_BUF_BYTES = BM * 128;     // 128 rows x 128 B
+constexpr int NUM_EPI_BUFS = 4;
+constexpr int TN_THREADS = 256;
+
+struct TnArgs {
+    CUtensorMap tmA, tmB, tmOut, tmOut2, tmAux;
+    const float* bias;
+    const float* rowtab;
+    int rowtab_period;
+    int M, N, K;
+};
+
+template <int BN>
+struct TnCfg {
+    static constexpr int STAGES = (BN >= 256) ? 3 : 4;
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + NUM_EPI_BUFS * EPI_BUF_BYTES +
+                                      BN * 4 /*bias*/ + 256 /*barriers*/;
+};
+
+template <typename OutT, int MODE, int BN>
+__global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_constant__ TnArgs args) {
+    using Cfg = TnCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int UC = 128 / (int)sizeof(OutT);  // columns per epilogue unit (one 128-byte row of the staging box)
+    constexpr int UNITS = BN / UC;
+    static_assert(BN % UC == 0, "BN must be a multiple of the epilogue unit");
+    constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU);
+    constexpr int OUTS_PER_UNIT = (MODE == EPI_GELU) ? 2 : 1;
+    constexpr int FIRST_OUT_BUF = HAS_AUX ? 2 : 0;
+    constexpr int NUM_OUT_BUFS = NUM_EPI_BUFS - FIRST_OUT_BUF;
+    constexpr int OUT_SLOTS = NUM_OUT_BUFS / OUTS_PER_UNIT;  // units that may be in flight
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;
+    float* sBias = reinterpret_cast<float*>(sEpi + NUM_EPI_BUFS * EPI_BUF_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+    uint64_t* full_bar = bars;                  // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+    uint64_t* afull_bar = tempty_bar + 2;       // [2]
+    uint64_t* aempty_bar = afull_bar + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int M = args.M, N = args.N, K = args.K;
+    const int tiles_m = (M + BM - 1) / BM;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&args.tmA);
+        tma_prefetch_desc(&args.tmB);
+        tma_prefetch_desc(&args.tmOut);
+        if (MODE == EPI_GELU) tma_prefetch_desc(&args.tmOut2);
+        if (HAS_AUX) tma_prefetch_desc(&args.tmAux);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&afull_bar[i], 1);
+            mbar_init(&aempty_bar[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 3) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sA + stage * A_STAGE_BYTES, &args.tmA, &full_bar[stage], kb * BK, m0);
+                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &args.tmB, &full_bar[stage], kb * BK, n0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== aux (residual / pre-activation) loader =====================
+        if (HAS_AUX && elect_one()) {
+            int ait = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int u = 0; u < UNITS; ++u, ++ait) {
+                    const int s = ait & 1;
+                    const uint32_t ph = (ait >> 1) & 1;
+                    mbar_wait(&aempty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&afull_bar[s], EPI_BUF_BYTES);
+                    tma_load_2d(sEpi + s * EPI_BUF_BYTES, &args.tmAux, &afull_bar[s], n0 + u * UC, m0);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;  // row inside the tile == TMEM lane
+        const bool leader = (threadIdx.x == 4 * 32);
+        const int et = threadIdx.x - 4 * 32;  // 0..127
+        int it = 0, ait = 0, oit = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / tiles_n) * BM;
+            const int n0 = (tile % tiles_n) * BN;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            // stage the bias slice of this tile
+            for (int i = et; i < BN; i += 128) {
+                const int c = n0 + i;
+                sBias[i] = (args.bias != nullptr && c < N) ? args.bias[c] : 0.0f;
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+            const int grow = m0 + row;
+#pragma unroll 1
+            for (int u = 0; u < UNITS; ++u, ++oit) {
+                float v[UC];
+#pragma unroll
+                for (int h = 0; h < UC / 32; ++h) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + u * UC + h * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[j]) + sBias[u * UC + h * 32 + j];
+                }
+                if (u == UNITS - 1) {
+                    // accumulator fully read: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                }
+                if (MODE == EPI_STORE && args.rowtab != nullptr) {
+                    const float* tr = args.rowtab + static_cast<size_t>(grow % args.rowtab_period) * N + n0 + u * UC;
+#pragma unroll
+                    for (int j = 0; j < UC; j += 4) {
+                        if (n0 + u * UC + j < N) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(tr + j);
+                            v[j] += t4.x;
+                            v[j + 1] += t4.y;
+                            v[j + 2] += t4.z;
+                            v[j + 3] += t4.w;
+                        }
+                    }
+                }
+                if (HAS_AUX) {
+                    const int s = ait & 1;
+                    const uint32_t ph = (ait >> 1) & 1;
+                    mbar_wait(&afull_bar[s], ph);
+                    const uint8_t* arow = sEpi + s * EPI_BUF_BYTES + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 a4 = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+                        if (sizeof(OutT) == 4) {
+                            // fp32 aux: 4 values per 16-byte chunk
+                            v[c * 4 + 0] += __uint_as_float(a4.x);
+                            v[c * 4 + 1] += __uint_as_float(a4.y);
+                            v[c * 4 + 2] += __uint_as_float(a4.z);
+                            v[c * 4 + 3] += __uint_as_float(a4.w);
+                        } else {
+                            const uint32_t w[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+                                if (MODE == EPI_DGELU) {
+                                    v[(c * 8 + e * 2) % UC] *= dgelu_f(lo);
+                                    v[(c * 8 + e * 2 + 1) % UC] *= dgelu_f(hi);
+                                } else {
+                                    v[(c * 8 + e * 2) % UC] += lo;
+                                    v[(c * 8 + e * 2 + 1) % UC] += hi;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&aempty_bar[s]);
+                    ++ait;
+                }
+                // ---- stage the unit in shared memory (128B-swizzled rows) and TMA-store it ----
+                const int slot = oit % OUT_SLOTS;
+                uint8_t* obuf = sEpi + (FIRST_OUT_BUF + slot * OUTS_PER_UNIT) * EPI_BUF_BYTES;
+                if (leader) tma_store_wait_read<OUT_SLOTS - 1>();
+                named_bar_sync(1, 128);
+                uint8_t* orow = obuf + row * 128;
+                if (sizeof(OutT) == 4) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 o;
+                        o.x = __float_as_uint(v[(c * 4 + 0) % UC]);
+                        o.y = __float_as_uint(v[(c * 4 + 1) % UC]);
+                        o.z = __float_as_uint(v[(c * 4 + 2) % UC]);
+                        o.w = __float_as_uint(v[(c * 4 + 3) % UC]);
+                        *reinterpret_cast<uint4*>(orow + ((c ^ (row & 7)) << 4)) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 o;
+                        o.x = pack_bf16(v[(c * 8 + 0) % UC], v[(c * 8 + 1) % UC]);
+                        o.y = pack_bf16(v[(c * 8 + 2) % UC], v[(c * 8 + 3) % UC]);
+                        o.z = pack_bf16(v[(c * 8 + 4) % UC], v[(c * 8 + 5) % UC]);
+                        o.w = pack_bf16(v[(c * 8 + 6) % UC], v[(c * 8 + 7) % UC]);
+                        *reinterpret_cast<uint4*>(orow + ((c ^ (row & 7)) << 4)) = o;
+                    }
+                    if (MODE == EPI_GELU) {
+                        uint8_t* orow2 = orow + EPI_BUF_BYTES;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float g[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                // activation is applied to the bf16-rounded pre-activation that backward will see
+                                const float ub = bf16_lo(pack_bf16(v[(c * 8 + e) % UC], 0.0f));
+                                g[e] = gelu_f(ub);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16(g[0], g[1]);
+                            o.y = pack_bf16(g[2], g[3]);
+                            o.z = pack_bf16(g[4], g[5]);
+                            o.w = pack_bf16(g[6], g[7]);
+                            *reinterpret_cast<uint4*>(orow2 + ((c ^ (row & 7)) << 4)) = o;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    tma_store_2d(&args.tmOut, obuf, n0 + u * UC, m0);
+                    if (MODE == EPI_GELU) tma_store_2d(&args.tmOut2, obuf + EPI_BUF_BYTES, n0 + u * UC, m0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (leader) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient GEMM: dW[N,K] += dY[M,N]^T X[M,K]
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;
+constexpr int WG_BN = 192;  // tile over the K (input-feature) axis of dW
+constexpr int WG_STAGES = 4;
+constexpr int WG_A_BYTES = 64 * 128 * 2;    // 64 tokens x 128 out-features
+constexpr int WG_B_BYTES = 64 * WG_BN * 2;  // 64 tokens x 192 in-features
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
+
+struct WgArgs {
+    CUtensorMap tmY, tmX;
+    float* dW;
+    int M, N, K, ldw;
+    int kb_per_split;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_constant__ WgArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + WG_STAGES;
+    uint64_t* done_bar = bars + 2 * WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_k = (args.K + WG_BN - 1) / WG_BN;
+    const int n0 = (blockIdx.x / tiles_k) * 128;
+    const int k0 = (blockIdx.x % tiles_k) * WG_BN;
+    const int total_kb = (args.M + 63) / 64;
+    const int kb_begin = blockIdx.y * args.kb_per_split;
+    const int kb_end = min(total_kb, kb_begin + args.kb_per_split);
+    const int num_kb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&args.tmY);
+        tma_prefetch_desc(&args.tmX);
+        for (int i = 0; i < WG_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (num_kb > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+                    uint8_t* a = smem + stage * WG_STAGE_BYTES;
+                    uint8_t* b = a + WG_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tma_load_2d(a + j * 8192, &args.tmY, &full_bar[stage], n0 + j * 64, kb * 64);
+#pragma unroll
+                    for (int j = 0; j < WG_BN / 64; ++j)
+                        tma_load_2d(b + j * 8192, &args.tmX, &full_bar[stage], k0 + j * 64, kb * 64);
+                    if (++stage == WG_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                constexpr uint32_t idesc = umma_idesc_bf16(128, WG_BN, 1, 1);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int i = 0; i < num_kb; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + WG_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // MN-major, 128B swizzle: 64-element MN blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO)
+                        const uint64_t ad = umma_smem_desc(a_addr + k * 2048, 8192, 1024);
+                        const uint64_t bd = umma_smem_desc(b_addr + k * 2048, 8192, 1024);
+                        umma_ss(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == WG_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(done_bar);
+            }
+        } else {
+            // epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1
+            const int q = warp & 3;
+            const int row = q * 32 + lane;
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            const int n = n0 + row;
+            float* dst = args.dW + static_cast<size_t>(n) * args.ldw + k0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < WG_BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + c0 + (static_cast<uint32_t>(q * 32) << 16), r);
+                tmem_ld_wait();
+                if (n < args.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (k0 + c0 + j < args.K) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <typename OutT, int MODE, int BN>
+static int launch_tn_inst(const TnArgs& a, int num_sms, cudaStream_t stream) {
+    using Cfg = TnCfg<BN>;
+    auto kfn = gemm_tn_kernel<OutT, MODE, BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(gemm_tn) failed: %s", cudaGetErrorString(e));
+            return -10;
+        }
+        configured = true;
+    }
+    const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kfn<<<grid, TN_THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("gemm_tn launch failed: %s", cudaGetErrorString(e));
+        return -11;
+    }
+    return 0;
+}
+
+int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) {
+        set_error("gemm_tn: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
+        return -1;
+    }
+    if ((d.lda % 8) || (d.ldb % 8) || (d.ldo % (d.out_f32 ? 4 : 8)) || (d.N % 4)) {
+        set_error("gemm_tn: pitches must be 16-byte multiples (lda=%d ldb=%d ldo=%d N=%d)", d.lda, d.ldb, d.ldo, d.N);
+        return -2;
+    }
+    constexpr int BN = 192;
+    TnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bias = d.bias;
+    a.rowtab = d.rowtab;
+    a.rowtab_period = d.rowtab_period > 0 ? d.rowtab_period : 1;
+    a.M = d.M;
+    a.N = d.N;
+    a.K = d.K;
+    int rc = 0;
+    rc |= make_tmap_2d(&a.tmA, d.A, TmapDtype::BF16, d.K, d.M, (uint64_t)d.lda * 2, BK, BM);
+    rc |= make_tmap_2d(&a.tmB, d.B, TmapDtype::BF16, d.K, d.N, (uint64_t)d.ldb * 2, BK, BN);
+    const TmapDtype odt = d.out_f32 ? TmapDtype::F32 : TmapDtype::BF16;
+    const int osz = d.out_f32 ? 4 : 2;
+    rc |= make_tmap_2d(&a.tmOut, d.out, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, BM);
+    if (d.mode == EPI_GELU) rc |= make_tmap_2d(&a.tmOut2, d.out2, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, BM);
+    if (d.mode == EPI_RESID || d.mode == EPI_DGELU)
+        rc |= make_tmap_2d(&a.tmAux, d.aux, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, BM);
+    if (rc != 0) {
+        set_error("gemm_tn: tensor map creation failed: %s", tmap_last_error());
+        return -3;
+    }
+    if (d.out_f32) {
+        if (d.mode == EPI_STORE) return launch_tn_inst<float, EPI_STORE, BN>(a, num_sms, stream);
+        if (d.mode == EPI_RESID) return launch_tn_inst<float, EPI_RESID, BN>(a, num_sms, stream);
+    } else {
+        if (d.mode == EPI_STORE) return launch_tn_inst<__nv_bfloat16, EPI_STORE, BN>(a, num_sms, stream);
+        if (d.mode == EPI_GELU) return launch_tn_inst<__nv_bfloat16, EPI_GELU, BN>(a, num_sms, stream);
+        if (d.mode == EPI_RESID) return launch_tn_inst<__nv_bfloat16, EPI_RESID, BN>(a, num_sms, stream);
+        if (d.mode == EPI_DGELU) return launch_tn_inst<__nv_bfloat16, EPI_DGELU, BN>(a, num_sms, stream);
+    }
+    set_error("gemm_tn: unsupported mode %d for out_f32=%d", d.mode, d.out_f32);
+    return -4;
+}
+
+int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream) {
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) {
+        set_error("gemm_wgrad: empty problem");
+        return -1;
+    }
+    if ((d.ldy % 8) || (d.ldx % 8)) {
+        set_error("gemm_wgrad: pitches must be 16-byte multiples (ldy=%d ldx=%d)", d.ldy, d.ldx);
+        return -2;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(gemm_wgrad) failed: %s", cudaGetErrorString(e));
+            return -10;
+        }
+        configured = true;
+    }
+    WgArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = 0;
+    rc |= make_tmap_2d(&a.tmY, d.dY, TmapDtype::BF16, d.N, d.M, (uint64_t)d.ldy * 2, 64, 64);
+    rc |= make_tmap_2d(&a.tmX, d.X, TmapDtype::BF16, d.K, d.M, (uint64_t)d.ldx * 2, 64, 64);
+    if (rc != 0) {
+        set_error("gemm_wgrad: tensor map creation failed: %s", tmap_last_error());
+        return -3;
+    }
+    a.dW = d.dW;
+    a.M = d.M;
+    a.N = d.N;
+    a.K = d.K;
+    a.ldw = d.ldw;
+    const int tiles = ((d.N + 127) / 128) * ((d.K + WG_BN - 1) / WG_BN);
+    const int total_kb = (d.M + 63) / 64;
+    int splits = (2 * num_sms + tiles - 1) / tiles;
+    if (splits > total_kb) splits = total_kb;
+    if (splits < 1) splits = 1;
+    a.kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + a.kb_per_split - 1) / a.kb_per_split;
+    dim3 grid(tiles, splits);
+    gemm_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("gemm_wgrad launch failed: %s", cudaGetErrorString(e));
+        return -11;
+    }
+    return 0;
+}
+
+}  // namespace svit

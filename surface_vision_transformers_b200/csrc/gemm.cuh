@@ -1,0 +1,51 @@
+// gemm.cuh -- host-visible declarations of the tcgen05 GEMM kernels.
+//
+//   gemm_tn   : C[M,N] = A[M,K] * B[N,K]^T   (both operands K-major bf16, fp32 accumulate in TMEM)
+//               used for every nn.Linear forward (models/sit.py:50,  vit_pytorch Attention.to_qkv /
+//               to_out / FeedForward.net in the reference) and, with a transposed bf16 weight shadow,
+//               for every input-gradient GEMM of loss.backward() (tools/train.py:290).
+//   gemm_wgrad: dW[N,K] += dY[M,N]^T * X[M,K] (both operands MN-major, reduction over the token axis,
+//               split over CTAs, fp32 atomics into the flat gradient buffer).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace svit {
+
+enum EpiMode : int {
+    EPI_STORE = 0,  // out = acc (+ bias[col]) (+ rowtab[row % period][col])
+    EPI_GELU = 1,   // out = acc + bias (pre-activation); out2 = gelu(out)      (both bf16)
+    EPI_RESID = 2,  // out = acc + bias + aux                                    (aux/out same dtype)
+    EPI_DGELU = 3,  // out = acc * gelu'(aux)                                    (aux/out bf16)
+};
+
+struct GemmTnDesc {
+    const void* A;      // bf16 [M, K], row pitch lda elements
+    const void* B;      // bf16 [N, K], row pitch ldb elements
+    void* out;          // OutT [M, N], row pitch ldo elements
+    void* out2;         // EPI_GELU only: bf16 [M, N] (pitch ldo)
+    const void* aux;    // EPI_RESID / EPI_DGELU: same dtype/pitch as out
+    const float* bias;  // [N] or nullptr
+    const float* rowtab;  // [period, N] fp32 or nullptr (EPI_STORE only)
+    int rowtab_period;
+    int M, N, K;
+    int lda, ldb, ldo;
+    int mode;
+    int out_f32;  // 1: out (and aux) fp32, 0: bf16
+};
+
+// Returns 0 on success; on failure a negative code and a message retrievable by svit_last_error().
+int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream);
+
+struct GemmWgradDesc {
+    const void* dY;  // bf16 [M, N], pitch ldy
+    const void* X;   // bf16 [M, K], pitch ldx
+    float* dW;       // fp32 [N, K], pitch ldw; accumulated with atomics (caller zeroes)
+    int M, N, K;
+    int ldy, ldx, ldw;
+};
+int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace svit

@@ -1,0 +1,20 @@
+// tma.h -- host-side CUtensorMap construction (driver entry point resolved at run time,
+// so the shared library has no link-time dependency on libcuda and loads on a CPU-only box).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace svit {
+
+enum class TmapDtype { BF16, F32 };
+
+// 2-D row-major tensor [outer][inner] with a row pitch in bytes, 128-byte swizzled box.
+// box_inner * elem_size must be 128 bytes; box_outer <= 256.
+// Returns 0 on success, a CUresult otherwise.
+int make_tmap_2d(CUtensorMap* out, const void* gptr, TmapDtype dt, uint64_t inner, uint64_t outer,
+                 uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer);
+
+const char* tmap_last_error();
+
+}  // namespace svit
