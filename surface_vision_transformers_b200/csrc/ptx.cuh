@@ -9,7 +9,7 @@ namespace svit {
 
 #ifndef SVIT_SPIN_LIMIT
 // Bounded spins turn a pipeline dead-lock into a trap (an error) instead of a hung GPU.
-#define SVIT_SPIN_LIMIT (1u << 28)
+#define SVIT_SPIN_LIMIT 4000000000LL  /* ~2 s of SM clocks */
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -57,10 +57,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > SVIT_SPIN_LIMIT) {
-            printf("svit: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
+        if (clock64() - t0 > SVIT_SPIN_LIMIT) {
+            printf("svit: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, smem_u32(bar), parity);
             __trap();
         }
