@@ -1,0 +1,594 @@
+// attention.cu -- tcgen05 fused attention forward / backward for sequences of at most 384 tokens.
+// See attention.cuh for what it replaces in the reference.
+#include "attention.cuh"
+
+#include <cuda_bf16.h>
+#include <cstring>
+
+#include "gemm.cuh"  // set_error
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace svit {
+
+constexpr int ATT_MAX_T = 384;
+constexpr int TILE_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
+
+// =================================================================================================
+// forward
+// =================================================================================================
+// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sP 96K | barriers
+constexpr int FWD_SQ = 0;
+constexpr int FWD_SK = FWD_SQ + TILE_BYTES;
+constexpr int FWD_SV = FWD_SK + 3 * TILE_BYTES;
+constexpr int FWD_SP = FWD_SV + 3 * TILE_BYTES;
+constexpr int FWD_BAR = FWD_SP + 6 * TILE_BYTES;
+constexpr int FWD_SMEM = 1024 + FWD_BAR + 128;
+constexpr int FWD_THREADS = 160;
+constexpr int FWD_TMEM_O = 384;  // O accumulator columns [384, 448)
+
+struct AttnFwdArgs {
+    CUtensorMap tmQKV;  // (3*inner, T, B) bf16, box 64 x 128 x 1
+    CUtensorMap tmO;    // (inner, T, B) bf16, box 64 x 128 x 1
+    float* lse;
+    int B, H, T;
+    float scale, scale_log2e;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + FWD_SQ;
+    uint8_t* sK = smem + FWD_SK;
+    uint8_t* sV = smem + FWD_SV;
+    uint8_t* sP = smem + FWD_SP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
+    uint64_t* bar_kv = bars + 0;
+    uint64_t* bar_q = bars + 1;
+    uint64_t* bar_s = bars + 2;
+    uint64_t* bar_p = bars + 3;
+    uint64_t* bar_o = bars + 4;
+    uint64_t* bar_of = bars + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int T = args.T, H = args.H;
+    const int inner = H * 64;
+    const int b = blockIdx.x / H;
+    const int h = blockIdx.x % H;
+    const int tk = (T + 15) & ~15;       // keys padded to the UMMA K step
+    const int nkb = (T + 127) / 128;     // 128-row K/V boxes
+    const int nqb = (T + 127) / 128;     // query blocks
+    const int n1 = tk < 256 ? tk : 256;  // first S chunk (UMMA N <= 256)
+    const int n2 = tk - n1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&args.tmQKV);
+        tma_prefetch_desc(&args.tmO);
+        mbar_init(bar_kv, 1);
+        mbar_init(bar_q, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, 128);
+        mbar_init(bar_o, 1);
+        mbar_init(bar_of, 128);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ============================ control: TMA + MMA issue ============================
+        if (elect_one()) {
+            mbar_expect_tx(bar_kv, nkb * 2 * TILE_BYTES);
+            for (int r = 0; r < nkb; ++r) {
+                tma_load_3d(sK + r * TILE_BYTES, &args.tmQKV, bar_kv, inner + h * 64, r * 128, b);
+                tma_load_3d(sV + r * TILE_BYTES, &args.tmQKV, bar_kv, 2 * inner + h * 64, r * 128, b);
+            }
+            mbar_expect_tx(bar_q, TILE_BYTES);
+            tma_load_3d(sQ, &args.tmQKV, bar_q, h * 64, 0, b);
+            const uint32_t idesc_s1 = umma_idesc_bf16(128, n1, 0, 0);
+            const uint32_t idesc_s2 = umma_idesc_bf16(128, n2 > 0 ? n2 : 16, 0, 0);
+            const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+            mbar_wait(bar_kv, 0);
+            for (int i = 0; i < nqb; ++i) {
+                const uint32_t ph = i & 1;
+                mbar_wait(bar_q, ph);
+                tc_fence_after();
+                // S = Q K^T  (K-major A and B)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, 1024);
+                    umma_ss(tmem_base, ad, umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s1, k != 0);
+                    if (n2 > 0)
+                        umma_ss(tmem_base + n1, ad, umma_smem_desc(k_addr + n1 * 128 + k * 32, 16, 1024), idesc_s2, k != 0);
+                }
+                umma_commit(bar_s);
+                mbar_wait(bar_s, ph);  // S done -> sQ reusable
+                if (i + 1 < nqb) {
+                    mbar_expect_tx(bar_q, TILE_BYTES);
+                    tma_load_3d(sQ, &args.tmQKV, bar_q, h * 64, (i + 1) * 128, b);
+                }
+                mbar_wait(bar_p, ph);  // P written to smem, S columns free
+                if (i > 0) mbar_wait(bar_of, (i - 1) & 1);  // previous O drained from TMEM
+                tc_fence_after();
+                // O = P V  (A = P K-major from smem, B = V MN-major)
+                const int ksteps = tk / 16;
+                for (int s = 0; s < ksteps; ++s) {
+                    const uint64_t ad = umma_smem_desc(p_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024);
+                    const uint64_t bd = umma_smem_desc(v_addr + s * 2048, 8192, 1024);
+                    umma_ss(tmem_base + FWD_TMEM_O, ad, bd, idesc_pv, s != 0);
+                }
+                umma_commit(bar_o);
+            }
+        }
+    } else {
+        // ============================ softmax + epilogue warps ============================
+        const int q = warp;  // TMEM lane quadrant
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const bool leader = threadIdx.x == 0;
+        const float c = args.scale_log2e;
+        for (int i = 0; i < nqb; ++i) {
+            const uint32_t ph = i & 1;
+            mbar_wait(bar_s, ph);
+            tc_fence_after();
+            // ---- pass 1: row maximum over the valid keys ----
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < tk; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
+            }
+            // the previous block's O tile was staged in sP: make sure its TMA store finished reading
+            if (i > 0) {
+                if (leader) tma_store_wait_read<0>();
+                named_bar_sync(1, 128);
+            }
+            // ---- pass 2: p = exp2((s - max) * scale*log2e), row sum, P -> smem (bf16, K-major swizzled) ----
+            const float mc = mx * c;
+            float sum = 0.0f;
+            for (int c0 = 0; c0 < tk; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_wait();
+                float p[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = exp2f(__uint_as_float(r[j]) * c - mc);
+                    p[j] = (c0 + j < T) ? e : 0.0f;
+                }
+                uint8_t* prow = sP + (c0 >> 6) * TILE_BYTES + row * 128;
+                const int cb = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group (0 or 4)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 o;
+                    o.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
+                    o.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
+                    o.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
+                    o.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
+                    // the row sum uses the bf16-rounded probabilities that the PV product will see
+                    sum += bf16_lo(o.x) + bf16_hi(o.x) + bf16_lo(o.y) + bf16_hi(o.y) + bf16_lo(o.z) + bf16_hi(o.z) +
+                           bf16_lo(o.w) + bf16_hi(o.w);
+                    *reinterpret_cast<uint4*>(prow + (((cb + g) ^ (row & 7)) << 4)) = o;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_p);
+            // ---- epilogue: O / sum -> bf16 -> staging (first tile of sP) -> TMA store ----
+            mbar_wait(bar_o, ph);
+            tc_fence_after();
+            const float inv = 1.0f / sum;
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(t_row + FWD_TMEM_O, o0);
+            tmem_ld_32x32(t_row + FWD_TMEM_O + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_of);
+            uint8_t* orow = sP + row * 128;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+                o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+                o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+                o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+                *reinterpret_cast<uint4*>(orow + ((g ^ (row & 7)) << 4)) = o;
+            }
+            const int t = i * 128 + row;
+            if (t < T) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = mx * args.scale + logf(sum);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (leader) {
+                tma_store_3d(&args.tmO, sP, h * 64, i * 128, b);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+// delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   -- one warp per (b,t) row
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                  float* __restrict__ delta, int B, int H, int T) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= B * T) return;
+    const int b = warp_global / T, t = warp_global % T;
+    const size_t base = static_cast<size_t>(warp_global) * H * 64;
+    for (int h = 0; h < H; ++h) {
+        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(out + base + h * 64 + lane * 2);
+        const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(dout + base + h * 64 + lane * 2);
+        float s = __bfloat162float(o2.x) * __bfloat162float(d2.x) + __bfloat162float(o2.y) * __bfloat162float(d2.y);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) delta[(static_cast<size_t>(b) * H + h) * T + t] = s;
+    }
+}
+
+// One kernel, two roles (template DQ):
+//   DQ = false : CTA owns key block j -> accumulates dK_j, dV_j over all query blocks
+//   DQ = true  : CTA owns query block i -> accumulates dQ_i over all key blocks
+// Per step: S = Q K^T, dP = dO V^T (TMEM); threads (one query row each) form P = exp(S*scale - lse) and
+// dS = P * (dP - delta) in bf16 shared memory tiles [query][key]; then the accumulate MMAs read them.
+// smem: sQ | sdO | sK | sV (16K each) | sP 32K | sdS 32K | barriers
+constexpr int BWD_SQ = 0;
+constexpr int BWD_SDO = BWD_SQ + TILE_BYTES;
+constexpr int BWD_SK = BWD_SDO + TILE_BYTES;
+constexpr int BWD_SV = BWD_SK + TILE_BYTES;
+constexpr int BWD_SP = BWD_SV + TILE_BYTES;
+constexpr int BWD_SDS = BWD_SP + 2 * TILE_BYTES;
+constexpr int BWD_BAR = BWD_SDS + 2 * TILE_BYTES;
+constexpr int BWD_SMEM = 1024 + BWD_BAR + 128;
+constexpr int BWD_THREADS = 128;
+// TMEM columns: S [0,128) dP [128,256) acc0 [256,320) acc1 [320,384)
+
+struct AttnBwdArgs {
+    CUtensorMap tmQKV;   // (3*inner, T, B) bf16 box 64x128x1 (loads)
+    CUtensorMap tmDO;    // (inner, T, B) bf16 box 64x128x1
+    CUtensorMap tmDQKV;  // (3*inner, T, B) bf16 box 64x128x1 (stores)
+    const float* lse;
+    const float* delta;
+    int B, H, T;
+    float scale, scale_log2e;
+};
+
+template <bool DQ>
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + BWD_SQ;
+    uint8_t* sdO = smem + BWD_SDO;
+    uint8_t* sK = smem + BWD_SK;
+    uint8_t* sV = smem + BWD_SV;
+    uint8_t* sP = smem + BWD_SP;
+    uint8_t* sdS = smem + BWD_SDS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_BAR);
+    uint64_t* bar_fix = bars + 0;  // resident operands landed
+    uint64_t* bar_ld = bars + 1;   // streamed operands landed
+    uint64_t* bar_s = bars + 2;    // S and dP ready
+    uint64_t* bar_acc = bars + 3;  // accumulate MMAs retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int T = args.T, H = args.H;
+    const int inner = H * 64;
+    const int nblk = (T + 127) / 128;
+    const int fixed = blockIdx.x % nblk;  // key block (DQ=false) or query block (DQ=true)
+    const int bh = blockIdx.x / nblk;
+    const int b = bh / H, h = bh % H;
+    const bool t0 = threadIdx.x == 0;
+
+    if (t0) {
+        tma_prefetch_desc(&args.tmQKV);
+        tma_prefetch_desc(&args.tmDO);
+        tma_prefetch_desc(&args.tmDQKV);
+        mbar_init(bar_fix, 1);
+        mbar_init(bar_ld, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_acc, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int row = warp * 32 + lane;
+
+    const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // S / dP : K-major x K-major
+    const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);     // dK / dV: A = P^T/dS^T (MN-major), B MN-major
+    const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);     // dQ    : A = dS (K-major),      B = K MN-major
+
+    if (t0) {
+        mbar_expect_tx(bar_fix, 2 * TILE_BYTES);
+        if (DQ) {
+            tma_load_3d(sQ, &args.tmQKV, bar_fix, h * 64, fixed * 128, b);
+            tma_load_3d(sdO, &args.tmDO, bar_fix, h * 64, fixed * 128, b);
+        } else {
+            tma_load_3d(sK, &args.tmQKV, bar_fix, inner + h * 64, fixed * 128, b);
+            tma_load_3d(sV, &args.tmQKV, bar_fix, 2 * inner + h * 64, fixed * 128, b);
+        }
+    }
+    mbar_wait(bar_fix, 0);
+
+    float lse_r = 0.0f, delta_r = 0.0f;
+    bool qvalid = false;
+    if (DQ) {
+        const int t = fixed * 128 + row;
+        qvalid = t < T;
+        if (qvalid) {
+            lse_r = args.lse[(static_cast<size_t>(b) * H + h) * T + t];
+            delta_r = args.delta[(static_cast<size_t>(b) * H + h) * T + t];
+        }
+    }
+
+    for (int step = 0; step < nblk; ++step) {
+        const uint32_t ph = step & 1;
+        const int qb = DQ ? fixed : step;
+        const int kb = DQ ? step : fixed;
+        if (t0) {
+            mbar_expect_tx(bar_ld, 2 * TILE_BYTES);
+            if (DQ) {
+                tma_load_3d(sK, &args.tmQKV, bar_ld, inner + h * 64, kb * 128, b);
+                tma_load_3d(sV, &args.tmQKV, bar_ld, 2 * inner + h * 64, kb * 128, b);
+            } else {
+                tma_load_3d(sQ, &args.tmQKV, bar_ld, h * 64, qb * 128, b);
+                tma_load_3d(sdO, &args.tmDO, bar_ld, h * 64, qb * 128, b);
+            }
+        }
+        if (!DQ) {
+            const int t = qb * 128 + row;
+            qvalid = t < T;
+            lse_r = qvalid ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] : 0.0f;
+            delta_r = qvalid ? args.delta[(static_cast<size_t>(b) * H + h) * T + t] : 0.0f;
+        }
+        mbar_wait(bar_ld, ph);
+        if (t0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                umma_ss(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
+                        idesc_s, k != 0);
+                umma_ss(tmem_base + 128, umma_smem_desc(do_addr + k * 32, 16, 1024),
+                        umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
+            }
+            umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, ph);
+        tc_fence_after();
+        // ---- P and dS for this (query block, key block) pair ----
+        const float lse2 = lse_r * 1.4426950408889634f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t s[32], dp[32];
+            tmem_ld_32x32(t_row + c0, s);
+            tmem_ld_32x32(t_row + 128 + c0, dp);
+            tmem_ld_wait();
+            float p[32], ds[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool valid = qvalid && (kb * 128 + c0 + j < T);
+                const float e = exp2f(__uint_as_float(s[j]) * args.scale_log2e - lse2);
+                p[j] = valid ? e : 0.0f;
+                ds[j] = p[j] * (__uint_as_float(dp[j]) - delta_r);
+            }
+            const int tile = c0 >> 6;
+            const int cb = (c0 & 63) >> 3;
+            uint8_t* prow = sP + tile * TILE_BYTES + row * 128;
+            uint8_t* dsrow = sdS + tile * TILE_BYTES + row * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                const int sw = ((cb + g) ^ (row & 7)) << 4;
+                if (!DQ) {
+                    o.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
+                    o.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
+                    o.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
+                    o.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
+                    *reinterpret_cast<uint4*>(prow + sw) = o;
+                }
+                o.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]);
+                o.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
+                o.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]);
+                o.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(dsrow + sw) = o;
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (t0) {
+            tc_fence_after();
+            if (DQ) {
+                // dQ += dS K : A = dS [q][key] K-major, B = K [key][d] MN-major, 8 K-steps of 16 keys
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    umma_ss(tmem_base + 256, umma_smem_desc(ds_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024),
+                            umma_smem_desc(k_addr + s * 2048, 8192, 1024), idesc_dq, (step | s) != 0);
+            } else {
+                // dV += P^T dO ; dK += dS^T Q : A = [q][key] tiles read MN-major (M = key), B = dO / Q MN-major
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    umma_ss(tmem_base + 320, umma_smem_desc(p_addr + s * 2048, TILE_BYTES, 1024),
+                            umma_smem_desc(do_addr + s * 2048, 8192, 1024), idesc_tn, (step | s) != 0);
+                    umma_ss(tmem_base + 256, umma_smem_desc(ds_addr + s * 2048, TILE_BYTES, 1024),
+                            umma_smem_desc(q_addr + s * 2048, 8192, 1024), idesc_tn, (step | s) != 0);
+                }
+            }
+            umma_commit(bar_acc);
+        }
+        mbar_wait(bar_acc, ph);
+        tc_fence_after();
+    }
+
+    // ---- epilogue: accumulators -> bf16 -> staging (sP) -> TMA store into dqkv ----
+    const int nacc = DQ ? 1 : 2;
+    for (int a = 0; a < nacc; ++a) {
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_row + 256 + a * 64, o0);
+        tmem_ld_32x32(t_row + 256 + a * 64 + 32, o1);
+        tmem_ld_wait();
+        const float sc = (a == 0) ? args.scale : 1.0f;  // dQ and dK carry the softmax scale, dV does not
+        uint8_t* orow = sP + a * TILE_BYTES + row * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(src[0]) * sc, __uint_as_float(src[1]) * sc);
+            o.y = pack_bf16(__uint_as_float(src[2]) * sc, __uint_as_float(src[3]) * sc);
+            o.z = pack_bf16(__uint_as_float(src[4]) * sc, __uint_as_float(src[5]) * sc);
+            o.w = pack_bf16(__uint_as_float(src[6]) * sc, __uint_as_float(src[7]) * sc);
+            *reinterpret_cast<uint4*>(orow + ((g ^ (row & 7)) << 4)) = o;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t0) {
+        if (DQ) {
+            tma_store_3d(&args.tmDQKV, sP, h * 64, fixed * 128, b);
+        } else {
+            tma_store_3d(&args.tmDQKV, sP, inner + h * 64, fixed * 128, b);                    // dK
+            tma_store_3d(&args.tmDQKV, sP + TILE_BYTES, 2 * inner + h * 64, fixed * 128, b);   // dV
+        }
+        tma_store_commit();
+        tma_store_wait_all<0>();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+// host
+// =================================================================================================
+static int check_attn_shape(int B, int H, int T) {
+    if (B <= 0 || H <= 0 || T <= 0 || T > ATT_MAX_T) {
+        set_error("attention: unsupported shape B=%d H=%d T=%d (T must be in [1,%d])", B, H, T, ATT_MAX_T);
+        return -1;
+    }
+    return 0;
+}
+
+int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
+    if (check_attn_shape(d.B, d.H, d.T)) return -1;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_fwd) failed: %s", cudaGetErrorString(e));
+            return -10;
+        }
+        configured = true;
+    }
+    const int inner = d.H * 64;
+    AttnFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = 0;
+    rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
+                       (uint64_t)d.T * 3 * inner * 2, 64, 128);
+    rc |= make_tmap_3d(&a.tmO, d.out, TmapDtype::BF16, inner, d.T, d.B, (uint64_t)inner * 2, (uint64_t)d.T * inner * 2, 64,
+                       128);
+    if (rc) {
+        set_error("attn_fwd: tensor map creation failed: %s", tmap_last_error());
+        return -3;
+    }
+    a.lse = d.lse;
+    a.B = d.B;
+    a.H = d.H;
+    a.T = d.T;
+    a.scale = d.scale;
+    a.scale_log2e = d.scale * 1.4426950408889634f;
+    attn_fwd_kernel<<<d.B * d.H, FWD_THREADS, FWD_SMEM, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attn_fwd launch failed: %s", cudaGetErrorString(e));
+        return -11;
+    }
+    return 0;
+}
+
+int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
+    if (check_attn_shape(d.B, d.H, d.T)) return -1;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_bwd) failed");
+            return -10;
+        }
+        configured = true;
+    }
+    const int inner = d.H * 64;
+    {
+        const int rows = d.B * d.T;
+        const int threads = 256;
+        const int blocks = (rows * 32 + threads - 1) / threads;
+        attn_delta_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.out),
+                                                          reinterpret_cast<const __nv_bfloat16*>(d.dout), d.delta, d.B,
+                                                          d.H, d.T);
+    }
+    AttnBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = 0;
+    rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
+                       (uint64_t)d.T * 3 * inner * 2, 64, 128);
+    rc |= make_tmap_3d(&a.tmDO, d.dout, TmapDtype::BF16, inner, d.T, d.B, (uint64_t)inner * 2, (uint64_t)d.T * inner * 2,
+                       64, 128);
+    rc |= make_tmap_3d(&a.tmDQKV, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
+                       (uint64_t)d.T * 3 * inner * 2, 64, 128);
+    if (rc) {
+        set_error("attn_bwd: tensor map creation failed: %s", tmap_last_error());
+        return -3;
+    }
+    a.lse = d.lse;
+    a.delta = d.delta;
+    a.B = d.B;
+    a.H = d.H;
+    a.T = d.T;
+    a.scale = d.scale;
+    a.scale_log2e = d.scale * 1.4426950408889634f;
+    const int nblk = (d.T + 127) / 128;
+    attn_bwd_kernel<false><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
+    attn_bwd_kernel<true><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attn_bwd launch failed: %s", cudaGetErrorString(e));
+        return -11;
+    }
+    return 0;
+}
+
+}  // namespace svit

@@ -15,3 +15,15 @@ int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int 
     return svit::launch_gemm_wgrad(d, num_sms, (cudaStream_t)stream);
 }
 }
+#include "attention.cuh"
+extern "C" {
+int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, float scale, void* stream) {
+    svit::AttnDesc d{qkv, out, lse, B, H, T, scale};
+    return svit::launch_attn_fwd(d, (cudaStream_t)stream);
+}
+int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
+                  int H, int T, float scale, void* stream) {
+    svit::AttnBwdDesc d{qkv, out, dout, lse, delta, dqkv, B, H, T, scale};
+    return svit::launch_attn_bwd(d, (cudaStream_t)stream);
+}
+}

@@ -59,4 +59,32 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, TmapDtype dt, uint64_t inne
     return 0;
 }
 
+int make_tmap_3d(CUtensorMap* out, const void* gptr, TmapDtype dt, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1) {
+    std::call_once(g_once, resolve);
+    if (!g_encode) return -1;
+    const uint32_t esz = dt == TmapDtype::BF16 ? 2 : 4;
+    if (box0 * esz != 128 || box1 == 0 || box1 > 256 || (pitch1_bytes & 15) || (pitch2_bytes & 15) ||
+        (reinterpret_cast<uintptr_t>(gptr) & 15)) {
+        snprintf(g_err, sizeof(g_err), "make_tmap_3d: bad geometry ptr=%p dims=%llu,%llu,%llu pitch=%llu,%llu box=%ux%u",
+                 gptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                 (unsigned long long)pitch1_bytes, (unsigned long long)pitch2_bytes, box0, box1);
+        return -2;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(out, dt == TmapDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                          3, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p dims=%llu,%llu,%llu", (int)r, gptr,
+                 (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+        return (int)r;
+    }
+    return 0;
+}
+
 }  // namespace svit
