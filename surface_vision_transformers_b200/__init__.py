@@ -1,0 +1,13 @@
+"""surface_vision_transformers_b200 -- B200-native (sm_100a) hot path of the Surface Vision Transformer.
+
+Public API mirrors the reference (SD3004/surface-vision-transformers):
+    SiT                         <- models/sit.py::SiT
+    masked_patch_pretraining    <- models/mpp.py::masked_patch_pretraining
+plus the pieces the north star adds around them: FusedAdamW / FusedSGD (optim), DataParallel (ddp),
+gather_patches / index tables (gather).
+"""
+from .sit import SiT, Transformer  # noqa: F401
+from .mpp import masked_patch_pretraining, get_mask_from_prob, prob_mask_like  # noqa: F401
+from .optim import FusedAdamW, FusedSGD  # noqa: F401
+from .ddp import DataParallel  # noqa: F401
+from .gather import gather_patches, load_index_table  # noqa: F401

@@ -1,0 +1,715 @@
+// elementwise.cu -- HBM-bound kernels of the SiT hot path. See elementwise.cuh.
+#include "elementwise.cuh"
+
+#include <cuda_bf16.h>
+
+#include "gemm.cuh"  // set_error
+
+namespace svit {
+
+#define SVIT_CHECK_LAUNCH(name)                                                  \
+    do {                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) {                                                \
+            set_error("%s launch failed: %s", name, cudaGetErrorString(e__));    \
+            return -11;                                                          \
+        }                                                                        \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =================================================================================================
+// a1: patch gather (bit-exact)
+// =================================================================================================
+__global__ void gather_patches_kernel(const float* __restrict__ mesh, const int32_t* __restrict__ table,
+                                      float* __restrict__ out, int SC, int n_mesh, int N, int V) {
+    // grid: (N, SC); each block copies one patch of one (sample, channel) plane
+    const int j = blockIdx.x;
+    const int sc = blockIdx.y;
+    const float* plane = mesh + static_cast<size_t>(sc) * n_mesh;
+    float* dst = out + (static_cast<size_t>(sc) * N + j) * V;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) dst[v] = __ldg(plane + table[static_cast<size_t>(v) * N + j]);
+}
+
+int launch_gather_patches(const float* mesh, const int32_t* table, float* out, int S, int C, int n_mesh, int N, int V,
+                          cudaStream_t st) {
+    if (S <= 0) return 0;
+    dim3 grid(N, S * C);
+    gather_patches_kernel<<<grid, 128, 0, st>>>(mesh, table, out, S * C, n_mesh, N, V);
+    SVIT_CHECK_LAUNCH("gather_patches");
+    return 0;
+}
+
+// =================================================================================================
+// a2/a8: pack patches (+ MPP corruption, + optional fused gather / z-score)
+// =================================================================================================
+__global__ void pack_patches_kernel(const PackDesc d) {
+    const int T = d.N + 1;
+    const int row = blockIdx.x;  // b*T + t
+    const int b = row / T, t = row % T;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d.A) + static_cast<size_t>(row) * d.Kp;
+    const int CV = d.C * d.V;
+    if (t == 0) {
+        for (int k = threadIdx.x; k < d.Kp; k += blockDim.x) dst[k] = __float2bfloat16(0.0f);
+        return;
+    }
+    int n = t - 1;
+    const size_t bn = static_cast<size_t>(b) * d.N + n;
+    const bool replace = d.replace_sel != nullptr && d.replace_sel[bn] != 0;
+    if (!replace && d.swap_sel != nullptr && d.swap_sel[bn] != 0) n = static_cast<int>(d.swap_src[bn]);
+    for (int k = threadIdx.x; k < d.Kp; k += blockDim.x) {
+        float val = 0.0f;
+        if (k < CV) {
+            const int c = k / d.V, v = k - c * d.V;
+            if (replace) {
+                val = d.mask_token[v * d.C + c];
+            } else if (d.table != nullptr) {
+                val = __ldg(d.x + (static_cast<size_t>(b) * d.C + c) * d.n_mesh + d.table[static_cast<size_t>(v) * d.N + n]);
+                if (d.ch_mean != nullptr) val = (val - d.ch_mean[c]) / d.ch_std[c];
+            } else {
+                val = __ldg(d.x + ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v);
+            }
+        }
+        dst[k] = __float2bfloat16(val);
+    }
+}
+
+int launch_pack_patches(const PackDesc& d, cudaStream_t st) {
+    if (d.B <= 0) return 0;
+    if (d.Kp < d.C * d.V || (d.Kp % 8) != 0) {
+        set_error("pack_patches: Kp=%d must be a multiple of 8 and >= C*V=%d", d.Kp, d.C * d.V);
+        return -2;
+    }
+    pack_patches_kernel<<<d.B * (d.N + 1), 256, 0, st>>>(d);
+    SVIT_CHECK_LAUNCH("pack_patches");
+    return 0;
+}
+
+// =================================================================================================
+// LayerNorm forward (one warp per row; row cached in registers, two-pass variance)
+// =================================================================================================
+constexpr int LN_MAX_VEC = 8;  // float4 per lane -> D <= 1024
+
+__global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              __nv_bfloat16* __restrict__ a, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                              int M, int D, float eps) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+        float4 v[LN_MAX_VEC];
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < LN_MAX_VEC; ++k) {
+            const int i = lane + k * 32;
+            if (i < nvec) {
+                v[k] = xr[i];
+                s += v[k].x + v[k].y + v[k].z + v[k].w;
+            }
+        }
+        const float mean = warp_sum(s) / D;
+        float q = 0.0f;
+#pragma unroll
+        for (int k = 0; k < LN_MAX_VEC; ++k) {
+            const int i = lane + k * 32;
+            if (i < nvec) {
+                const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+                q += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / D + eps);
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+        uint2* ar = reinterpret_cast<uint2*>(a + static_cast<size_t>(row) * D);
+#pragma unroll
+        for (int k = 0; k < LN_MAX_VEC; ++k) {
+            const int i = lane + k * 32;
+            if (i < nvec) {
+                const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+                const float4 bb = reinterpret_cast<const float4*>(beta)[i];
+                __nv_bfloat162 lo = __floats2bfloat162_rn((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+                uint2 o;
+                o.x = *reinterpret_cast<uint32_t*>(&lo);
+                o.y = *reinterpret_cast<uint32_t*>(&hi);
+                ar[i] = o;
+            }
+        }
+    }
+}
+
+static int ln_shape_ok(int D) {
+    if (D <= 0 || (D % 4) != 0 || D > LN_MAX_VEC * 128) {
+        set_error("layernorm: D=%d must be a multiple of 4 and <= %d", D, LN_MAX_VEC * 128);
+        return 0;
+    }
+    return 1;
+}
+
+int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd, int M,
+                  int D, float eps, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (!ln_shape_ok(D)) return -2;
+    const int wpb = 8;
+    int blocks = (M + wpb - 1) / wpb;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ln_fwd_kernel<<<blocks, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(a_bf16), mean, rstd, M, D, eps);
+    SVIT_CHECK_LAUNCH("ln_fwd");
+    return 0;
+}
+
+// =================================================================================================
+// LayerNorm backward + residual-gradient add + column reductions
+// =================================================================================================
+__global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ x,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              const float* __restrict__ gamma, const float* g_in, float* g_out,
+                              __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, float* __restrict__ colsum_out, int M, int D) {
+    extern __shared__ float red[];  // [3][D] block-level partial column sums
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.0f;
+    __syncthreads();
+    float4 acc_g[LN_MAX_VEC], acc_b[LN_MAX_VEC], acc_c[LN_MAX_VEC];
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+        acc_g[k] = make_float4(0, 0, 0, 0);
+        acc_b[k] = make_float4(0, 0, 0, 0);
+        acc_c[k] = make_float4(0, 0, 0, 0);
+    }
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+        const float mu = mean[row], rs = rstd[row];
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+        const uint2* dar = reinterpret_cast<const uint2*>(da + static_cast<size_t>(row) * D);
+        float4 xh[LN_MAX_VEC], dy[LN_MAX_VEC];
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < LN_MAX_VEC; ++k) {
+            const int i = lane + k * 32;
+            if (i < nvec) {
+                const float4 xv = xr[i];
+                const uint2 dv = dar[i];
+                const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+                const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+                const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+                const float4 d = make_float4(__bfloat162float(d01.x), __bfloat162float(d01.y), __bfloat162float(d23.x),
+                                             __bfloat162float(d23.y));
+                xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                acc_g[k].x += d.x * xh[k].x; acc_g[k].y += d.y * xh[k].y; acc_g[k].z += d.z * xh[k].z; acc_g[k].w += d.w * xh[k].w;
+                acc_b[k].x += d.x; acc_b[k].y += d.y; acc_b[k].z += d.z; acc_b[k].w += d.w;
+                dy[k] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+                s1 += dy[k].x + dy[k].y + dy[k].z + dy[k].w;
+                s2 += dy[k].x * xh[k].x + dy[k].y * xh[k].y + dy[k].z * xh[k].z + dy[k].w * xh[k].w;
+            }
+        }
+        const float m1 = warp_sum(s1) / D;
+        const float m2 = warp_sum(s2) / D;
+        const float4* gir = reinterpret_cast<const float4*>(g_in + static_cast<size_t>(row) * D);
+        float4* gor = reinterpret_cast<float4*>(g_out + static_cast<size_t>(row) * D);
+        uint2* gbr = reinterpret_cast<uint2*>(g_out_bf16 + static_cast<size_t>(row) * D);
+#pragma unroll
+        for (int k = 0; k < LN_MAX_VEC; ++k) {
+            const int i = lane + k * 32;
+            if (i < nvec) {
+                const float4 gi = gir[i];
+                float4 o;
+                o.x = gi.x + rs * (dy[k].x - m1 - xh[k].x * m2);
+                o.y = gi.y + rs * (dy[k].y - m1 - xh[k].y * m2);
+                o.z = gi.z + rs * (dy[k].z - m1 - xh[k].z * m2);
+                o.w = gi.w + rs * (dy[k].w - m1 - xh[k].w * m2);
+                gor[i] = o;
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 ob;
+                ob.x = *reinterpret_cast<uint32_t*>(&lo);
+                ob.y = *reinterpret_cast<uint32_t*>(&hi);
+                gbr[i] = ob;
+                acc_c[k].x += o.x; acc_c[k].y += o.y; acc_c[k].z += o.z; acc_c[k].w += o.w;
+            }
+        }
+    }
+    // block reduction through shared memory, then one atomic per column per block
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+            const int c = i * 4;
+            atomicAdd(&red[c + 0], acc_g[k].x); atomicAdd(&red[c + 1], acc_g[k].y);
+            atomicAdd(&red[c + 2], acc_g[k].z); atomicAdd(&red[c + 3], acc_g[k].w);
+            atomicAdd(&red[D + c + 0], acc_b[k].x); atomicAdd(&red[D + c + 1], acc_b[k].y);
+            atomicAdd(&red[D + c + 2], acc_b[k].z); atomicAdd(&red[D + c + 3], acc_b[k].w);
+            atomicAdd(&red[2 * D + c + 0], acc_c[k].x); atomicAdd(&red[2 * D + c + 1], acc_c[k].y);
+            atomicAdd(&red[2 * D + c + 2], acc_c[k].z); atomicAdd(&red[2 * D + c + 3], acc_c[k].w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        atomicAdd(&dgamma[i], red[i]);
+        atomicAdd(&dbeta[i], red[D + i]);
+        if (colsum_out != nullptr) atomicAdd(&colsum_out[i], red[2 * D + i]);
+    }
+}
+
+int launch_ln_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta, float* colsum_out,
+                  int M, int D, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (!ln_shape_ok(D)) return -2;
+    const int wpb = 8;
+    int blocks = (M + wpb - 1) / wpb;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    ln_bwd_kernel<<<blocks, wpb * 32, 3 * D * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
+        reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D);
+    SVIT_CHECK_LAUNCH("ln_bwd");
+    return 0;
+}
+
+// =================================================================================================
+// a5: head forward / backward   (one block per sample)
+// =================================================================================================
+__device__ float block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.0f;
+    if (w == 0) t = warp_sum(t);
+    if (threadIdx.x == 0) scratch[0] = t;
+    __syncthreads();
+    return scratch[0];
+}
+
+// pooled[d] into shared memory p[] (D floats); returns (mean, rstd) of the pooled vector
+__device__ void head_pool_stats(const float* x, int T, int D, int pool_mean, float eps, float* p, float* scratch,
+                                float& mu, float& rs) {
+    const float* xb = x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float v;
+        if (pool_mean) {
+            v = 0.0f;
+            for (int t = 0; t < T; ++t) v += xb[static_cast<size_t>(t) * D + d];
+            v /= T;
+        } else {
+            v = xb[d];
+        }
+        p[d] = v;
+    }
+    __syncthreads();
+    float s = 0.0f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s += p[d];
+    mu = block_sum(s, scratch) / D;
+    float q = 0.0f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) q += (p[d] - mu) * (p[d] - mu);
+    rs = rsqrtf(block_sum(q, scratch) / D + eps);
+}
+
+__global__ void head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ out, int T,
+                                int D, int C, int pool_mean, float eps) {
+    extern __shared__ float sm[];
+    float* p = sm;
+    float* scratch = sm + D;
+    const int b = blockIdx.x;
+    float mu, rs;
+    head_pool_stats(x + static_cast<size_t>(b) * T * D, T, D, pool_mean, eps, p, scratch, mu, rs);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) p[d] = (p[d] - mu) * rs * gamma[d] + beta[d];
+    __syncthreads();
+    for (int c = 0; c < C; ++c) {
+        float s = 0.0f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) s += p[d] * W[static_cast<size_t>(c) * D + d];
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) out[static_cast<size_t>(b) * C + c] = s + bias[c];
+    }
+}
+
+__global__ void head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ W, const float* __restrict__ dout, float* __restrict__ g,
+                                __nv_bfloat16* __restrict__ g_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ colsum_out, int T,
+                                int D, int C, int pool_mean, float eps) {
+    extern __shared__ float sm[];
+    float* p = sm;           // pooled -> xhat
+    float* dz = sm + D;      // grad wrt LN output
+    float* scratch = sm + 2 * D;
+    const int b = blockIdx.x;
+    float mu, rs;
+    head_pool_stats(x + static_cast<size_t>(b) * T * D, T, D, pool_mean, eps, p, scratch, mu, rs);
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float xh = (p[d] - mu) * rs;
+        const float z = xh * gamma[d] + beta[d];
+        float dzd = 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const float go = dout[static_cast<size_t>(b) * C + c];
+            dzd += go * W[static_cast<size_t>(c) * D + d];
+            atomicAdd(&dW[static_cast<size_t>(c) * D + d], go * z);
+        }
+        atomicAdd(&dgamma[d], dzd * xh);
+        atomicAdd(&dbeta[d], dzd);
+        const float dy = dzd * gamma[d];
+        p[d] = xh;
+        dz[d] = dy;
+        s1 += dy;
+        s2 += dy * xh;
+    }
+    if (threadIdx.x < C) atomicAdd(&dbias[threadIdx.x], dout[static_cast<size_t>(b) * C + threadIdx.x]);
+    const float m1 = block_sum(s1, scratch) / D;
+    const float m2 = block_sum(s2, scratch) / D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float dp = rs * (dz[d] - m1 - p[d] * m2);  // grad wrt pooled vector
+        dz[d] = dp;
+        if (colsum_out != nullptr) atomicAdd(&colsum_out[d], dp);  // sum over rows of g equals dp for both pool modes
+    }
+    __syncthreads();
+    float* gb = g + static_cast<size_t>(b) * T * D;
+    __nv_bfloat16* gbb = g_bf16 + static_cast<size_t>(b) * T * D;
+    const float inv_t = 1.0f / T;
+    for (size_t i = threadIdx.x; i < static_cast<size_t>(T) * D; i += blockDim.x) {
+        const int t = static_cast<int>(i / D), d = static_cast<int>(i - static_cast<size_t>(t) * D);
+        const float v = pool_mean ? dz[d] * inv_t : (t == 0 ? dz[d] : 0.0f);
+        gb[i] = v;
+        gbb[i] = __float2bfloat16(v);
+    }
+}
+
+int launch_head_fwd(const float* x, const float* gamma, const float* beta, const float* W, const float* bias, float* out,
+                    int B, int T, int D, int C, int pool_mean, float eps, cudaStream_t st) {
+    if (B <= 0) return 0;
+    head_fwd_kernel<<<B, 128, (D + 32) * sizeof(float), st>>>(x, gamma, beta, W, bias, out, T, D, C, pool_mean, eps);
+    SVIT_CHECK_LAUNCH("head_fwd");
+    return 0;
+}
+
+int launch_head_bwd(const float* x, const float* gamma, const float* beta, const float* W, const float* dout, float* g,
+                    void* g_bf16, float* dgamma, float* dbeta, float* dW, float* dbias, float* colsum_out, int B, int T,
+                    int D, int C, int pool_mean, float eps, cudaStream_t st) {
+    if (B <= 0) return 0;
+    if (C > 256) {
+        set_error("head_bwd: num_classes=%d > 256 unsupported", C);
+        return -2;
+    }
+    head_bwd_kernel<<<B, 256, (2 * D + 32) * sizeof(float), st>>>(x, gamma, beta, W, dout, g,
+                                                                  reinterpret_cast<__nv_bfloat16*>(g_bf16), dgamma, dbeta,
+                                                                  dW, dbias, colsum_out, T, D, C, pool_mean, eps);
+    SVIT_CHECK_LAUNCH("head_bwd");
+    return 0;
+}
+
+// =================================================================================================
+// column sums, casts, weight shadows
+// =================================================================================================
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, float* __restrict__ out, int M, int N, int ld,
+                                   int rows_per_block) {
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    for (int c = threadIdx.x * 2; c < N; c += blockDim.x * 2) {
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int r = r0; r < r1; ++r) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(Y + static_cast<size_t>(r) * ld + c);
+            s0 += __bfloat162float(v.x);
+            s1 += __bfloat162float(v.y);
+        }
+        atomicAdd(&out[c], s0);
+        if (c + 1 < N) atomicAdd(&out[c + 1], s1);
+    }
+}
+
+int launch_colsum_bf16(const void* Y, float* out, int M, int N, int ld, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if ((N & 1) || (ld & 1)) {
+        set_error("colsum_bf16: N and ld must be even");
+        return -2;
+    }
+    const int rpb = 128;
+    colsum_bf16_kernel<<<(M + rpb - 1) / rpb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(Y), out, M, N, ld, rpb);
+    SVIT_CHECK_LAUNCH("colsum_bf16");
+    return 0;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __float2bfloat16(src[i]);
+}
+int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    cast_bf16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    SVIT_CHECK_LAUNCH("cast_bf16");
+    return 0;
+}
+
+__global__ void cast_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      __nv_bfloat16* __restrict__ dstT, int rows, int cols, int ld_direct, int ld_t,
+                                      size_t src_stride, size_t dst_stride, size_t dstT_stride) {
+    __shared__ float tile[32][33];
+    const int z = blockIdx.z;
+    src += z * src_stride;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        float v = 0.0f;
+        if (r < rows && c < cols) {
+            v = src[static_cast<size_t>(r) * cols + c];
+            if (dst != nullptr) dst[z * dst_stride + static_cast<size_t>(r) * ld_direct + c] = __float2bfloat16(v);
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (dstT != nullptr) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const int c = c0 + i, r = r0 + threadIdx.x;
+            if (c < cols && r < rows) dstT[z * dstT_stride + static_cast<size_t>(c) * ld_t + r] = __float2bfloat16(tile[threadIdx.x][i]);
+        }
+    }
+}
+
+int launch_cast_transpose(const float* src, void* dst, void* dstT, int rows, int cols, int ld_direct, int ld_t, int count,
+                          size_t src_stride, size_t dst_stride, size_t dstT_stride, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0 || count <= 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, count);
+    dim3 block(32, 8);
+    cast_transpose_kernel<<<grid, block, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                  reinterpret_cast<__nv_bfloat16*>(dstT), rows, cols, ld_direct, ld_t,
+                                                  src_stride, dst_stride, dstT_stride);
+    SVIT_CHECK_LAUNCH("cast_transpose");
+    return 0;
+}
+
+__global__ void prepare_patch_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp, int D, int C, int V,
+                                            int Kp) {
+    const int d = blockIdx.x;
+    const int CV = C * V;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        float v = 0.0f;
+        if (k < CV) {
+            const int c = k / V, vv = k - c * V;
+            v = W[static_cast<size_t>(d) * CV + vv * C + c];
+        }
+        Wp[static_cast<size_t>(d) * Kp + k] = __float2bfloat16(v);
+    }
+}
+int launch_prepare_patch_weight(const float* W, void* Wp, int D, int C, int V, int Kp, cudaStream_t st) {
+    prepare_patch_weight_kernel<<<D, 256, 0, st>>>(W, reinterpret_cast<__nv_bfloat16*>(Wp), D, C, V, Kp);
+    SVIT_CHECK_LAUNCH("prepare_patch_weight");
+    return 0;
+}
+
+__global__ void prepare_rowtab_kernel(const float* __restrict__ pos, const float* __restrict__ cls,
+                                      const float* __restrict__ bias, float* __restrict__ E, int T, int D) {
+    const int t = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x)
+        E[static_cast<size_t>(t) * D + d] = pos[static_cast<size_t>(t) * D + d] + (t == 0 ? cls[d] : bias[d]);
+}
+int launch_prepare_rowtab(const float* pos, const float* cls, const float* bias, float* E, int T, int D, cudaStream_t st) {
+    prepare_rowtab_kernel<<<T, 128, 0, st>>>(pos, cls, bias, E, T, D);
+    SVIT_CHECK_LAUNCH("prepare_rowtab");
+    return 0;
+}
+
+// =================================================================================================
+// patch-embedding backward reductions
+// =================================================================================================
+__global__ void embed_bwd_kernel(const float* __restrict__ g0, float* __restrict__ dpos, float* __restrict__ dcls,
+                                 float* __restrict__ dbias, int B, int T, int D) {
+    const int t = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.0f;
+        for (int b = 0; b < B; ++b) s += g0[(static_cast<size_t>(b) * T + t) * D + d];
+        atomicAdd(&dpos[static_cast<size_t>(t) * D + d], s);
+        if (t == 0) atomicAdd(&dcls[d], s);
+        else atomicAdd(&dbias[d], s);
+    }
+}
+int launch_embed_bwd(const float* g0, float* dpos, float* dcls, float* dbias, int B, int T, int D, cudaStream_t st) {
+    embed_bwd_kernel<<<T, 128, 0, st>>>(g0, dpos, dcls, dbias, B, T, D);
+    SVIT_CHECK_LAUNCH("embed_bwd");
+    return 0;
+}
+
+__global__ void unpermute_patch_wgrad_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int C, int V, int Kp) {
+    const int d = blockIdx.x;
+    const int CV = C * V;
+    for (int k = threadIdx.x; k < CV; k += blockDim.x) {
+        const int c = k / V, vv = k - c * V;
+        dW[static_cast<size_t>(d) * CV + vv * C + c] += dWp[static_cast<size_t>(d) * Kp + k];
+    }
+}
+int launch_unpermute_patch_wgrad(const float* dWp, float* dW, int D, int C, int V, int Kp, cudaStream_t st) {
+    unpermute_patch_wgrad_kernel<<<D, 256, 0, st>>>(dWp, dW, C, V, Kp);
+    SVIT_CHECK_LAUNCH("unpermute_patch_wgrad");
+    return 0;
+}
+
+// =================================================================================================
+// a9: MPP loss
+// =================================================================================================
+__global__ void mpp_loss_fwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ x,
+                                    const uint8_t* __restrict__ mask, float* __restrict__ loss_sum, int C, int N, int V) {
+    __shared__ float scratch[32];
+    const int bn = blockIdx.x;
+    if (mask[bn] == 0) return;
+    const int b = bn / N, n = bn % N;
+    const int T = N + 1;
+    const float* yr = y + (static_cast<size_t>(b) * T + 1 + n) * ldy;
+    float s = 0.0f;
+    for (int k = threadIdx.x; k < C * V; k += blockDim.x) {
+        const int v = k / C, c = k - v * C;
+        const float t = x[((static_cast<size_t>(b) * C + c) * N + n) * V + v];
+        const float dlt = yr[k] - t;
+        s += dlt * dlt;
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, s);
+}
+int launch_mpp_loss_fwd(const float* y, int ldy, const float* x, const uint8_t* mask, float* loss_sum, int B, int C, int N,
+                        int V, cudaStream_t st) {
+    if (B <= 0) return 0;
+    mpp_loss_fwd_kernel<<<B * N, 128, 0, st>>>(y, ldy, x, mask, loss_sum, C, N, V);
+    SVIT_CHECK_LAUNCH("mpp_loss_fwd");
+    return 0;
+}
+
+__global__ void mpp_loss_bwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ x,
+                                    const uint8_t* __restrict__ mask, const float* __restrict__ coef_dev,
+                                    __nv_bfloat16* __restrict__ dy, int lddy, int C, int N, int V) {
+    const int T = N + 1;
+    const int row = blockIdx.x;  // b*T + t
+    const int b = row / T, t = row % T;
+    __nv_bfloat16* dr = dy + static_cast<size_t>(row) * lddy;
+    const bool on = t > 0 && mask[static_cast<size_t>(b) * N + (t - 1)] != 0;
+    const float coef = *coef_dev;
+    const int n = t - 1;
+    const float* yr = y + static_cast<size_t>(row) * ldy;
+    for (int k = threadIdx.x; k < lddy; k += blockDim.x) {
+        float val = 0.0f;
+        if (on && k < C * V) {
+            const int v = k / C, c = k - v * C;
+            val = coef * (yr[k] - x[((static_cast<size_t>(b) * C + c) * N + n) * V + v]);
+        }
+        dr[k] = __float2bfloat16(val);
+    }
+}
+int launch_mpp_loss_bwd(const float* y, int ldy, const float* x, const uint8_t* mask, const float* coef_dev, void* dy,
+                        int lddy, int B, int C, int N, int V, cudaStream_t st) {
+    if (B <= 0) return 0;
+    mpp_loss_bwd_kernel<<<B * (N + 1), 128, 0, st>>>(y, ldy, x, mask, coef_dev, reinterpret_cast<__nv_bfloat16*>(dy), lddy,
+                                                     C, N, V);
+    SVIT_CHECK_LAUNCH("mpp_loss_bwd");
+    return 0;
+}
+
+__global__ void masked_rowsum_kernel(const float* __restrict__ g0, const uint8_t* __restrict__ sel, float* __restrict__ r,
+                                     int B, int T, int D, int rows_per_block) {
+    const int N = T - 1;
+    const int i0 = blockIdx.x * rows_per_block;
+    const int i1 = min(B * N, i0 + rows_per_block);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.0f;
+        for (int i = i0; i < i1; ++i) {
+            if (sel[i]) {
+                const int b = i / N, n = i - b * N;
+                s += g0[(static_cast<size_t>(b) * T + 1 + n) * D + d];
+            }
+        }
+        atomicAdd(&r[d], s);
+    }
+}
+__global__ void mask_token_gemv_kernel(const float* __restrict__ r, const float* __restrict__ W, float* __restrict__ dmt,
+                                       int D, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float s = 0.0f;
+    for (int d = 0; d < D; ++d) s += r[d] * W[static_cast<size_t>(d) * K + k];
+    dmt[k] += s;
+}
+int launch_mask_token_grad(const float* g0, const uint8_t* replace_sel, const float* W, float* scratch_r, float* dmt,
+                           int B, int T, int D, int K, cudaStream_t st) {
+    if (B <= 0) return 0;
+    cudaMemsetAsync(scratch_r, 0, D * sizeof(float), st);
+    const int rpb = 64;
+    masked_rowsum_kernel<<<(B * (T - 1) + rpb - 1) / rpb, 128, 0, st>>>(g0, replace_sel, scratch_r, B, T, D, rpb);
+    mask_token_gemv_kernel<<<(K + 127) / 128, 128, 0, st>>>(scratch_r, W, dmt, D, K);
+    SVIT_CHECK_LAUNCH("mask_token_grad");
+    return 0;
+}
+
+// =================================================================================================
+// a10: optimizers over flat buffers
+// =================================================================================================
+constexpr int ADAM_BLOCK_ELEMS = 4096;
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, const AdamSegment* __restrict__ segs,
+                             const int* __restrict__ block_map, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int decoupled, float grad_scale) {
+    // block_map[2*blockIdx.x] = segment index, [2*blockIdx.x+1] = chunk index inside the segment
+    const int si = block_map[2 * blockIdx.x];
+    const AdamSegment sg = segs[si];
+    if (!sg.active) return;
+    const long long c0 = static_cast<long long>(block_map[2 * blockIdx.x + 1]) * ADAM_BLOCK_ELEMS;
+    const long long c1 = min(sg.numel, c0 + ADAM_BLOCK_ELEMS);
+    const float step_size = lr / sg.bias_corr1;
+    const float inv_sqrt_bc2 = rsqrtf(sg.bias_corr2);
+    for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const long long j = sg.offset + i;
+        float pj = p[j];
+        float gj = g[j] * grad_scale;
+        if (decoupled) pj *= (1.0f - lr * weight_decay);
+        else gj += weight_decay * pj;
+        const float mj = beta1 * m[j] + (1.0f - beta1) * gj;
+        const float vj = beta2 * v[j] + (1.0f - beta2) * gj * gj;
+        m[j] = mj;
+        v[j] = vj;
+        const float denom = sqrtf(vj) * inv_sqrt_bc2 + eps;
+        p[j] = pj - step_size * (mj / denom);
+    }
+}
+
+int launch_adamw(float* p, const float* g, float* m, float* v, const AdamSegment* segs_dev, int nsegs,
+                 const int* block_map_dev, int nblocks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                 int decoupled, float grad_scale, cudaStream_t st) {
+    if (nblocks <= 0 || nsegs <= 0) return 0;
+    adamw_kernel<<<nblocks, 256, 0, st>>>(p, g, m, v, segs_dev, block_map_dev, lr, beta1, beta2, eps, weight_decay,
+                                          decoupled, grad_scale);
+    SVIT_CHECK_LAUNCH("adamw");
+    return 0;
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, long long n,
+                           float lr, float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                           float grad_scale) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gi = g[i] * grad_scale + weight_decay * p[i];
+        if (momentum != 0.0f) {
+            const float b = first_step ? gi : momentum * mom[i] + (1.0f - dampening) * gi;
+            mom[i] = b;
+            gi = nesterov ? gi + momentum * b : b;
+        }
+        p[i] -= lr * gi;
+    }
+}
+int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float dampening,
+               float weight_decay, int nesterov, int first_step, float grad_scale, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    sgd_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(p, g, mom, n, lr, momentum, dampening, weight_decay, nesterov,
+                                                         first_step, grad_scale);
+    SVIT_CHECK_LAUNCH("sgd");
+    return 0;
+}
+
+}  // namespace svit

@@ -1,0 +1,574 @@
+// engine.cu -- C-ABI implementation: orchestrates the sm_100a kernels into SiT / MPP forward and backward.
+// Host-side only bookkeeping lives here (offsets, workspace carving, launch order); see include/svit_b200.h.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "svit_b200.h"
+
+namespace svit {
+const char* last_error();
+}
+using namespace svit;
+
+typedef __nv_bfloat16 bf16;
+
+struct svit_engine {
+    svit_config cfg;
+    int D, depth, H, I, mlp, N, V, C, NC, T, K, Kp, Kd;
+    int num_sms;
+    std::vector<long long> poff, pnum;
+    long long flat_numel;
+    long long layer_stride;  // elements between the same tensor of consecutive layers
+    // shadow offsets in bytes
+    size_t sh_wpe, sh_rowtab, sh_qkv, sh_qkvT, sh_o, sh_oT, sh_w1, sh_w1T, sh_w2, sh_w2T, sh_total;
+    size_t msh_wdec, msh_wdecT, msh_total;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+enum LayerParam { LN1_W = 0, LN1_B, QKV_W, OUT_W, OUT_B, LN2_W, LN2_B, FC1_W, FC1_B, FC2_W, FC2_B };
+enum { P_POS = 0, P_CLS = 1, P_PE_W = 2, P_PE_B = 3, P_LAYER0 = 4 };
+
+static inline int pidx_layer(int l, int which) { return P_LAYER0 + 11 * l + which; }
+static inline int pidx_head(const svit_engine* e, int which) { return P_LAYER0 + 11 * e->depth + which; }
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+struct LayerWs {
+    float *xmid, *xout, *mean1, *rstd1, *mean2, *rstd2, *lse;
+    bf16 *a1, *a2, *qkv, *O, *u, *h;
+};
+struct Ws {
+    int B, M, training, mpp;
+    bf16* Apatch;
+    float* x0;
+    std::vector<LayerWs> L;
+    // backward temporaries
+    float *g, *delta, *dWp, *rvec;
+    bf16 *g16, *du, *da, *dO, *dqkv;
+    // mpp
+    bf16 *xL16, *dy;
+    size_t total;
+};
+
+struct Bump {
+    uint8_t* base;
+    size_t off;
+    template <typename Tp>
+    Tp* take(size_t n) {
+        off = align_up(off, 256);
+        Tp* p = reinterpret_cast<Tp*>(base + off);
+        off += n * sizeof(Tp);
+        return p;
+    }
+};
+
+static void carve(const svit_engine* e, int B, int training, int mpp, int with_embed, void* base, Ws* w) {
+    Bump bp{reinterpret_cast<uint8_t*>(base), 0};
+    const size_t M = static_cast<size_t>(B) * e->T;
+    w->B = B;
+    w->M = static_cast<int>(M);
+    w->training = training;
+    w->mpp = mpp;
+    w->Apatch = with_embed ? bp.take<bf16>(M * e->Kp) : nullptr;
+    w->x0 = with_embed ? bp.take<float>(M * e->D) : nullptr;
+    w->L.resize(e->depth);
+    const size_t BHT = static_cast<size_t>(B) * e->H * e->T;
+    if (training) {
+        for (int l = 0; l < e->depth; ++l) {
+            LayerWs& L = w->L[l];
+            L.xmid = bp.take<float>(M * e->D);
+            L.xout = bp.take<float>(M * e->D);
+            L.mean1 = bp.take<float>(M);
+            L.rstd1 = bp.take<float>(M);
+            L.mean2 = bp.take<float>(M);
+            L.rstd2 = bp.take<float>(M);
+            L.lse = bp.take<float>(BHT);
+            L.a1 = bp.take<bf16>(M * e->D);
+            L.a2 = bp.take<bf16>(M * e->D);
+            L.qkv = bp.take<bf16>(M * 3 * e->I);
+            L.O = bp.take<bf16>(M * e->I);
+            L.u = bp.take<bf16>(M * e->mlp);
+            L.h = bp.take<bf16>(M * e->mlp);
+        }
+        w->g = bp.take<float>(M * e->D);
+        w->g16 = bp.take<bf16>(M * e->D);
+        w->du = bp.take<bf16>(M * e->mlp);
+        w->da = bp.take<bf16>(M * e->D);
+        w->dO = bp.take<bf16>(M * e->I);
+        w->dqkv = bp.take<bf16>(M * 3 * e->I);
+        w->delta = bp.take<float>(BHT);
+        w->dWp = bp.take<float>(static_cast<size_t>(e->D) * e->Kp);
+        w->rvec = bp.take<float>(e->D);
+    } else {
+        // inference: all layers share one set of buffers, the residual stream ping-pongs
+        LayerWs S;
+        S.xmid = bp.take<float>(M * e->D);
+        float* xa = bp.take<float>(M * e->D);
+        float* xb = bp.take<float>(M * e->D);
+        S.mean1 = bp.take<float>(M);
+        S.rstd1 = bp.take<float>(M);
+        S.mean2 = S.mean1;
+        S.rstd2 = S.rstd1;
+        S.lse = bp.take<float>(BHT);
+        S.a1 = bp.take<bf16>(M * e->D);
+        S.a2 = S.a1;
+        S.qkv = bp.take<bf16>(M * 3 * e->I);
+        S.O = bp.take<bf16>(M * e->I);
+        S.h = bp.take<bf16>(M * e->mlp);
+        S.u = nullptr;
+        for (int l = 0; l < e->depth; ++l) {
+            w->L[l] = S;
+            w->L[l].xout = (l & 1) ? xb : xa;
+        }
+        w->g = nullptr;
+        w->g16 = w->du = w->da = w->dO = w->dqkv = nullptr;
+        w->delta = w->dWp = w->rvec = nullptr;
+    }
+    if (mpp) {
+        w->xL16 = bp.take<bf16>(M * e->D);
+        w->dy = training ? bp.take<bf16>(M * e->Kd) : nullptr;
+    } else {
+        w->xL16 = w->dy = nullptr;
+    }
+    w->total = align_up(bp.off, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+#define RET_IF(x)            \
+    do {                     \
+        int rc__ = (x);      \
+        if (rc__) return rc__; \
+    } while (0)
+
+static int gemm(const svit_engine* e, cudaStream_t st, const void* A, int lda, const void* Bm, int ldb, void* out, int ldo,
+                int M, int N, int K, int mode, int out_f32, const float* bias = nullptr, const void* aux = nullptr,
+                void* out2 = nullptr, const float* rowtab = nullptr, int period = 1) {
+    GemmTnDesc d{A, Bm, out, out2, aux, bias, rowtab, period, M, N, K, lda, ldb, ldo, mode, out_f32};
+    return launch_gemm_tn(d, e->num_sms, st);
+}
+static int wgrad(const svit_engine* e, cudaStream_t st, const void* dY, int ldy, const void* X, int ldx, float* dW, int ldw,
+                 int M, int N, int K) {
+    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw};
+    return launch_gemm_wgrad(d, e->num_sms, st);
+}
+
+static inline const bf16* shp(const void* shadow, size_t off) {
+    return reinterpret_cast<const bf16*>(reinterpret_cast<const uint8_t*>(shadow) + off);
+}
+
+static int check_ws(const svit_engine* e, int B, int training, int mpp, int with_embed, void* ws_ptr, size_t ws_bytes,
+                    Ws* w) {
+    if (B <= 0) {
+        set_error("batch must be >= 1 (got %d)", B);
+        return -1;
+    }
+    if (ws_ptr == nullptr || (reinterpret_cast<uintptr_t>(ws_ptr) & 255)) {
+        set_error("workspace must be a 256-byte aligned device pointer");
+        return -1;
+    }
+    carve(e, B, training, mpp, with_embed, ws_ptr, w);
+    if (ws_bytes != 0 && w->total > ws_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", w->total, ws_bytes);
+        return -1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder forward / backward over the workspace
+// ---------------------------------------------------------------------------------------------
+static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws& w, const float* x_in, cudaStream_t st,
+                       const float** x_final) {
+    const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
+    const float scale = 0.125f;  // dim_head ** -0.5 with dim_head = 64
+    const float* xin = x_in;
+    for (int l = 0; l < e->depth; ++l) {
+        LayerWs& L = w.L[l];
+        const float* lp = P;
+        auto pp = [&](int which) { return lp + e->poff[pidx_layer(l, which)]; };
+        RET_IF(launch_ln_fwd(xin, pp(LN1_W), pp(LN1_B), L.a1, L.mean1, L.rstd1, M, D, 1e-5f, st));
+        RET_IF(gemm(e, st, L.a1, D, shp(sh, e->sh_qkv) + static_cast<size_t>(l) * 3 * I * D, D, L.qkv, 3 * I, M, 3 * I, D,
+                    EPI_STORE, 0));
+        AttnDesc ad{L.qkv, L.O, L.lse, w.B, e->H, e->T, scale};
+        RET_IF(launch_attn_fwd(ad, st));
+        RET_IF(gemm(e, st, L.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, L.xmid, D, M, D, I, EPI_RESID, 1,
+                    pp(OUT_B), xin));
+        RET_IF(launch_ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
+        if (w.training) {
+            RET_IF(gemm(e, st, L.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, L.u, mlp, M, mlp, D,
+                        EPI_GELU, 0, pp(FC1_B), nullptr, L.h));
+        } else {
+            RET_IF(gemm(e, st, L.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, L.h, mlp, M, mlp, D,
+                        EPI_GELU_ONLY, 0, pp(FC1_B)));
+        }
+        RET_IF(gemm(e, st, L.h, mlp, shp(sh, e->sh_w2) + static_cast<size_t>(l) * D * mlp, mlp, L.xout, D, M, D, mlp,
+                    EPI_RESID, 1, pp(FC2_B), L.xmid));
+        xin = L.xout;
+    }
+    *x_final = xin;
+    return 0;
+}
+
+// On entry w.g / w.g16 hold dL/dx_final (fp32 + bf16) and grads[fc2_b of last layer] already holds colsum(g).
+// On exit w.g / w.g16 hold dL/dx_in.
+static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws& w, const float* x_in, float* G,
+                       cudaStream_t st, svit_progress_fn progress = nullptr, void* user = nullptr) {
+    const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
+    const float scale = 0.125f;
+    for (int l = e->depth - 1; l >= 0; --l) {
+        LayerWs& L = w.L[l];
+        const float* xin = (l == 0) ? x_in : w.L[l - 1].xout;
+        auto pp = [&](int which) { return P + e->poff[pidx_layer(l, which)]; };
+        auto gp = [&](int which) { return G + e->poff[pidx_layer(l, which)]; };
+        // ---- FeedForward ----
+        // du = (g W2) * gelu'(u)
+        RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_DGELU,
+                    0, nullptr, L.u));
+        RET_IF(wgrad(e, st, w.g16, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp));
+        RET_IF(launch_colsum_bf16(w.du, gp(FC1_B), M, mlp, mlp, st));
+        // da2 = du W1
+        RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, M, D, mlp,
+                    EPI_STORE, 0));
+        RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D));
+        // g_mid = g + LN2'(da2) ; colsum(g_mid) = d out_b
+        RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, w.g16, gp(LN2_W), gp(LN2_B), gp(OUT_B), M, D,
+                             st));
+        // ---- Attention ----
+        RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
+        RET_IF(wgrad(e, st, w.g16, D, L.O, I, gp(OUT_W), I, M, D, I));
+        AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, w.delta, w.dqkv, w.B, e->H, e->T, scale};
+        RET_IF(launch_attn_bwd(bd, st));
+        RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
+                    EPI_STORE, 0));
+        RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+        // g_in = g_mid + LN1'(da1) ; colsum(g_in) = d fc2_b of the previous layer
+        float* cs = (l > 0) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
+        RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs, M, D, st));
+        // every gradient of layer l is final now (d fc2_b[l] was added by the layer above / the head)
+        if (progress != nullptr) progress(l, user);
+    }
+    return 0;
+}
+
+static int embed_fwd(const svit_engine* e, const void* sh, Ws& w, const PackDesc& pd, cudaStream_t st) {
+    RET_IF(launch_pack_patches(pd, st));
+    return gemm(e, st, w.Apatch, e->Kp, shp(sh, e->sh_wpe), e->Kp, w.x0, e->D, w.M, e->D, e->Kp, EPI_STORE, 1, nullptr,
+                nullptr, nullptr, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(sh) + e->sh_rowtab),
+                e->T);
+}
+
+// g / g16 hold dL/dx0
+static int embed_bwd(const svit_engine* e, Ws& w, float* G, cudaStream_t st) {
+    RET_IF(launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], w.B, e->T, e->D, st));
+    cudaMemsetAsync(w.dWp, 0, static_cast<size_t>(e->D) * e->Kp * sizeof(float), st);
+    RET_IF(wgrad(e, st, w.g16, e->D, w.Apatch, e->Kp, w.dWp, e->Kp, w.M, e->D, e->Kp));
+    return launch_unpermute_patch_wgrad(w.dWp, G + e->poff[P_PE_W], e->D, e->C, e->V, e->Kp, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* svit_last_error(void) { return svit::last_error(); }
+int svit_version(void) { return 100; }
+
+svit_engine* svit_create(const svit_config* cfg) {
+    if (cfg == nullptr) {
+        set_error("svit_create: null config");
+        return nullptr;
+    }
+    if (cfg->dim_head != 64) {
+        set_error("svit_create: dim_head must be 64 (got %d)", cfg->dim_head);
+        return nullptr;
+    }
+    if (cfg->dim <= 0 || cfg->dim % 8 != 0 || cfg->dim > 1024 || cfg->depth <= 0 || cfg->heads <= 0 || cfg->mlp_dim <= 0 ||
+        cfg->mlp_dim % 8 != 0 || cfg->num_patches <= 0 || cfg->num_vertices <= 0 || cfg->num_channels <= 0 ||
+        cfg->num_classes <= 0) {
+        set_error("svit_create: unsupported configuration (dim %% 8, mlp_dim %% 8, dim <= 1024 required)");
+        return nullptr;
+    }
+    if (cfg->num_patches + 1 > 384) {
+        set_error("svit_create: sequence length %d > 384 unsupported by the fused attention kernel", cfg->num_patches + 1);
+        return nullptr;
+    }
+    if ((cfg->num_channels * cfg->num_vertices) % 4 != 0) {
+        set_error("svit_create: num_channels*num_vertices must be a multiple of 4");
+        return nullptr;
+    }
+    svit_engine* e = new svit_engine();
+    e->cfg = *cfg;
+    e->D = cfg->dim;
+    e->depth = cfg->depth;
+    e->H = cfg->heads;
+    e->I = cfg->heads * 64;
+    e->mlp = cfg->mlp_dim;
+    e->N = cfg->num_patches;
+    e->V = cfg->num_vertices;
+    e->C = cfg->num_channels;
+    e->NC = cfg->num_classes;
+    e->T = e->N + 1;
+    e->K = e->C * e->V;
+    e->Kp = static_cast<int>(align_up(e->K, 64));
+    e->Kd = static_cast<int>(align_up(e->K, 8));
+    e->num_sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
+    } else {
+        cudaGetLastError();
+    }
+    // parameter table
+    const long long D = e->D, I = e->I, mlp = e->mlp;
+    std::vector<long long> sizes;
+    sizes.push_back(static_cast<long long>(e->T) * D);
+    sizes.push_back(D);
+    sizes.push_back(D * e->K);
+    sizes.push_back(D);
+    for (int l = 0; l < e->depth; ++l) {
+        const long long ls[11] = {D, D, 3 * I * D, D * I, D, D, D, mlp * D, mlp, D * mlp, D};
+        for (int i = 0; i < 11; ++i) sizes.push_back(ls[i]);
+    }
+    sizes.push_back(D);
+    sizes.push_back(D);
+    sizes.push_back(static_cast<long long>(e->NC) * D);
+    sizes.push_back(e->NC);
+    long long off = 0;
+    for (size_t i = 0; i < sizes.size(); ++i) {
+        e->poff.push_back(off);
+        e->pnum.push_back(sizes[i]);
+        off += static_cast<long long>(align_up(static_cast<size_t>(sizes[i]), 64));
+    }
+    e->flat_numel = off;
+    e->layer_stride = e->depth > 1 ? e->poff[pidx_layer(1, 0)] - e->poff[pidx_layer(0, 0)] : 0;
+    // shadow layout
+    size_t so = 0;
+    auto take = [&](size_t bytes) {
+        so = align_up(so, 256);
+        size_t r = so;
+        so += bytes;
+        return r;
+    };
+    e->sh_wpe = take(static_cast<size_t>(D) * e->Kp * 2);
+    e->sh_rowtab = take(static_cast<size_t>(e->T) * D * 4);
+    const size_t dl = e->depth;
+    e->sh_qkv = take(dl * 3 * I * D * 2);
+    e->sh_qkvT = take(dl * 3 * I * D * 2);
+    e->sh_o = take(dl * D * I * 2);
+    e->sh_oT = take(dl * D * I * 2);
+    e->sh_w1 = take(dl * mlp * D * 2);
+    e->sh_w1T = take(dl * mlp * D * 2);
+    e->sh_w2 = take(dl * mlp * D * 2);
+    e->sh_w2T = take(dl * mlp * D * 2);
+    e->sh_total = align_up(so, 256);
+    e->msh_wdec = 0;
+    e->msh_wdecT = align_up(static_cast<size_t>(e->K) * D * 2, 256);
+    e->msh_total = e->msh_wdecT + align_up(static_cast<size_t>(D) * e->Kd * 2, 256);
+    return e;
+}
+
+void svit_destroy(svit_engine* e) { delete e; }
+int svit_num_params(const svit_engine* e) { return static_cast<int>(e->poff.size()); }
+long long svit_param_offset(const svit_engine* e, int i) { return (i >= 0 && i < (int)e->poff.size()) ? e->poff[i] : -1; }
+long long svit_param_numel(const svit_engine* e, int i) { return (i >= 0 && i < (int)e->pnum.size()) ? e->pnum[i] : -1; }
+long long svit_flat_numel(const svit_engine* e) { return e->flat_numel; }
+size_t svit_shadow_bytes(const svit_engine* e) { return e->sh_total; }
+size_t svit_mpp_shadow_bytes(const svit_engine* e) { return e->msh_total; }
+size_t svit_workspace_bytes(const svit_engine* e, int batch, int training, int mpp) {
+    if (batch <= 0) return 0;
+    Ws w;
+    carve(e, batch, training, mpp, 1, nullptr, &w);
+    return w.total;
+}
+
+int svit_prepare_weights(svit_engine* e, const float* P, void* shadow, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* sh = reinterpret_cast<uint8_t*>(shadow);
+    const int D = e->D, I = e->I, mlp = e->mlp, dl = e->depth;
+    const size_t ls = static_cast<size_t>(e->layer_stride);
+    RET_IF(launch_prepare_patch_weight(P + e->poff[P_PE_W], sh + e->sh_wpe, D, e->C, e->V, e->Kp, st));
+    RET_IF(launch_prepare_rowtab(P + e->poff[P_POS], P + e->poff[P_CLS], P + e->poff[P_PE_B],
+                                 reinterpret_cast<float*>(sh + e->sh_rowtab), e->T, D, st));
+    RET_IF(launch_cast_transpose(P + e->poff[pidx_layer(0, QKV_W)], sh + e->sh_qkv, sh + e->sh_qkvT, 3 * I, D, D, 3 * I, dl, ls,
+                                 static_cast<size_t>(3) * I * D, static_cast<size_t>(3) * I * D, st));
+    RET_IF(launch_cast_transpose(P + e->poff[pidx_layer(0, OUT_W)], sh + e->sh_o, sh + e->sh_oT, D, I, I, D, dl, ls,
+                                 static_cast<size_t>(D) * I, static_cast<size_t>(D) * I, st));
+    RET_IF(launch_cast_transpose(P + e->poff[pidx_layer(0, FC1_W)], sh + e->sh_w1, sh + e->sh_w1T, mlp, D, D, mlp, dl, ls,
+                                 static_cast<size_t>(mlp) * D, static_cast<size_t>(mlp) * D, st));
+    RET_IF(launch_cast_transpose(P + e->poff[pidx_layer(0, FC2_W)], sh + e->sh_w2, sh + e->sh_w2T, D, mlp, mlp, D, dl, ls,
+                                 static_cast<size_t>(mlp) * D, static_cast<size_t>(mlp) * D, st));
+    return 0;
+}
+
+int svit_mpp_prepare_weights(svit_engine* e, const float* Wdec, void* mpp_shadow, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* sh = reinterpret_cast<uint8_t*>(mpp_shadow);
+    // Wdec (K, D): direct [K, D] pitch D; transposed [D, K] pitch Kd
+    return launch_cast_transpose(Wdec, sh + e->msh_wdec, sh + e->msh_wdecT, e->K, e->D, e->D, e->Kd, 1, 0, 0, 0, st);
+}
+
+int svit_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, size_t ws_bytes, const float* input, int B,
+                 const int32_t* table, int n_mesh, const float* ch_mean, const float* ch_std, float* out, int training,
+                 void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws w;
+    RET_IF(check_ws(e, B, training, 0, 1, ws_ptr, ws_bytes, &w));
+    PackDesc pd{input, w.Apatch, B, e->C, e->N, e->V, e->Kp, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
+    RET_IF(embed_fwd(e, sh, w, pd, st));
+    const float* xf = nullptr;
+    RET_IF(encoder_fwd(e, P, sh, w, w.x0, st, &xf));
+    return launch_head_fwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)],
+                           P + e->poff[pidx_head(e, 3)], out, B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st);
+}
+
+int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, int B, const float* dout, float* G,
+                  svit_progress_fn progress, void* user, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws w;
+    RET_IF(check_ws(e, B, 1, 0, 1, ws_ptr, 0, &w));
+    const float* xf = w.L[e->depth - 1].xout;
+    RET_IF(launch_head_bwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)], dout,
+                           w.g, w.g16, G + e->poff[pidx_head(e, 0)], G + e->poff[pidx_head(e, 1)],
+                           G + e->poff[pidx_head(e, 2)], G + e->poff[pidx_head(e, 3)],
+                           G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st));
+    if (progress != nullptr) progress(e->depth, user);
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user));
+    RET_IF(embed_bwd(e, w, G, st));
+    if (progress != nullptr) progress(-1, user);
+    return 0;
+}
+
+int svit_encoder_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, size_t ws_bytes, const float* x, int B,
+                         float* y, int training, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws w;
+    RET_IF(check_ws(e, B, training, 0, 1, ws_ptr, ws_bytes, &w));
+    const float* xf = nullptr;
+    RET_IF(encoder_fwd(e, P, sh, w, x, st, &xf));
+    cudaError_t ce = cudaMemcpyAsync(y, xf, static_cast<size_t>(w.M) * e->D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) {
+        set_error("encoder_forward: copy failed: %s", cudaGetErrorString(ce));
+        return -12;
+    }
+    return 0;
+}
+
+int svit_encoder_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, int B, const float* x,
+                            const float* dy, float* dx, float* G, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws w;
+    RET_IF(check_ws(e, B, 1, 0, 1, ws_ptr, 0, &w));
+    const size_t n = static_cast<size_t>(w.M) * e->D;
+    cudaMemcpyAsync(w.g, dy, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    RET_IF(launch_cast_bf16(dy, w.g16, n, st));
+    RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], w.M, e->D, e->D, st));
+    RET_IF(encoder_bwd(e, P, sh, w, x, G, st));
+    if (dx != nullptr) cudaMemcpyAsync(dx, w.g, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return 0;
+}
+
+int svit_mpp_forward(svit_engine* e, const float* P, const void* sh, const void* msh, const float* bdec,
+                     const float* mask_token, void* ws_ptr, size_t ws_bytes, const float* input, int B, const uint8_t* mask,
+                     const uint8_t* swap_sel, const int64_t* swap_src, const uint8_t* replace_sel, float* loss_sum,
+                     float* batch_out, int training, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws w;
+    RET_IF(check_ws(e, B, training, 1, 1, ws_ptr, ws_bytes, &w));
+    PackDesc pd{input, w.Apatch, B, e->C, e->N, e->V, e->Kp, swap_sel, swap_src, replace_sel, mask_token, nullptr, 0, nullptr, nullptr};
+    RET_IF(embed_fwd(e, sh, w, pd, st));
+    const float* xf = nullptr;
+    RET_IF(encoder_fwd(e, P, sh, w, w.x0, st, &xf));
+    RET_IF(launch_cast_bf16(xf, w.xL16, static_cast<size_t>(w.M) * e->D, st));
+    // decoder: batch_out[B*T, K] = xL Wdec^T + b
+    RET_IF(gemm(e, st, w.xL16, e->D, shp(msh, e->msh_wdec), e->D, batch_out, e->K, w.M, e->K, e->D, EPI_STORE, 1, bdec));
+    return launch_mpp_loss_fwd(batch_out, e->K, input, mask, loss_sum, B, e->C, e->N, e->V, st);
+}
+
+int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void* msh, void* ws_ptr, int B,
+                        const float* input, const float* batch_out, const uint8_t* mask, const uint8_t* replace_sel,
+                        const float* coef, float* G, float* MG, svit_progress_fn progress, void* user, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws w;
+    RET_IF(check_ws(e, B, 1, 1, 1, ws_ptr, 0, &w));
+    const int M = w.M, D = e->D, K = e->K, Kd = e->Kd;
+    float* gWdec = MG;
+    float* gbdec = MG + static_cast<size_t>(K) * D;
+    float* gmt = gbdec + K;
+    RET_IF(launch_mpp_loss_bwd(batch_out, K, input, mask, coef, w.dy, Kd, B, e->C, e->N, e->V, st));
+    // decoder grads
+    RET_IF(wgrad(e, st, w.dy, Kd, w.xL16, D, gWdec, D, M, K, D));
+    RET_IF(launch_colsum_bf16(w.dy, gbdec, M, K, Kd, st));
+    // g = dy Wdec   (A = dy [M, K] pitch Kd, B = WdecT [D, K] pitch Kd)
+    RET_IF(gemm(e, st, w.dy, Kd, shp(msh, e->msh_wdecT), Kd, w.g, D, M, D, K, EPI_STORE, 1));
+    RET_IF(launch_cast_bf16(w.g, w.g16, static_cast<size_t>(M) * D, st));
+    RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], M, D, D, st));
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user));
+    RET_IF(embed_bwd(e, w, G, st));
+    if (progress != nullptr) progress(-1, user);
+    if (replace_sel != nullptr)
+        RET_IF(launch_mask_token_grad(w.g, replace_sel, P + e->poff[P_PE_W], w.rvec, gmt, B, e->T, D, K, st));
+    return 0;
+}
+
+int svit_gather_patches(const float* mesh, const int32_t* table, float* out, int S, int C, int n_mesh, int N, int V,
+                        void* stream) {
+    return launch_gather_patches(mesh, table, out, S, C, n_mesh, N, V, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int svit_adamw_step(float* p, const float* g, float* m, float* v, const svit_adam_segment* segs_dev, int nsegs,
+                    const int* block_map_dev, int nblocks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int decoupled, float grad_scale, void* stream) {
+    static_assert(sizeof(svit_adam_segment) == sizeof(AdamSegment), "segment layout mismatch");
+    return launch_adamw(p, g, m, v, reinterpret_cast<const AdamSegment*>(segs_dev), nsegs, block_map_dev, nblocks, lr, beta1,
+                        beta2, eps, weight_decay, decoupled, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float dampening,
+                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream) {
+    return launch_sgd(p, g, mom, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void* aux, const float* bias, const float* rowtab,
+                 int rowtab_period, int M, int N, int K, int lda, int ldb, int ldo, int mode, int out_f32, int num_sms,
+                 void* stream) {
+    GemmTnDesc d{A, B, out, out2, aux, bias, rowtab, rowtab_period, M, N, K, lda, ldb, ldo, mode, out_f32};
+    return launch_gemm_tn(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int K, int ldy, int ldx, int ldw, int num_sms,
+                    void* stream) {
+    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw};
+    return launch_gemm_wgrad(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, float scale, void* stream) {
+    AttnDesc d{qkv, out, lse, B, H, T, scale};
+    return launch_attn_fwd(d, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int H,
+                  int T, float scale, void* stream) {
+    AttnBwdDesc d{qkv, out, dout, lse, delta, dqkv, B, H, T, scale};
+    return launch_attn_bwd(d, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd, int M,
+                       int D, float eps, void* stream) {
+    return launch_ln_fwd(x, gamma, beta, a_bf16, mean, rstd, M, D, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_layernorm_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta, float* colsum_out,
+                       int M, int D, void* stream) {
+    return launch_ln_bwd(da_bf16, x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma, dbeta, colsum_out, M, D,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -279,6 +279,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     if (lane == 0) mbar_arrive(&aempty_bar[s]);
                     ++ait;
                 }
+                if (MODE == EPI_GELU_ONLY) {
+#pragma unroll
+                    for (int j = 0; j < UC; ++j) v[j] = gelu_f(v[j]);
+                }
                 // ---- stage the unit in shared memory (128B-swizzled rows) and TMA-store it ----
                 const int slot = oit % OUT_SLOTS;
                 uint8_t* obuf = sEpi + (FIRST_OUT_BUF + slot * OUTS_PER_UNIT) * EPI_BUF_BYTES;
@@ -543,6 +547,7 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
         if (d.mode == EPI_GELU) return launch_tn_inst<__nv_bfloat16, EPI_GELU, BN>(a, num_sms, stream);
         if (d.mode == EPI_RESID) return launch_tn_inst<__nv_bfloat16, EPI_RESID, BN>(a, num_sms, stream);
         if (d.mode == EPI_DGELU) return launch_tn_inst<__nv_bfloat16, EPI_DGELU, BN>(a, num_sms, stream);
+        if (d.mode == EPI_GELU_ONLY) return launch_tn_inst<__nv_bfloat16, EPI_GELU_ONLY, BN>(a, num_sms, stream);
     }
     set_error("gemm_tn: unsupported mode %d for out_f32=%d", d.mode, d.out_f32);
     return -4;

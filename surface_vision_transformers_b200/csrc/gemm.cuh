@@ -17,6 +17,7 @@ enum EpiMode : int {
     EPI_GELU = 1,   // out = acc + bias (pre-activation); out2 = gelu(out)      (both bf16)
     EPI_RESID = 2,  // out = acc + bias + aux                                    (aux/out same dtype)
     EPI_DGELU = 3,  // out = acc * gelu'(aux)                                    (aux/out bf16)
+    EPI_GELU_ONLY = 4,  // out = gelu(acc + bias)   (inference: pre-activation not kept)
 };
 
 struct GemmTnDesc {

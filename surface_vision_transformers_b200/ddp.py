@@ -1,0 +1,74 @@
+"""Batch-sharded data parallelism for the fused SiT path: one process per GPU, replicated weights,
+ONE exchange step per iteration -- a sum all-reduce of the flat gradient buffer, issued range by range while the
+backward kernels are still being enqueued (NCCL runs on its own stream, so communication overlaps the remaining
+backward compute), averaged by 1/world_size.
+
+The reference has no distributed code (single ``cuda:{gpu}``, tools/train.py:72); this is the one strategy the
+north star adds.  Works with any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests of the bucketing
+logic, which use plain tensors instead of the engine).
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ["DataParallel", "FlatGradReducer"]
+
+
+class FlatGradReducer:
+    """All-reduces ranges of a flat gradient tensor asynchronously and finalises them (wait + average)."""
+
+    def __init__(self, process_group=None, average=True):
+        self.pg = process_group
+        self.average = average
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.pending = []
+
+    def reduce_range(self, G, start, numel):
+        if self.world == 1 or numel == 0:
+            return
+        seg = G[start:start + numel]
+        work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self.pending.append((work, seg))
+
+    def finish(self):
+        for work, seg in self.pending:
+            work.wait()
+            if self.average:
+                seg.mul_(1.0 / self.world)
+        self.pending = []
+
+
+class DataParallel(torch.nn.Module):
+    """Wraps a B200 ``SiT`` or ``masked_patch_pretraining``: forwards calls unchanged and installs the gradient
+    hooks that overlap the flat-buffer all-reduce with backward.  ``broadcast_parameters`` syncs the replicas once."""
+
+    def __init__(self, module, process_group=None, broadcast_parameters=True):
+        super().__init__()
+        self.module = module
+        self.reducer = FlatGradReducer(process_group)
+        sit = getattr(module, "transformer", None)
+        self._sit = module if hasattr(module, "stage_segment") else sit
+        if self._sit is None or not hasattr(self._sit, "stage_segment"):
+            raise TypeError("DataParallel wraps a B200 SiT or masked_patch_pretraining")
+        self._sit._grad_hook = self._on_stage
+        if self._sit is not module:
+            module._grad_hook = self._on_small_buffer
+        if broadcast_parameters and self.reducer.world > 1:
+            dist.broadcast(self._sit._flat, src=0, group=process_group)
+            self._sit.mark_weights_dirty()
+            if self._sit is not module:
+                dist.broadcast(module._flat, src=0, group=process_group)
+                module.mark_weights_dirty()
+
+    def _on_stage(self, sit, stage, G):
+        if stage is None:
+            self.reducer.finish()
+            return
+        start, numel = sit.stage_segment(stage)
+        self.reducer.reduce_range(G, start, numel)
+
+    def _on_small_buffer(self, module, MG):
+        self.reducer.reduce_range(MG, 0, MG.numel())
+        self.reducer.finish()
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)

@@ -1,0 +1,337 @@
+"""Drop-in ``SiT`` -- same constructor, attributes, ``forward`` and ``state_dict`` as the reference's
+``models/sit.py::SiT`` (/root/reference/models/sit.py:25-82), with forward and backward executed by the
+hand-written sm_100a kernels behind the C ABI in ``include/svit_b200.h``.
+
+Host code is plumbing only: parameters live in ONE flat fp32 buffer (views keep the reference's names and
+shapes, so checkpoints round-trip), activations live in a per-call workspace, and the whole forward (or
+backward) is a single C call on the current CUDA stream.  There is no CPU / eager fallback: tensors that are
+not on a CUDA device raise.
+"""
+import ctypes
+import weakref
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import SvitConfig, check, ptr, vp
+
+__all__ = ["SiT", "Transformer"]
+
+
+class Rearrange(nn.Module):
+    """'b c n v -> b n (v c)' (models/sit.py:49); parameter-free placeholder at index 0 of to_patch_embedding."""
+
+    def forward(self, x):
+        b, c, n, v = x.shape
+        return x.permute(0, 2, 3, 1).reshape(b, n, v * c)
+
+
+class _Holder(nn.Module):
+    """Parameter container mirroring a vit_pytorch sub-module; the arithmetic runs in the fused engine."""
+
+    def forward(self, *a, **k):
+        raise RuntimeError("this sub-module only holds parameters; call SiT(...) or SiT.transformer(x) instead")
+
+
+class Attention(_Holder):
+    def __init__(self, dim, heads, dim_head, dropout):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+
+
+class FeedForward(_Holder):
+    def __init__(self, dim, hidden_dim, dropout):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+
+class PreNorm(_Holder):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class Transformer(nn.Module):
+    """Same parameter layout as ``vit_pytorch.vit.Transformer`` (keys pinned by utils/utils.py:18-33).
+    ``forward(x)`` runs the fused encoder: x (B,T,D) fp32 -> (B,T,D) fp32."""
+
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.0):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                PreNorm(dim, Attention(dim, heads, dim_head, dropout)),
+                PreNorm(dim, FeedForward(dim, mlp_dim, dropout)),
+            ]))
+        self._owner = None
+
+    def forward(self, x, **kwargs):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError("Transformer is not attached to a SiT")
+        return owner._encoder(x)
+
+
+def _stream(device):
+    return vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _SiTFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, img, *params):
+        B = img.shape[0]
+        dev = img.device
+        model._refresh_shadow(dev)
+        lib = _lib.load()
+        nbytes = lib.svit_workspace_bytes(model._engine, B, 1, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, model.num_classes, dtype=torch.float32, device=dev)
+        check(lib.svit_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(img), B,
+                               vp(0), 0, vp(0), vp(0), ptr(out), 1, _stream(dev)), "svit_forward")
+        ctx.model = model
+        ctx.ws = ws
+        ctx.B = B
+        ctx.dev = dev
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model = ctx.model
+        lib = _lib.load()
+        dout = dout.contiguous().float()
+        G = torch.zeros_like(model._flat)
+        with torch.cuda.device(ctx.dev):
+            hook = model._make_progress_hook(G)
+            check(lib.svit_backward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ctx.ws), ctx.B, ptr(dout),
+                                    ptr(G), hook, vp(0), _stream(ctx.dev)), "svit_backward")
+            model._finish_progress_hook(G)
+        ctx.ws = None
+        return (None, None) + model._grad_views(G)
+
+
+class _EncoderFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        B = x.shape[0]
+        dev = x.device
+        model._refresh_shadow(dev)
+        lib = _lib.load()
+        training = 1
+        nbytes = lib.svit_workspace_bytes(model._engine, B, training, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        y = torch.empty_like(x)
+        check(lib.svit_encoder_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(x), B,
+                                       ptr(y), training, _stream(dev)), "svit_encoder_forward")
+        ctx.model = model
+        ctx.ws = ws
+        ctx.B = B
+        ctx.dev = dev
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        model = ctx.model
+        lib = _lib.load()
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        G = torch.zeros_like(model._flat)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(ctx.dev):
+            check(lib.svit_encoder_backward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ctx.ws), ctx.B,
+                                            ptr(x), ptr(dy), ptr(dx), ptr(G), _stream(ctx.dev)), "svit_encoder_backward")
+        ctx.ws = None
+        return (None, dx) + model._grad_views(G)
+
+
+class SiT(nn.Module):
+    # models/sit.py:26-39 -- keyword-only constructor, same defaults
+    def __init__(self, *, dim, depth, heads, mlp_dim, pool='cls', num_patches=20, num_classes=1, num_channels=4,
+                 num_vertices=2145, dim_head=64, dropout=0., emb_dropout=0.):
+        super().__init__()
+        assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+        if dropout != 0. or emb_dropout != 0.:
+            raise NotImplementedError("the fused sm_100a path supports dropout=0 / emb_dropout=0 only "
+                                      "(all shipped reference configs use 0.0)")
+        if dim_head != 64:
+            raise NotImplementedError("the fused attention kernel requires dim_head == 64")
+        patch_dim = num_channels * num_vertices
+        self.to_patch_embedding = nn.Sequential(Rearrange(), nn.Linear(patch_dim, dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        self.pool = pool
+        self.to_latent = nn.Identity()
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+
+        self.dim, self.depth, self.heads, self.mlp_dim = dim, depth, heads, mlp_dim
+        self.num_patches, self.num_classes = num_patches, num_classes
+        self.num_channels, self.num_vertices = num_channels, num_vertices
+        self.transformer._owner = weakref.ref(self)
+
+        cfg = SvitConfig(dim, depth, heads, dim_head, mlp_dim, num_patches, num_vertices, num_channels, num_classes,
+                         1 if pool == 'mean' else 0)
+        lib = _lib.load()
+        eng = lib.svit_create(ctypes.byref(cfg))
+        if not eng:
+            raise _lib.SvitError("svit_create failed: " + lib.svit_last_error().decode())
+        self._engine = vp(eng)
+        self._finalizer = weakref.finalize(self, lib.svit_destroy, self._engine)
+        self._flat = None
+        self._shadow = None
+        self._shadow_key = None
+        self._grad_hook = None   # set by ddp.DataParallel: called as hook(stage, G) while backward is being enqueued
+        self._flatten()
+
+    # ------------------------------------------------------------------ parameters
+    def _canonical_params(self):
+        ps = [self.pos_embedding, self.cls_token, self.to_patch_embedding[1].weight, self.to_patch_embedding[1].bias]
+        for attn, ff in self.transformer.layers:
+            ps += [attn.norm.weight, attn.norm.bias, attn.fn.to_qkv.weight, attn.fn.to_out[0].weight,
+                   attn.fn.to_out[0].bias, ff.norm.weight, ff.norm.bias, ff.fn.net[0].weight, ff.fn.net[0].bias,
+                   ff.fn.net[3].weight, ff.fn.net[3].bias]
+        ps += [self.mlp_head[0].weight, self.mlp_head[0].bias, self.mlp_head[1].weight, self.mlp_head[1].bias]
+        return ps
+
+    def _flatten(self):
+        """(Re)creates the flat fp32 buffer on the parameters' device and re-points every parameter at its slice."""
+        lib = _lib.load()
+        ps = self._canonical_params()
+        assert len(ps) == lib.svit_num_params(self._engine)
+        dev = ps[0].device
+        flat = torch.zeros(lib.svit_flat_numel(self._engine), dtype=torch.float32, device=dev)
+        self._offsets = []
+        for i, p in enumerate(ps):
+            off, n = lib.svit_param_offset(self._engine, i), lib.svit_param_numel(self._engine, i)
+            assert n == p.numel(), (i, n, p.shape)
+            view = flat[off:off + n].view(p.shape)
+            view.copy_(p.data.to(torch.float32))
+            p.data = view
+            p._svit_owner = weakref.ref(self)
+            p._svit_index = i
+            self._offsets.append((off, n))
+        self._flat = flat
+        self._plist = ps
+        self._shadow = None
+        self._shadow_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if self._flat is not None:
+            self._flatten()
+        return out
+
+    def _weights_version(self):
+        return (self._flat.data_ptr(), self._flat._version, sum(p._version for p in self._plist))
+
+    def mark_weights_dirty(self):
+        """Called by optimizers that update the flat buffer through the C ABI (no autograd version bump)."""
+        self._shadow_key = None
+
+    def _refresh_shadow(self, dev):
+        if self._flat.device != dev or dev.type != 'cuda':
+            raise RuntimeError(f"SiT parameters are on {self._flat.device} but the input is on {dev}: the sm_100a path "
+                               "needs both on the same CUDA device (there is no CPU fallback)")
+        if self._flat.dtype != torch.float32:
+            raise RuntimeError("SiT parameters must be fp32 master weights")
+        key = self._weights_version()
+        if self._shadow is not None and key == self._shadow_key:
+            return
+        lib = _lib.load()
+        if self._shadow is None or self._shadow.device != dev:
+            self._shadow = torch.empty(lib.svit_shadow_bytes(self._engine), dtype=torch.uint8, device=dev)
+        check(lib.svit_prepare_weights(self._engine, ptr(self._flat), ptr(self._shadow), _stream(dev)),
+              "svit_prepare_weights")
+        self._shadow_key = key
+
+    def _grad_views(self, G):
+        return tuple(G[off:off + n].view(p.shape) for (off, n), p in zip(self._offsets, self._plist))
+
+    # ------------------------------------------------------------------ DDP progress hook plumbing
+    def _make_progress_hook(self, G):
+        if self._grad_hook is None:
+            return vp(0)
+        hook = self._grad_hook
+
+        def cb(stage, _user):
+            hook(self, stage, G)
+
+        self._cb_keepalive = _lib.PROGRESS_FN(cb)
+        return ctypes.cast(self._cb_keepalive, vp)
+
+    def _finish_progress_hook(self, G):
+        if self._grad_hook is not None:
+            self._grad_hook(self, None, G)   # stage None == "backward fully enqueued": wait for outstanding work
+        self._cb_keepalive = None
+
+    def stage_segment(self, stage):
+        """(offset, numel) of the flat-buffer range whose gradients are final after `stage`
+        (depth = head, l = encoder layer l, -1 = patch embedding / pos / cls)."""
+        if stage == self.depth:
+            a = self._offsets[4 + 11 * self.depth][0]
+            return a, self._flat.numel() - a
+        if stage >= 0:
+            a = self._offsets[4 + 11 * stage][0]
+            b = self._offsets[4 + 11 * (stage + 1)][0]
+            return a, b - a
+        return 0, self._offsets[4][0]
+
+    # ------------------------------------------------------------------ forward paths
+    def _check_input(self, img):
+        if img.dim() != 4 or img.shape[1] != self.num_channels or img.shape[2] != self.num_patches or \
+                img.shape[3] != self.num_vertices:
+            raise ValueError(f"expected input (B,{self.num_channels},{self.num_patches},{self.num_vertices}), "
+                             f"got {tuple(img.shape)}")
+        if not img.is_cuda:
+            raise RuntimeError("SiT (B200) needs a CUDA input: there is no CPU fallback")
+        return img.contiguous().float()
+
+    def forward(self, img):
+        img = self._check_input(img)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
+            return _SiTFunction.apply(self, img, *self._plist)
+        return self.infer(img)
+
+    @torch.no_grad()
+    def infer(self, img, table=None, n_mesh=0, ch_mean=None, ch_std=None):
+        """Forward without autograd (eval / torch.no_grad()); small ping-pong workspace."""
+        B, dev = img.shape[0], img.device
+        self._refresh_shadow(dev)
+        lib = _lib.load()
+        nbytes = lib.svit_workspace_bytes(self._engine, B, 0, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, self.num_classes, dtype=torch.float32, device=dev)
+        check(lib.svit_forward(self._engine, ptr(self._flat), ptr(self._shadow), ptr(ws), nbytes, ptr(img), B,
+                               ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std), ptr(out), 0, _stream(dev)), "svit_forward")
+        return out
+
+    def forward_mesh(self, mesh, table, ch_mean=None, ch_std=None):
+        """raw ico-6 mesh (B,C,40962) + gather table (V,N) int32 -> prediction; the patch gather
+        (tools/preprocessing.py:79-84) and optional z-score (:72) are fused into the patch packing kernel."""
+        mesh = mesh.contiguous().float()
+        return self.infer(mesh, table=table.contiguous(), n_mesh=mesh.shape[-1], ch_mean=ch_mean, ch_std=ch_std)
+
+    def _encoder(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("SiT.transformer (B200) needs a CUDA input: there is no CPU fallback")
+        x = x.contiguous().float()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._plist)):
+            return _EncoderFunction.apply(self, x, *self._plist)
+        with torch.no_grad():
+            B, dev = x.shape[0], x.device
+            self._refresh_shadow(dev)
+            lib = _lib.load()
+            nbytes = lib.svit_workspace_bytes(self._engine, B, 0, 0)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            y = torch.empty_like(x)
+            check(lib.svit_encoder_forward(self._engine, ptr(self._flat), ptr(self._shadow), ptr(ws), nbytes, ptr(x), B,
+                                           ptr(y), 0, _stream(dev)), "svit_encoder_forward")
+            return y
