@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- SiT train samples/s on B200 (BASELINE.json metric) for the B200-native hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload NAME]
+
+N > 1 is launched by the driver as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+(one rank per GPU, NCCL).  A "step" is one full training iteration of the workload: forward, MSE loss, backward,
+gradient all-reduce (N > 1) and a fused AdamW update, on one synthetic batch per GPU (weak scaling).
+
+One JSON line is printed by rank 0:
+  value        whole-job samples/s with the inputs already resident in HBM (CUDA-event timed, max over ranks)
+  e2e          same metric through the public API with HOST (pinned) inputs: H2D copy of every step's batch and a
+               D2H read of the loss inside the timed region
+  roofline     dominant kernel (tcgen05 GEMM of the MLP up-projection, the largest single launch) timed live
+               with CUDA events; whole-step tensor fraction reported next to it
+  cpu_baseline the oracle port of the reference (fp32 PyTorch on the host cores) on a bounded sample
+--impl reference times that CPU path as its own arm (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the headline metric is quoted on
+    "sit_small_ico2_scan_age_train": dict(
+        model=dict(dim=384, depth=12, heads=6, mlp_dim=1536, num_patches=320, num_vertices=153, num_channels=4,
+                   num_classes=1, dim_head=64), kind="train", gflop_per_sample=46.895),
+    "sit_tiny_ico2_scan_age_train": dict(
+        model=dict(dim=192, depth=12, heads=3, mlp_dim=768, num_patches=320, num_vertices=153, num_channels=4,
+                   num_classes=1, dim_head=64), kind="train", gflop_per_sample=13.223),
+    "sit_small_ico1_birth_age_train": dict(
+        model=dict(dim=384, depth=12, heads=6, mlp_dim=1536, num_patches=80, num_vertices=561, num_channels=4,
+                   num_classes=1, dim_head=64), kind="train", gflop_per_sample=10.958),
+    "sit_small_ico2_mpp_pretrain": dict(
+        model=dict(dim=384, depth=12, heads=6, mlp_dim=1536, num_patches=320, num_vertices=153, num_channels=4,
+                   num_classes=1, dim_head=64), kind="mpp", gflop_per_sample=47.346),
+    "sit_base_ico2_inference": dict(
+        model=dict(dim=768, depth=12, heads=12, mlp_dim=3072, num_patches=320, num_vertices=153, num_channels=4,
+                   num_classes=1, dim_head=64), kind="infer", gflop_per_sample=58.627),
+}
+DEFAULT_WORKLOAD = "sit_small_ico2_scan_age_train"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops_burst=p["bf16_tflops"], tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm_gbs=p["hbm_gbs"], source="MEASURED_PEAKS.json")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_rate(wl, batch, steps, warmup):
+    """fp32 PyTorch restatement of the reference (oracle port) on the host cores: full train step / eval forward."""
+    import torch
+    from oracle.sit_oracle import OracleMPP, OracleSiT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = wl["model"]
+    model = OracleSiT(dim=m["dim"], depth=m["depth"], heads=m["heads"], mlp_dim=m["mlp_dim"],
+                      num_patches=m["num_patches"], num_classes=m["num_classes"], num_channels=m["num_channels"],
+                      num_vertices=m["num_vertices"], dim_head=m["dim_head"])
+    x = torch.randn(batch, m["num_channels"], m["num_patches"], m["num_vertices"])
+    y = torch.rand(batch) * 19 + 26
+    kind = wl["kind"]
+    if kind == "mpp":
+        K = m["num_channels"] * m["num_vertices"]
+        ssl = OracleMPP(model, m["dim"], K, "cpu", 0.5, 0.8, 0.02, m["num_channels"], m["num_vertices"])
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0.0)
+    elif kind == "train":
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=0.0)
+
+    def step():
+        if kind == "infer":
+            with torch.no_grad():
+                return model(x)
+        opt.zero_grad()
+        if kind == "mpp":
+            loss, _ = ssl(x)
+        else:
+            loss = torch.nn.functional.mse_loss(model(x).squeeze(), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference_arm(args, wl, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    rate, ms, cores = cpu_reference_step_rate(wl, batch, args.steps, args.warmup)
+    sample = f"oracle port of models/sit.py + vit_pytorch shim, fp32, batch {batch} per step, {args.steps} steps"
+    line = dict(impl="reference", metric="SiT train samples/sec", value=rate, unit="samples/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl_name, batch_per_step=batch, device="host cpu", **wl["model"]),
+                cpu_baseline=dict(value=rate, unit="samples/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=rate, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="the reference cannot be installed (its encoder is the un-pinned third-party vit-pytorch, absent "
+                     "offline; /root/reference is not on the GPU box): this arm runs the oracle port on the host cores")
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    wl_name = args.workload
+    wl = WORKLOADS[wl_name]
+    if args.impl == "reference":
+        run_reference_arm(args, wl, wl_name)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import surface_vision_transformers_b200 as svit
+    from surface_vision_transformers_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    m = wl["model"]
+    kind = wl["kind"]
+    B = args.batch
+    torch.manual_seed(0)
+    model = svit.SiT(dim=m["dim"], depth=m["depth"], heads=m["heads"], mlp_dim=m["mlp_dim"], num_patches=m["num_patches"],
+                     num_classes=m["num_classes"], num_channels=m["num_channels"], num_vertices=m["num_vertices"],
+                     dim_head=m["dim_head"]).to(dev)
+    runner = model
+    if kind == "mpp":
+        K = m["num_channels"] * m["num_vertices"]
+        runner = svit.masked_patch_pretraining(transformer=model, dim_in=m["dim"], dim_out=K, device=dev, mask_prob=0.5,
+                                               replace_prob=0.8, swap_prob=0.02, channels=m["num_channels"],
+                                               num_vertices=m["num_vertices"]).to(dev)
+    if world > 1:
+        runner = svit.DataParallel(runner)
+    opt = svit.FusedAdamW(model.parameters(), lr=1e-5 if kind == "train" else 3e-4, weight_decay=0.0) \
+        if kind != "infer" else None
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    x_dev = torch.randn(B, m["num_channels"], m["num_patches"], m["num_vertices"], device=dev, generator=g)
+    y_dev = torch.rand(B, device=dev, generator=g) * 19 + 26
+    x_host = x_dev.cpu().pin_memory()
+    y_host = y_dev.cpu().pin_memory()
+
+    def step(x, y):
+        if kind == "infer":
+            with torch.no_grad():
+                return model(x).sum()
+        opt.zero_grad(set_to_none=True)
+        if kind == "mpp":
+            loss, _ = runner(x)
+        else:
+            loss = torch.nn.functional.mse_loss(runner(x).squeeze(), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.svit_launch_count()
+    ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = lib.svit_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end: host inputs in, loss out, every step ----
+    x_stage = torch.empty_like(x_dev)
+    y_stage = torch.empty_like(y_dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        x_stage.copy_(x_host, non_blocking=True)
+        y_stage.copy_(y_host, non_blocking=True)
+        loss = step(x_stage, y_stage)
+        loss_host.copy_(loss.detach().reshape(()), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the loss every step (tools/train.py:293)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = x_host.numel() * 4 + y_host.numel() * 4
+    d2h = 4
+
+    # ---- dominant kernel (MLP up-projection GEMM + bias + GELU epilogue) timed alone ----
+    roof = None
+    if rank == 0:
+        M = B * (m["num_patches"] + 1)
+        D, H4 = m["dim"], m["mlp_dim"]
+        A = (torch.randn(M, D, device=dev) * 0.5).bfloat16()
+        W = (torch.randn(H4, D, device=dev) * 0.05).bfloat16()
+        bias = torch.zeros(H4, device=dev)
+        o1 = torch.empty(M, H4, device=dev, dtype=torch.bfloat16)
+        o2 = torch.empty(M, H4, device=dev, dtype=torch.bfloat16)
+        mode = 4 if kind == "infer" else 1
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        st = _lib.vp(torch.cuda.current_stream().cuda_stream)
+
+        def gemm():
+            _lib.check(lib.svit_gemm_tn(_lib.ptr(A), _lib.ptr(W), _lib.ptr(o1), _lib.ptr(o2), _lib.vp(0), _lib.ptr(bias),
+                                        _lib.vp(0), 1, M, H4, D, D, D, H4, mode, 0, sms, st), "gemm")
+        for _ in range(3):
+            gemm()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_it = 20
+        e0.record()
+        for _ in range(n_it):
+            gemm()
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / n_it
+        flops = 2.0 * M * H4 * D
+        ach = flops / (k_ms * 1e-3) / 1e12
+        step_tf = value / world * wl["gflop_per_sample"] / 1e3
+        roof = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,EPI_GELU,192> (fc1 + bias + exact GELU, M=%d N=%d K=%d)" % (M, H4, D),
+                    achieved=ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=ach / peaks["tflops_burst"],
+                    traffic=None, peak_source=peaks["source"] + " (burst: kernel timed alone)",
+                    us_per_launch=k_ms * 1e3, flops_per_launch=flops,
+                    step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
+                    step_frac_of_nominal_2250=step_tf / 2250.0)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, ms_cpu, cores = cpu_reference_step_rate(wl, args.cpu_batch, 3, 1)
+        cpu = dict(value=rate, unit="samples/s", cores=cores, kind="port",
+                   sample=f"oracle port (fp32 PyTorch restatement of the reference), batch {args.cpu_batch}, 1 warm-up + 3 "
+                          f"timed steps of the same workload ({ms_cpu:.0f} ms/step)")
+
+    if rank == 0:
+        line = dict(metric="SiT train samples/sec" if kind != "infer" else "SiT inference samples/sec", value=value,
+                    unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload=wl_name, batch_per_gpu=B, global_batch=B * world,
+                                parallelism=f"dp{world}" if world > 1 else "single", optimizer="FusedAdamW",
+                                l2_policy="inputs and activations larger than L2 (batch %.0f MB, activations > 10 GB)" % (x_dev.numel() * 4 / 1e6),
+                                **m),
+                    clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                                            ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

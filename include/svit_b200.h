@@ -50,6 +50,8 @@ typedef struct svit_engine svit_engine;
 
 const char* svit_last_error(void);
 int svit_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+unsigned long long svit_launch_count(void);
 
 /* ---- engine life cycle (host-side object; owns no device memory) ---- */
 svit_engine* svit_create(const svit_config* cfg);

@@ -30,6 +30,7 @@ PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
 SIGNATURES = {
     "svit_last_error": (ctypes.c_char_p, []),
     "svit_version": (ci, []),
+    "svit_launch_count": (ctypes.c_ulonglong, []),
     "svit_create": (vp, [ctypes.POINTER(SvitConfig)]),
     "svit_destroy": (None, [vp]),
     "svit_num_params": (ci, [vp]),

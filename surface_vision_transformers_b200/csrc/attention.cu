@@ -531,6 +531,7 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     a.scale = d.scale;
     a.scale_log2e = d.scale * 1.4426950408889634f;
     attn_fwd_kernel<<<d.B * d.H, FWD_THREADS, FWD_SMEM, stream>>>(a);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("attn_fwd launch failed: %s", cudaGetErrorString(e));
@@ -583,6 +584,7 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     const int nblk = (d.T + 127) / 128;
     attn_bwd_kernel<false><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
     attn_bwd_kernel<true><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
+    count_launch(3);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("attn_bwd launch failed: %s", cudaGetErrorString(e));

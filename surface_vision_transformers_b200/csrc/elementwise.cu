@@ -14,6 +14,7 @@ namespace svit {
             set_error("%s launch failed: %s", name, cudaGetErrorString(e__));    \
             return -11;                                                          \
         }                                                                        \
+        count_launch();                                                          \
     } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -641,6 +642,7 @@ int launch_mask_token_grad(const float* g0, const uint8_t* replace_sel, const fl
     const int rpb = 64;
     masked_rowsum_kernel<<<(B * (T - 1) + rpb - 1) / rpb, 128, 0, st>>>(g0, replace_sel, scratch_r, B, T, D, rpb);
     mask_token_gemv_kernel<<<(K + 127) / 128, 128, 0, st>>>(scratch_r, W, dmt, D, K);
+    count_launch();
     SVIT_CHECK_LAUNCH("mask_token_grad");
     return 0;
 }

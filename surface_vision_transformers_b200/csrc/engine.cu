@@ -14,6 +14,7 @@
 
 namespace svit {
 const char* last_error();
+unsigned long long launch_count();
 }
 using namespace svit;
 
@@ -283,6 +284,7 @@ extern "C" {
 
 const char* svit_last_error(void) { return svit::last_error(); }
 int svit_version(void) { return 100; }
+unsigned long long svit_launch_count(void) { return svit::launch_count(); }
 
 svit_engine* svit_create(const svit_config* cfg) {
     if (cfg == nullptr) {

@@ -23,6 +23,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_last_error; }
+static unsigned long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+unsigned long long launch_count() { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------
 // exact (erf) GELU, as nn.GELU() in the reference FeedForward
@@ -500,6 +503,7 @@ static int launch_tn_inst(const TnArgs& a, int num_sms, cudaStream_t stream) {
     const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
     kfn<<<grid, TN_THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("gemm_tn launch failed: %s", cudaGetErrorString(e));
@@ -594,6 +598,7 @@ int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream) 
     splits = (total_kb + a.kb_per_split - 1) / a.kb_per_split;
     dim3 grid(tiles, splits);
     gemm_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(a);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("gemm_wgrad launch failed: %s", cudaGetErrorString(e));

@@ -48,5 +48,6 @@ struct GemmWgradDesc {
 int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // kernels launched through this library (svit_launch_count)
 
 }  // namespace svit
