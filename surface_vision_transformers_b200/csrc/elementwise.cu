@@ -91,52 +91,65 @@ int launch_pack_patches(const PackDesc& d, cudaStream_t st) {
 }
 
 // =================================================================================================
-// LayerNorm forward (one warp per row; row cached in registers, two-pass variance)
+// LayerNorm forward (one warp per row; row cached in registers, two-pass variance).
+// NVEC = float4 per lane (compile time, so only the registers a given D needs are allocated).
 // =================================================================================================
-constexpr int LN_MAX_VEC = 8;  // float4 per lane -> D <= 1024
+constexpr int LN_MAX_VEC = 8;  // D <= 1024
 
-__global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                              __nv_bfloat16* __restrict__ a, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                              int M, int D, float eps) {
+template <int NVEC>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ a,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int M,
+                                                     int D, float eps) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
+    const float inv_d = 1.0f / D;
+    float4 g[NVEC], bb[NVEC];
+#pragma unroll
+    for (int k = 0; k < NVEC; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+            g[k] = reinterpret_cast<const float4*>(gamma)[i];
+            bb[k] = reinterpret_cast<const float4*>(beta)[i];
+        }
+    }
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
         const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-        float4 v[LN_MAX_VEC];
+        float4 v[NVEC];
         float s = 0.0f;
 #pragma unroll
-        for (int k = 0; k < LN_MAX_VEC; ++k) {
+        for (int k = 0; k < NVEC; ++k) {
             const int i = lane + k * 32;
             if (i < nvec) {
-                v[k] = xr[i];
+                v[k] = __ldcs(xr + i);
                 s += v[k].x + v[k].y + v[k].z + v[k].w;
             }
         }
-        const float mean = warp_sum(s) / D;
+        const float mean = warp_sum(s) * inv_d;
         float q = 0.0f;
 #pragma unroll
-        for (int k = 0; k < LN_MAX_VEC; ++k) {
+        for (int k = 0; k < NVEC; ++k) {
             const int i = lane + k * 32;
             if (i < nvec) {
                 const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
                 q += dx * dx + dy * dy + dz * dz + dw * dw;
             }
         }
-        const float rstd = rsqrtf(warp_sum(q) / D + eps);
+        const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
         if (lane == 0) {
             mean_out[row] = mean;
             rstd_out[row] = rstd;
         }
         uint2* ar = reinterpret_cast<uint2*>(a + static_cast<size_t>(row) * D);
 #pragma unroll
-        for (int k = 0; k < LN_MAX_VEC; ++k) {
+        for (int k = 0; k < NVEC; ++k) {
             const int i = lane + k * 32;
             if (i < nvec) {
-                const float4 g = reinterpret_cast<const float4*>(gamma)[i];
-                const float4 bb = reinterpret_cast<const float4*>(beta)[i];
-                __nv_bfloat162 lo = __floats2bfloat162_rn((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
-                __nv_bfloat162 hi = __floats2bfloat162_rn((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+                __nv_bfloat162 lo = __floats2bfloat162_rn((v[k].x - mean) * rstd * g[k].x + bb[k].x,
+                                                          (v[k].y - mean) * rstd * g[k].y + bb[k].y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn((v[k].z - mean) * rstd * g[k].z + bb[k].z,
+                                                          (v[k].w - mean) * rstd * g[k].w + bb[k].w);
                 uint2 o;
                 o.x = *reinterpret_cast<uint32_t*>(&lo);
                 o.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -154,14 +167,26 @@ static int ln_shape_ok(int D) {
     return 1;
 }
 
+#define SVIT_LN_DISPATCH(nv, CALL)                 \
+    switch (nv) {                                  \
+        case 1: { constexpr int NV = 1; CALL; break; } \
+        case 2: { constexpr int NV = 2; CALL; break; } \
+        case 3: { constexpr int NV = 3; CALL; break; } \
+        case 4: { constexpr int NV = 4; CALL; break; } \
+        case 5: case 6: { constexpr int NV = 6; CALL; break; } \
+        default: { constexpr int NV = 8; CALL; break; } \
+    }
+
 int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd, int M,
                   int D, float eps, cudaStream_t st) {
     if (M <= 0) return 0;
     if (!ln_shape_ok(D)) return -2;
     const int wpb = 8;
     int blocks = (M + wpb - 1) / wpb;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    ln_fwd_kernel<<<blocks, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(a_bf16), mean, rstd, M, D, eps);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const int nv = (D + 127) / 128;
+    SVIT_LN_DISPATCH(nv, (ln_fwd_kernel<NV><<<blocks, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(a_bf16),
+                                                                         mean, rstd, M, D, eps)));
     SVIT_CHECK_LAUNCH("ln_fwd");
     return 0;
 }
@@ -169,64 +194,81 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a
 // =================================================================================================
 // LayerNorm backward + residual-gradient add + column reductions
 // =================================================================================================
-__global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ x,
-                              const float* __restrict__ mean, const float* __restrict__ rstd,
-                              const float* __restrict__ gamma, const float* g_in, float* g_out,
-                              __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta, float* __restrict__ colsum_out, int M, int D) {
+template <int NVEC>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* g_in, float* g_out,
+                                                     __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, float* __restrict__ colsum_out, int M,
+                                                     int D) {
     extern __shared__ float red[];  // [3][D] block-level partial column sums
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
+    const float inv_d = 1.0f / D;
     for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.0f;
     __syncthreads();
-    float4 acc_g[LN_MAX_VEC], acc_b[LN_MAX_VEC], acc_c[LN_MAX_VEC];
+    float4 acc_g[NVEC], acc_b[NVEC], acc_c[NVEC], gm[NVEC];
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; ++k) {
+    for (int k = 0; k < NVEC; ++k) {
         acc_g[k] = make_float4(0, 0, 0, 0);
         acc_b[k] = make_float4(0, 0, 0, 0);
         acc_c[k] = make_float4(0, 0, 0, 0);
+        const int i = lane + k * 32;
+        gm[k] = (i < nvec) ? reinterpret_cast<const float4*>(gamma)[i] : make_float4(0, 0, 0, 0);
     }
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
         const float mu = mean[row], rs = rstd[row];
         const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
         const uint2* dar = reinterpret_cast<const uint2*>(da + static_cast<size_t>(row) * D);
-        float4 xh[LN_MAX_VEC], dy[LN_MAX_VEC];
+        const float4* gir = reinterpret_cast<const float4*>(g_in + static_cast<size_t>(row) * D);
+        float4 xh[NVEC], dy[NVEC], gi[NVEC];
         float s1 = 0.0f, s2 = 0.0f;
+        // issue every load of the row first (memory-level parallelism), then reduce
+        uint2 dv[NVEC];
 #pragma unroll
-        for (int k = 0; k < LN_MAX_VEC; ++k) {
+        for (int k = 0; k < NVEC; ++k) {
             const int i = lane + k * 32;
             if (i < nvec) {
-                const float4 xv = xr[i];
-                const uint2 dv = dar[i];
-                const float4 g = reinterpret_cast<const float4*>(gamma)[i];
-                const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
-                const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+                xh[k] = __ldcs(xr + i);
+                dv[k] = __ldcs(dar + i);
+                gi[k] = __ldcs(gir + i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NVEC; ++k) {
+            const int i = lane + k * 32;
+            if (i < nvec) {
+                const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv[k].x);
+                const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv[k].y);
                 const float4 d = make_float4(__bfloat162float(d01.x), __bfloat162float(d01.y), __bfloat162float(d23.x),
                                              __bfloat162float(d23.y));
-                xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                xh[k] = make_float4((xh[k].x - mu) * rs, (xh[k].y - mu) * rs, (xh[k].z - mu) * rs, (xh[k].w - mu) * rs);
                 acc_g[k].x += d.x * xh[k].x; acc_g[k].y += d.y * xh[k].y; acc_g[k].z += d.z * xh[k].z; acc_g[k].w += d.w * xh[k].w;
                 acc_b[k].x += d.x; acc_b[k].y += d.y; acc_b[k].z += d.z; acc_b[k].w += d.w;
-                dy[k] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+                dy[k] = make_float4(d.x * gm[k].x, d.y * gm[k].y, d.z * gm[k].z, d.w * gm[k].w);
                 s1 += dy[k].x + dy[k].y + dy[k].z + dy[k].w;
                 s2 += dy[k].x * xh[k].x + dy[k].y * xh[k].y + dy[k].z * xh[k].z + dy[k].w * xh[k].w;
             }
         }
-        const float m1 = warp_sum(s1) / D;
-        const float m2 = warp_sum(s2) / D;
-        const float4* gir = reinterpret_cast<const float4*>(g_in + static_cast<size_t>(row) * D);
+        // two independent butterfly reductions interleaved
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float m1 = s1 * inv_d, m2 = s2 * inv_d;
         float4* gor = reinterpret_cast<float4*>(g_out + static_cast<size_t>(row) * D);
         uint2* gbr = reinterpret_cast<uint2*>(g_out_bf16 + static_cast<size_t>(row) * D);
 #pragma unroll
-        for (int k = 0; k < LN_MAX_VEC; ++k) {
+        for (int k = 0; k < NVEC; ++k) {
             const int i = lane + k * 32;
             if (i < nvec) {
-                const float4 gi = gir[i];
                 float4 o;
-                o.x = gi.x + rs * (dy[k].x - m1 - xh[k].x * m2);
-                o.y = gi.y + rs * (dy[k].y - m1 - xh[k].y * m2);
-                o.z = gi.z + rs * (dy[k].z - m1 - xh[k].z * m2);
-                o.w = gi.w + rs * (dy[k].w - m1 - xh[k].w * m2);
+                o.x = gi[k].x + rs * (dy[k].x - m1 - xh[k].x * m2);
+                o.y = gi[k].y + rs * (dy[k].y - m1 - xh[k].y * m2);
+                o.z = gi[k].z + rs * (dy[k].z - m1 - xh[k].z * m2);
+                o.w = gi[k].w + rs * (dy[k].w - m1 - xh[k].w * m2);
                 gor[i] = o;
                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                 uint2 ob;
@@ -239,7 +281,7 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float*
     }
     // block reduction through shared memory, then one atomic per column per block
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; ++k) {
+    for (int k = 0; k < NVEC; ++k) {
         const int i = lane + k * 32;
         if (i < nvec) {
             const int c = i * 4;
@@ -266,10 +308,11 @@ int launch_ln_bwd(const void* da_bf16, const float* x, const float* mean, const 
     if (!ln_shape_ok(D)) return -2;
     const int wpb = 8;
     int blocks = (M + wpb - 1) / wpb;
-    if (blocks > 148 * 2) blocks = 148 * 2;
-    ln_bwd_kernel<<<blocks, wpb * 32, 3 * D * sizeof(float), st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
-        reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const int nv = (D + 127) / 128;
+    SVIT_LN_DISPATCH(nv, (ln_bwd_kernel<NV><<<blocks, wpb * 32, 3 * D * sizeof(float), st>>>(
+                             reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
+                             reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D)));
     SVIT_CHECK_LAUNCH("ln_bwd");
     return 0;
 }

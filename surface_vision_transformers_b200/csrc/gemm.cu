@@ -28,13 +28,42 @@ void count_launch(int n) { g_launches += n; }
 unsigned long long launch_count() { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------
-// exact (erf) GELU, as nn.GELU() in the reference FeedForward
+// exact (erf) GELU, as nn.GELU() in the reference FeedForward.
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution and below the fp32
+// check-mode tolerance): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z >= 0.
+// One MUFU.RCP + one MUFU.EX2 per element; the exponential exp(-u^2/2) is shared with the Gaussian pdf
+// needed by the derivative.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// returns Phi(u) = 0.5 (1 + erf(u / sqrt 2)) and E = exp(-u^2 / 2)
+__device__ __forceinline__ float gauss_cdf(float u, float& E) {
+    const float au = fabsf(u);
+    const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, au, 1.0f));
+    E = fast_ex2(u * u * -0.72134752044448170f);  // -0.5 * log2(e)
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_tail = 0.5f * poly * t * E;          // 0.5 * (1 - erf(|u|/sqrt2))
+    return u >= 0.0f ? 1.0f - half_tail : half_tail;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+    float E;
+    return x * gauss_cdf(x, E);
+}
 __device__ __forceinline__ float dgelu_f(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float E;
+    const float cdf = gauss_cdf(x, E);
+    return fmaf(x * 0.3989422804014327f, E, cdf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -45,7 +74,8 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int EPI_BUF_BYTES = BM * 128;     // 128 rows x 128 B
 constexpr int NUM_EPI_BUFS = 4;
-constexpr int TN_THREADS = 256;
+constexpr int TN_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 
 struct TnArgs {
     CUtensorMap tmA, tmB, tmOut, tmOut2, tmAux;
@@ -113,9 +143,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], 8);
             mbar_init(&afull_bar[i], 1);
-            mbar_init(&aempty_bar[i], 4);
+            mbar_init(&aempty_bar[i], 8);
         }
         fence_mbar_init();
     }
@@ -198,11 +228,15 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+        // ===================== epilogue: 8 warps =====================
+        // warp w owns TMEM lane quadrant (w & 3) and column half ((w - 4) >> 2) of every 128-byte output unit,
+        // so each SM sub-partition has two epilogue warps to hide TMEM / MUFU / shared-memory latency.
+        constexpr int HC = UC / 2;  // columns per thread per unit: 32 (bf16 out) or 16 (fp32 out)
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int row = q * 32 + lane;  // row inside the tile == TMEM lane
         const bool leader = (threadIdx.x == 4 * 32);
-        const int et = threadIdx.x - 4 * 32;  // 0..127
+        const int et = threadIdx.x - 4 * 32;  // 0..255
         int it = 0, ait = 0, oit = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m0 = (tile / tiles_n) * BM;
@@ -210,25 +244,26 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             // stage the bias slice of this tile
-            for (int i = et; i < BN; i += 128) {
+            for (int i = et; i < BN; i += EPI_THREADS) {
                 const int c = n0 + i;
                 sBias[i] = (args.bias != nullptr && c < N) ? args.bias[c] : 0.0f;
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, EPI_THREADS);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
             const int grow = m0 + row;
 #pragma unroll 1
             for (int u = 0; u < UNITS; ++u, ++oit) {
-                float v[UC];
-#pragma unroll
-                for (int h = 0; h < UC / 32; ++h) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_addr + u * UC + h * 32, r);
+                const int col0 = u * UC + half * HC;  // first column (inside the tile) handled by this thread
+                float v[HC];
+                {
+                    uint32_t r[HC];
+                    if constexpr (HC == 32) tmem_ld_32x32(t_addr + col0, r);
+                    else tmem_ld_32x16(t_addr + col0, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[j]) + sBias[u * UC + h * 32 + j];
+                    for (int j = 0; j < HC; ++j) v[j] = __uint_as_float(r[j]) + sBias[col0 + j];
                 }
                 if (u == UNITS - 1) {
                     // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -237,10 +272,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     if (lane == 0) mbar_arrive(&tempty_bar[as]);
                 }
                 if (MODE == EPI_STORE && args.rowtab != nullptr) {
-                    const float* tr = args.rowtab + static_cast<size_t>(grow % args.rowtab_period) * N + n0 + u * UC;
+                    const float* tr = args.rowtab + static_cast<size_t>(grow % args.rowtab_period) * N + n0 + col0;
 #pragma unroll
-                    for (int j = 0; j < UC; j += 4) {
-                        if (n0 + u * UC + j < N) {
+                    for (int j = 0; j < HC; j += 4) {
+                        if (n0 + col0 + j < N) {
                             const float4 t4 = *reinterpret_cast<const float4*>(tr + j);
                             v[j] += t4.x;
                             v[j + 1] += t4.y;
@@ -255,25 +290,26 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     mbar_wait(&afull_bar[s], ph);
                     const uint8_t* arow = sEpi + s * EPI_BUF_BYTES + row * 128;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int c = half * 4 + ci;
                         const uint4 a4 = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
                         if (sizeof(OutT) == 4) {
                             // fp32 aux: 4 values per 16-byte chunk
-                            v[c * 4 + 0] += __uint_as_float(a4.x);
-                            v[c * 4 + 1] += __uint_as_float(a4.y);
-                            v[c * 4 + 2] += __uint_as_float(a4.z);
-                            v[c * 4 + 3] += __uint_as_float(a4.w);
+                            v[(ci * 4 + 0) % HC] += __uint_as_float(a4.x);
+                            v[(ci * 4 + 1) % HC] += __uint_as_float(a4.y);
+                            v[(ci * 4 + 2) % HC] += __uint_as_float(a4.z);
+                            v[(ci * 4 + 3) % HC] += __uint_as_float(a4.w);
                         } else {
                             const uint32_t w[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
                                 if (MODE == EPI_DGELU) {
-                                    v[(c * 8 + e * 2) % UC] *= dgelu_f(lo);
-                                    v[(c * 8 + e * 2 + 1) % UC] *= dgelu_f(hi);
+                                    v[(ci * 8 + e * 2) % HC] *= dgelu_f(lo);
+                                    v[(ci * 8 + e * 2 + 1) % HC] *= dgelu_f(hi);
                                 } else {
-                                    v[(c * 8 + e * 2) % UC] += lo;
-                                    v[(c * 8 + e * 2 + 1) % UC] += hi;
+                                    v[(ci * 8 + e * 2) % HC] += lo;
+                                    v[(ci * 8 + e * 2 + 1) % HC] += hi;
                                 }
                             }
                         }
@@ -282,58 +318,52 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     if (lane == 0) mbar_arrive(&aempty_bar[s]);
                     ++ait;
                 }
-                if (MODE == EPI_GELU_ONLY) {
-#pragma unroll
-                    for (int j = 0; j < UC; ++j) v[j] = gelu_f(v[j]);
-                }
                 // ---- stage the unit in shared memory (128B-swizzled rows) and TMA-store it ----
                 const int slot = oit % OUT_SLOTS;
                 uint8_t* obuf = sEpi + (FIRST_OUT_BUF + slot * OUTS_PER_UNIT) * EPI_BUF_BYTES;
                 if (leader) tma_store_wait_read<OUT_SLOTS - 1>();
-                named_bar_sync(1, 128);
+                named_bar_sync(1, EPI_THREADS);
                 uint8_t* orow = obuf + row * 128;
                 if (sizeof(OutT) == 4) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int ci = 0; ci < 4; ++ci) {
                         uint4 o;
-                        o.x = __float_as_uint(v[(c * 4 + 0) % UC]);
-                        o.y = __float_as_uint(v[(c * 4 + 1) % UC]);
-                        o.z = __float_as_uint(v[(c * 4 + 2) % UC]);
-                        o.w = __float_as_uint(v[(c * 4 + 3) % UC]);
-                        *reinterpret_cast<uint4*>(orow + ((c ^ (row & 7)) << 4)) = o;
+                        o.x = __float_as_uint(v[(ci * 4 + 0) % HC]);
+                        o.y = __float_as_uint(v[(ci * 4 + 1) % HC]);
+                        o.z = __float_as_uint(v[(ci * 4 + 2) % HC]);
+                        o.w = __float_as_uint(v[(ci * 4 + 3) % HC]);
+                        *reinterpret_cast<uint4*>(orow + (((half * 4 + ci) ^ (row & 7)) << 4)) = o;
                     }
                 } else {
+                    if (MODE != EPI_GELU_ONLY) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4 o;
-                        o.x = pack_bf16(v[(c * 8 + 0) % UC], v[(c * 8 + 1) % UC]);
-                        o.y = pack_bf16(v[(c * 8 + 2) % UC], v[(c * 8 + 3) % UC]);
-                        o.z = pack_bf16(v[(c * 8 + 4) % UC], v[(c * 8 + 5) % UC]);
-                        o.w = pack_bf16(v[(c * 8 + 6) % UC], v[(c * 8 + 7) % UC]);
-                        *reinterpret_cast<uint4*>(orow + ((c ^ (row & 7)) << 4)) = o;
+                        for (int ci = 0; ci < 4; ++ci) {
+                            uint4 o;
+                            o.x = pack_bf16(v[(ci * 8 + 0) % HC], v[(ci * 8 + 1) % HC]);
+                            o.y = pack_bf16(v[(ci * 8 + 2) % HC], v[(ci * 8 + 3) % HC]);
+                            o.z = pack_bf16(v[(ci * 8 + 4) % HC], v[(ci * 8 + 5) % HC]);
+                            o.w = pack_bf16(v[(ci * 8 + 6) % HC], v[(ci * 8 + 7) % HC]);
+                            *reinterpret_cast<uint4*>(orow + (((half * 4 + ci) ^ (row & 7)) << 4)) = o;
+                        }
                     }
-                    if (MODE == EPI_GELU) {
-                        uint8_t* orow2 = orow + EPI_BUF_BYTES;
+                    if (MODE == EPI_GELU || MODE == EPI_GELU_ONLY) {
+                        uint8_t* orow2 = (MODE == EPI_GELU) ? orow + EPI_BUF_BYTES : orow;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
+                        for (int ci = 0; ci < 4; ++ci) {
                             float g[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                // activation is applied to the bf16-rounded pre-activation that backward will see
-                                const float ub = bf16_lo(pack_bf16(v[(c * 8 + e) % UC], 0.0f));
-                                g[e] = gelu_f(ub);
-                            }
+                            for (int e = 0; e < 8; ++e) g[e] = gelu_f(v[(ci * 8 + e) % HC]);
                             uint4 o;
                             o.x = pack_bf16(g[0], g[1]);
                             o.y = pack_bf16(g[2], g[3]);
                             o.z = pack_bf16(g[4], g[5]);
                             o.w = pack_bf16(g[6], g[7]);
-                            *reinterpret_cast<uint4*>(orow2 + ((c ^ (row & 7)) << 4)) = o;
+                            *reinterpret_cast<uint4*>(orow2 + (((half * 4 + ci) ^ (row & 7)) << 4)) = o;
                         }
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);
+                named_bar_sync(1, EPI_THREADS);
                 if (leader) {
                     tma_store_2d(&args.tmOut, obuf, n0 + u * UC, m0);
                     if (MODE == EPI_GELU) tma_store_2d(&args.tmOut2, obuf + EPI_BUF_BYTES, n0 + u * UC, m0);
