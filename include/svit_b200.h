@@ -131,8 +131,9 @@ int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void
 int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int K, int ldy, int ldx, int ldw,
                     int num_sms, void* stream);
 int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, float scale, void* stream);
-int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
-                  int H, int T, float scale, void* stream);
+/* delta: fp32 [B,H,T] scratch; dq_accum: fp32 [B,T,H*64] scratch (NULL selects the slower two-kernel variant) */
+int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum,
+                  void* dqkv, int B, int H, int T, float scale, void* stream);
 int svit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd,
                        int M, int D, float eps, void* stream);
 int svit_layernorm_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,

@@ -40,8 +40,9 @@ def run(B, H, T, bench=False):
     # backward
     dout = (torch.randn(B, T, inner, device=dev)).bfloat16()
     delta = torch.zeros(B, H, T, device=dev)
+    dqacc = torch.empty(B, T, inner, device=dev)
     dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
-    rc = lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, H, T, scale, st())
+    rc = lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, scale, st())
     assert rc == 0, lib.svit_last_error()
     torch.cuda.synchronize()
     ref.backward(dout.float())
@@ -60,7 +61,7 @@ def run(B, H, T, bench=False):
             print("#bad", bad.shape[0], bad[:10].tolist(), bad[-5:].tolist())
     if bench:
         for name, f in (("fwd", lambda: lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, scale, st())),
-                        ("bwd", lambda: lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, H, T, scale, st()))):
+                        ("bwd", lambda: lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, scale, st()))):
             for _ in range(3): f()
             a = torch.cuda.Event(enable_timing=True); bb = torch.cuda.Event(enable_timing=True)
             a.record()

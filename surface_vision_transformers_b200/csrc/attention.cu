@@ -491,6 +491,284 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
 }
 
 // =================================================================================================
+// backward, fused: one CTA per (sample, head, key block); two CTAs resident per SM (<= 256 TMEM columns and
+// < 100 KB shared memory each) so one CTA's MMAs overlap the other's exp / dS arithmetic.
+//   per query block i:   S = Q_i K_j^T            -> P = exp(S*scale - lse)           (registers + smem tile)
+//                        dV_j += P^T dO_i ;  dP = dO_i V_j^T  (dP re-uses the TMEM columns of S)
+//                        dS = P * (dP - delta) * scale                                 (same smem tile)
+//                        dK_j += dS^T Q_i ;  dQ_part = dS K_j (TMEM cols of S again)  -> fp32 red.add into dq_accum
+// smem: sK | sV | sQ | sdO (16K each) | PS 32K | barriers.   TMEM: S/dP/dQpart [0,128) dK [128,192) dV [192,256)
+// =================================================================================================
+constexpr int BF_SK = 0;
+constexpr int BF_SV = BF_SK + TILE_BYTES;
+constexpr int BF_SQ = BF_SV + TILE_BYTES;
+constexpr int BF_SDO = BF_SQ + TILE_BYTES;
+constexpr int BF_PS = BF_SDO + TILE_BYTES;
+constexpr int BF_BAR = BF_PS + 2 * TILE_BYTES;
+constexpr int BF_SMEM = 1024 + BF_BAR + 128;
+constexpr int BF_THREADS = 288;  // 8 compute warps + 1 control warp
+
+struct AttnBwdFusedArgs {
+    CUtensorMap tmQKV;   // (3*inner, T, B) bf16 box 64x128x1 (loads)
+    CUtensorMap tmDO;    // (inner, T, B) bf16 box 64x128x1
+    CUtensorMap tmDQKV;  // (3*inner, T, B) bf16 box 64x128x1 (stores of dK, dV)
+    const float* lse;
+    const float* delta;
+    float* dq_accum;     // fp32 [B, T, inner], zeroed by the launcher
+    int B, H, T;
+    float scale, scale_log2e;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(BF_THREADS, 2) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem + BF_SK;
+    uint8_t* sV = smem + BF_SV;
+    uint8_t* sQ = smem + BF_SQ;
+    uint8_t* sdO = smem + BF_SDO;
+    uint8_t* sPS = smem + BF_PS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BF_BAR);
+    uint64_t* bar_kv = bars + 0;
+    uint64_t* bar_qdo = bars + 1;
+    uint64_t* bar_s = bars + 2;
+    uint64_t* bar_p = bars + 3;
+    uint64_t* bar_dp = bars + 4;
+    uint64_t* bar_ds = bars + 5;
+    uint64_t* bar_dq = bars + 6;
+    uint64_t* bar_dqr = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int T = args.T, H = args.H;
+    const int inner = H * 64;
+    const int nblk = (T + 127) / 128;
+    const int j = blockIdx.x % nblk;  // key block
+    const int bh = blockIdx.x / nblk;
+    const int b = bh / H, h = bh % H;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&args.tmQKV);
+        tma_prefetch_desc(&args.tmDO);
+        tma_prefetch_desc(&args.tmDQKV);
+        mbar_init(bar_kv, 1);
+        mbar_init(bar_qdo, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, 256);
+        mbar_init(bar_dp, 1);
+        mbar_init(bar_ds, 256);
+        mbar_init(bar_dq, 1);
+        mbar_init(bar_dqr, 256);
+        fence_mbar_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ================================ control: TMA + MMA issue ================================
+        if (elect_one()) {
+            const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            const uint32_t ps_addr = smem_u32(sPS);
+            const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S / dP : K-major x K-major
+            const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);   // dK / dV: A = P^T / dS^T (MN-major), B MN-major
+            const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ    : A = dS (K-major), B = K (MN-major)
+            mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
+            tma_load_3d(sK, &args.tmQKV, bar_kv, inner + h * 64, j * 128, b);
+            tma_load_3d(sV, &args.tmQKV, bar_kv, 2 * inner + h * 64, j * 128, b);
+            mbar_expect_tx(bar_qdo, 2 * TILE_BYTES);
+            tma_load_3d(sQ, &args.tmQKV, bar_qdo, h * 64, 0, b);
+            tma_load_3d(sdO, &args.tmDO, bar_qdo, h * 64, 0, b);
+            mbar_wait(bar_kv, 0);
+            for (int i = 0; i < nblk; ++i) {
+                const uint32_t ph = i & 1;
+                mbar_wait(bar_qdo, ph);
+                if (i > 0) mbar_wait(bar_dqr, (i - 1) & 1);  // dQ_part of the previous pair drained from TMEM
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_ss(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
+                            idesc_s, k != 0);
+                umma_commit(bar_s);
+                mbar_wait(bar_p, ph);  // P tile in smem, S consumed
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < 8; ++s)  // dV += P^T dO
+                    umma_ss(tmem_base + 192, umma_smem_desc(ps_addr + s * 2048, TILE_BYTES, 1024),
+                            umma_smem_desc(do_addr + s * 2048, 8192, 1024), idesc_tn, (i | s) != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // dP = dO V^T (over the S columns)
+                    umma_ss(tmem_base, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024),
+                            idesc_s, k != 0);
+                umma_commit(bar_dp);
+                mbar_wait(bar_ds, ph);  // dS tile in smem, dP consumed
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < 8; ++s)  // dK += dS^T Q
+                    umma_ss(tmem_base + 128, umma_smem_desc(ps_addr + s * 2048, TILE_BYTES, 1024),
+                            umma_smem_desc(q_addr + s * 2048, 8192, 1024), idesc_tn, (i | s) != 0);
+#pragma unroll
+                for (int s = 0; s < 8; ++s)  // dQ_part = dS K
+                    umma_ss(tmem_base, umma_smem_desc(ps_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024),
+                            umma_smem_desc(k_addr + s * 2048, 8192, 1024), idesc_dq, s != 0);
+                umma_commit(bar_dq);
+                mbar_wait(bar_dq, ph);  // Q_i / dO_i no longer read by the tensor core
+                if (i + 1 < nblk) {
+                    mbar_expect_tx(bar_qdo, 2 * TILE_BYTES);
+                    tma_load_3d(sQ, &args.tmQKV, bar_qdo, h * 64, (i + 1) * 128, b);
+                    tma_load_3d(sdO, &args.tmDO, bar_qdo, h * 64, (i + 1) * 128, b);
+                }
+            }
+        }
+    } else {
+        // ================================ compute warps ================================
+        const int q = warp & 3;      // TMEM lane quadrant
+        const int half = warp >> 2;  // which 64 key columns of the S / dP tile (== which smem tile of PS)
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int kvalid = T - j * 128 - half * 64;  // columns [0, kvalid) of this thread's 64 are real keys
+        uint8_t* tile_row = sPS + half * TILE_BYTES + row * 128;
+        const float c = args.scale_log2e;
+        for (int i = 0; i < nblk; ++i) {
+            const uint32_t ph = i & 1;
+            const int t = i * 128 + row;
+            const bool qvalid = t < T;
+            const size_t sidx = (static_cast<size_t>(b) * H + h) * T + (qvalid ? t : 0);
+            const float lse2 = args.lse[sidx] * 1.4426950408889634f;
+            const float sdelta = args.delta[sidx] * args.scale;
+            uint32_t pk[32];  // P of this thread's 64 columns, packed bf16
+            // ---- P = exp2(S*c - lse2) ----
+            mbar_wait(bar_s, ph);
+            tc_fence_after();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t s[32];
+                tmem_ld_32x32(t_row + half * 64 + hh * 32, s);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float p0 = exp2f(fmaf(__uint_as_float(s[e]), c, -lse2));
+                    float p1 = exp2f(fmaf(__uint_as_float(s[e + 1]), c, -lse2));
+                    if (!qvalid || hh * 32 + e >= kvalid) p0 = 0.0f;
+                    if (!qvalid || hh * 32 + e + 1 >= kvalid) p1 = 0.0f;
+                    pk[hh * 16 + e / 2] = pack_bf16(p0, p1);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 o = make_uint4(pk[hh * 16 + g * 4], pk[hh * 16 + g * 4 + 1], pk[hh * 16 + g * 4 + 2],
+                                               pk[hh * 16 + g * 4 + 3]);
+                    *reinterpret_cast<uint4*>(tile_row + (((hh * 4 + g) ^ (row & 7)) << 4)) = o;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_p);
+            // ---- dS = P * (dP*scale - delta*scale) ----
+            mbar_wait(bar_dp, ph);
+            tc_fence_after();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t dp[32];
+                tmem_ld_32x32(t_row + half * 64 + hh * 32, dp);
+                tmem_ld_wait();
+                uint32_t dsk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const uint32_t pp = pk[hh * 16 + e / 2];
+                    const float d0 = bf16_lo(pp) * fmaf(__uint_as_float(dp[e]), args.scale, -sdelta);
+                    const float d1 = bf16_hi(pp) * fmaf(__uint_as_float(dp[e + 1]), args.scale, -sdelta);
+                    dsk[e / 2] = pack_bf16(d0, d1);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 o = make_uint4(dsk[g * 4], dsk[g * 4 + 1], dsk[g * 4 + 2], dsk[g * 4 + 3]);
+                    *reinterpret_cast<uint4*>(tile_row + (((hh * 4 + g) ^ (row & 7)) << 4)) = o;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_ds);
+            // ---- dQ_part (already scaled through dS) -> fp32 atomics ----
+            mbar_wait(bar_dq, ph);
+            tc_fence_after();
+            {
+                uint32_t dq[32];
+                tmem_ld_32x32(t_row + half * 32, dq);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar_dqr);
+                if (qvalid) {
+                    float* dst = args.dq_accum + (static_cast<size_t>(b) * T + t) * inner + h * 64 + half * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        red_add_v4(dst + e, __uint_as_float(dq[e]), __uint_as_float(dq[e + 1]), __uint_as_float(dq[e + 2]),
+                                   __uint_as_float(dq[e + 3]));
+                }
+            }
+        }
+        // ---- epilogue: half 0 stores dK, half 1 stores dV (bf16, through the PS tiles) ----
+        // the last bar_dq wait above guarantees every accumulate MMA has retired
+        {
+            uint32_t o0[32], o1[32];
+            const uint32_t acc = t_row + 128 + half * 64;
+            tmem_ld_32x32(acc, o0);
+            tmem_ld_32x32(acc + 32, o1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
+                o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
+                o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
+                o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+                *reinterpret_cast<uint4*>(tile_row + ((g ^ (row & 7)) << 4)) = o;
+            }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (threadIdx.x == 0) {
+            tma_store_3d(&args.tmDQKV, sPS, inner + h * 64, j * 128, b);                    // dK
+            tma_store_3d(&args.tmDQKV, sPS + TILE_BYTES, 2 * inner + h * 64, j * 128, b);   // dV
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// dqkv[b, t, 0:inner] = bf16(dq_accum[b, t, :])
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t rows, int inner) {
+    const int per_row = inner >> 2;
+    const size_t total = rows * per_row;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = idx / per_row;
+        const int cidx = static_cast<int>(idx - r * per_row);
+        const float4 v = reinterpret_cast<const float4*>(acc)[idx];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dqkv + r * 3 * inner + cidx * 4) = o;
+    }
+}
+
+// =================================================================================================
 // host
 // =================================================================================================
 static int check_attn_shape(int B, int H, int T) {
@@ -546,7 +824,8 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     if (!configured) {
         cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
         cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaError_t e3 = cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attn_bwd) failed");
             return -10;
         }
@@ -560,6 +839,45 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
         attn_delta_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.out),
                                                           reinterpret_cast<const __nv_bfloat16*>(d.dout), d.delta, d.B,
                                                           d.H, d.T);
+        count_launch();
+    }
+    const int nblk = (d.T + 127) / 128;
+    if (d.dq_accum != nullptr) {
+        AttnBwdFusedArgs a;
+        memset(&a, 0, sizeof(a));
+        int rc = 0;
+        rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
+                           (uint64_t)d.T * 3 * inner * 2, 64, 128);
+        rc |= make_tmap_3d(&a.tmDO, d.dout, TmapDtype::BF16, inner, d.T, d.B, (uint64_t)inner * 2,
+                           (uint64_t)d.T * inner * 2, 64, 128);
+        rc |= make_tmap_3d(&a.tmDQKV, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
+                           (uint64_t)d.T * 3 * inner * 2, 64, 128);
+        if (rc) {
+            set_error("attn_bwd: tensor map creation failed: %s", tmap_last_error());
+            return -3;
+        }
+        a.lse = d.lse;
+        a.delta = d.delta;
+        a.dq_accum = d.dq_accum;
+        a.B = d.B;
+        a.H = d.H;
+        a.T = d.T;
+        a.scale = d.scale;
+        a.scale_log2e = d.scale * 1.4426950408889634f;
+        const size_t rows = static_cast<size_t>(d.B) * d.T;
+        cudaMemsetAsync(d.dq_accum, 0, rows * inner * sizeof(float), stream);
+        attn_bwd_fused_kernel<<<d.B * d.H * nblk, BF_THREADS, BF_SMEM, stream>>>(a);
+        size_t cblocks = (rows * (inner / 4) + 255) / 256;
+        if (cblocks > 148 * 16) cblocks = 148 * 16;
+        attn_dq_convert_kernel<<<static_cast<int>(cblocks), 256, 0, stream>>>(d.dq_accum,
+                                                                             reinterpret_cast<__nv_bfloat16*>(d.dqkv), rows, inner);
+        count_launch(2);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("attn_bwd (fused) launch failed: %s", cudaGetErrorString(e));
+            return -11;
+        }
+        return 0;
     }
     AttnBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -581,10 +899,9 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     a.T = d.T;
     a.scale = d.scale;
     a.scale_log2e = d.scale * 1.4426950408889634f;
-    const int nblk = (d.T + 127) / 128;
     attn_bwd_kernel<false><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
     attn_bwd_kernel<true><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
-    count_launch(3);
+    count_launch(2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("attn_bwd launch failed: %s", cudaGetErrorString(e));

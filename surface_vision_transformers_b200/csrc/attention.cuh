@@ -28,6 +28,7 @@ struct AttnBwdDesc {
     void* dqkv;        // bf16 [B, T, 3*H*64]
     int B, H, T;
     float scale;
+    float* dq_accum;   // fp32 [B, T, H*64] scratch for the fused kernel (nullptr -> two-kernel fallback)
 };
 int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream);
 

@@ -119,8 +119,9 @@ def test_attention_fwd_bwd(env, B, H, T):
     assert rel_l2(lse, torch.logsumexp(dots, -1)) < 1e-3
     dout = torch.randn(B, T, inner, device=dev).bfloat16()
     delta = torch.zeros(B, H, T, device=dev)
+    dqacc = torch.empty(B, T, inner, device=dev)
     dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
-    check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
+    check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
     ref.backward(dout.float())
     torch.cuda.synchronize()
     dref = torch.cat([g.permute(0, 2, 1, 3).reshape(B, T, inner) for g in (q.grad, k.grad, v.grad)], dim=-1)
