@@ -4,6 +4,7 @@
 
 #include <cuda_bf16.h>
 #include <cstring>
+#include <cstdlib>
 
 #include "gemm.cuh"  // set_error
 #include "ptx.cuh"
@@ -491,22 +492,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
 }
 
 // =================================================================================================
-// backward, fused: one CTA per (sample, head, key block); two CTAs resident per SM (<= 256 TMEM columns and
-// < 100 KB shared memory each) so one CTA's MMAs overlap the other's exp / dS arithmetic.
-//   per query block i:   S = Q_i K_j^T            -> P = exp(S*scale - lse)           (registers + smem tile)
-//                        dV_j += P^T dO_i ;  dP = dO_i V_j^T  (dP re-uses the TMEM columns of S)
-//                        dS = P * (dP - delta) * scale                                 (same smem tile)
-//                        dK_j += dS^T Q_i ;  dQ_part = dS K_j (TMEM cols of S again)  -> fp32 red.add into dq_accum
-// smem: sK | sV | sQ | sdO (16K each) | PS 32K | barriers.   TMEM: S/dP/dQpart [0,128) dK [128,192) dV [192,256)
+// backward, fused and software-pipelined: one CTA per (sample, head, key block j).
+//   tensor core (one issuing thread)            compute warps (8 warps, one query row x 64 key columns per thread)
+//   a(i): S  = Q_i K_j^T                         P(i)  = exp2(S*scale*log2e - lse*log2e)      -> smem tile sP
+//   b(i): dP = dO_i V_j^T                        dS(i) = P * (dP*scale - delta*scale)          -> smem tile sdS
+//   c(i): dV_j += P^T dO_i                       dQ(i) : TMEM partial -> fp32 red.add into dq_accum
+//   d(i): dK_j += dS^T Q_i ; dQ_part = dS K_j
+// Issue order  a(0) b(0) | c(i) a(i+1) d(i) b(i+1) | ...  so the MMAs of pair i+1 / the accumulate MMAs of pair i run
+// while the compute warps are still busy with pair i; Q_i / dO_i are double-buffered by a TMA producer warp.
+// smem: sK | sV | sQ[2] | sdO[2] (16K each) | sP 32K | sdS 32K | barriers  (161 KB, 1 CTA / SM)
+// TMEM: S [0,128) dP [128,256) dK [256,320) dV [320,384) dQ_part [384,448)
 // =================================================================================================
 constexpr int BF_SK = 0;
 constexpr int BF_SV = BF_SK + TILE_BYTES;
-constexpr int BF_SQ = BF_SV + TILE_BYTES;
-constexpr int BF_SDO = BF_SQ + TILE_BYTES;
-constexpr int BF_PS = BF_SDO + TILE_BYTES;
-constexpr int BF_BAR = BF_PS + 2 * TILE_BYTES;
-constexpr int BF_SMEM = 1024 + BF_BAR + 128;
-constexpr int BF_THREADS = 288;  // 8 compute warps + 1 control warp
+constexpr int BF_SQ = BF_SV + TILE_BYTES;        // 2 stages
+constexpr int BF_SDO = BF_SQ + 2 * TILE_BYTES;   // 2 stages
+constexpr int BF_SP = BF_SDO + 2 * TILE_BYTES;
+constexpr int BF_SDS = BF_SP + 2 * TILE_BYTES;
+constexpr int BF_BAR = BF_SDS + 2 * TILE_BYTES;
+constexpr int BF_SMEM = 1024 + BF_BAR + 256;
+constexpr int BF_THREADS = 320;  // 8 compute warps + TMA warp + MMA warp
+constexpr int BF_T_S = 0, BF_T_DP = 128, BF_T_DK = 256, BF_T_DV = 320, BF_T_DQ = 384;
 
 struct AttnBwdFusedArgs {
     CUtensorMap tmQKV;   // (3*inner, T, B) bf16 box 64x128x1 (loads)
@@ -517,30 +523,44 @@ struct AttnBwdFusedArgs {
     float* dq_accum;     // fp32 [B, T, inner], zeroed by the launcher
     int B, H, T;
     float scale, scale_log2e;
+    int debug;  // experiment switches (SVIT_ATTN_DEBUG): 1 = skip dQ atomics, 2 = plain stores
 };
+
+__device__ long long g_attn_prof[256];
+#define PROF(slot) do { if ((args.debug & 4) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-__global__ void __launch_bounds__(BF_THREADS, 2) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedArgs args) {
+__global__ void __launch_bounds__(BF_THREADS, 1) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem + BF_SK;
     uint8_t* sV = smem + BF_SV;
     uint8_t* sQ = smem + BF_SQ;
     uint8_t* sdO = smem + BF_SDO;
-    uint8_t* sPS = smem + BF_PS;
+    uint8_t* sP = smem + BF_SP;
+    uint8_t* sdS = smem + BF_SDS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BF_BAR);
     uint64_t* bar_kv = bars + 0;
-    uint64_t* bar_qdo = bars + 1;
-    uint64_t* bar_s = bars + 2;
-    uint64_t* bar_p = bars + 3;
-    uint64_t* bar_dp = bars + 4;
-    uint64_t* bar_ds = bars + 5;
-    uint64_t* bar_dq = bars + 6;
-    uint64_t* bar_dqr = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* qdo_full = bars + 1;    // [2]
+    uint64_t* qdo_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_free = bars + 6;
+    uint64_t* dp_full = bars + 7;
+    uint64_t* dp_free = bars + 8;
+    uint64_t* p_full = bars + 9;
+    uint64_t* p_free = bars + 10;
+    uint64_t* ds_full = bars + 11;
+    uint64_t* d_done = bars + 12;
+    uint64_t* dq_free = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -556,17 +576,23 @@ __global__ void __launch_bounds__(BF_THREADS, 2) attn_bwd_fused_kernel(const __g
         tma_prefetch_desc(&args.tmDO);
         tma_prefetch_desc(&args.tmDQKV);
         mbar_init(bar_kv, 1);
-        mbar_init(bar_qdo, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_p, 256);
-        mbar_init(bar_dp, 1);
-        mbar_init(bar_ds, 256);
-        mbar_init(bar_dq, 1);
-        mbar_init(bar_dqr, 256);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&qdo_full[s], 1);
+            mbar_init(&qdo_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 256);
+        mbar_init(dp_full, 1);
+        mbar_init(dp_free, 256);
+        mbar_init(p_full, 256);
+        mbar_init(p_free, 1);
+        mbar_init(ds_full, 256);
+        mbar_init(d_done, 1);
+        mbar_init(dq_free, 256);
         fence_mbar_init();
     }
-    if (warp == 8) {
-        tmem_alloc(tmem_slot, 256);
+    if (warp == 9) {
+        tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -575,151 +601,221 @@ __global__ void __launch_bounds__(BF_THREADS, 2) attn_bwd_fused_kernel(const __g
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        // ================================ control: TMA + MMA issue ================================
+        // ================================ TMA producer ================================
         if (elect_one()) {
-            const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            const uint32_t ps_addr = smem_u32(sPS);
-            const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S / dP : K-major x K-major
-            const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);   // dK / dV: A = P^T / dS^T (MN-major), B MN-major
-            const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ    : A = dS (K-major), B = K (MN-major)
             mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
             tma_load_3d(sK, &args.tmQKV, bar_kv, inner + h * 64, j * 128, b);
             tma_load_3d(sV, &args.tmQKV, bar_kv, 2 * inner + h * 64, j * 128, b);
-            mbar_expect_tx(bar_qdo, 2 * TILE_BYTES);
-            tma_load_3d(sQ, &args.tmQKV, bar_qdo, h * 64, 0, b);
-            tma_load_3d(sdO, &args.tmDO, bar_qdo, h * 64, 0, b);
-            mbar_wait(bar_kv, 0);
             for (int i = 0; i < nblk; ++i) {
-                const uint32_t ph = i & 1;
-                mbar_wait(bar_qdo, ph);
-                if (i > 0) mbar_wait(bar_dqr, (i - 1) & 1);  // dQ_part of the previous pair drained from TMEM
-                tc_fence_after();
+                const int s = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                mbar_wait(&qdo_empty[s], ph ^ 1);
+                mbar_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
+                tma_load_3d(sQ + s * TILE_BYTES, &args.tmQKV, &qdo_full[s], h * 64, i * 128, b);
+                tma_load_3d(sdO + s * TILE_BYTES, &args.tmDO, &qdo_full[s], h * 64, i * 128, b);
+            }
+        }
+    } else if (warp == 9) {
+        // ================================ MMA issuer ================================
+        if (elect_one()) {
+            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+            const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S / dP : K-major x K-major
+            const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);   // dK / dV: A = P^T / dS^T (MN-major), B MN-major
+            const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ    : A = dS (K-major), B = K (MN-major)
+            auto issue_a = [&](int i) {  // S = Q_i K^T
+                const uint32_t q_addr = smem_u32(sQ + (i & 1) * TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_ss(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
-                            idesc_s, k != 0);
-                umma_commit(bar_s);
-                mbar_wait(bar_p, ph);  // P tile in smem, S consumed
+                    umma_ss(tmem_base + BF_T_S, umma_smem_desc(q_addr + k * 32, 16, 1024),
+                            umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
+                umma_commit(s_full);
+            };
+            auto issue_b = [&](int i) {  // dP = dO_i V^T
+                const uint32_t do_addr = smem_u32(sdO + (i & 1) * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_ss(tmem_base + BF_T_DP, umma_smem_desc(do_addr + k * 32, 16, 1024),
+                            umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
+                umma_commit(dp_full);
+            };
+            PROF(0);
+            mbar_wait(bar_kv, 0);
+            mbar_wait(&qdo_full[0], 0);
+            PROF(1);
+            tc_fence_after();
+            issue_a(0);
+            issue_b(0);
+            PROF(2);
+            for (int i = 0; i < nblk; ++i) {
+                const uint32_t pi = i & 1;
+                const uint32_t q_addr = smem_u32(sQ + (i & 1) * TILE_BYTES);
+                const uint32_t do_addr = smem_u32(sdO + (i & 1) * TILE_BYTES);
+                // c(i): dV += P^T dO_i
+                PROF(10 + i * 10 + 0);
+                mbar_wait(p_full, pi);
+                PROF(10 + i * 10 + 1);
                 tc_fence_after();
 #pragma unroll
-                for (int s = 0; s < 8; ++s)  // dV += P^T dO
-                    umma_ss(tmem_base + 192, umma_smem_desc(ps_addr + s * 2048, TILE_BYTES, 1024),
+                for (int s = 0; s < 8; ++s)
+                    umma_ss(tmem_base + BF_T_DV, umma_smem_desc(p_addr + s * 2048, TILE_BYTES, 1024),
                             umma_smem_desc(do_addr + s * 2048, 8192, 1024), idesc_tn, (i | s) != 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)  // dP = dO V^T (over the S columns)
-                    umma_ss(tmem_base, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024),
-                            idesc_s, k != 0);
-                umma_commit(bar_dp);
-                mbar_wait(bar_ds, ph);  // dS tile in smem, dP consumed
+                umma_commit(p_free);
+                PROF(10 + i * 10 + 2);
+                // a(i+1)
+                if (i + 1 < nblk) {
+                    mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+                    mbar_wait(s_free, pi);
+                    tc_fence_after();
+                    issue_a(i + 1);
+                }
+                // d(i): dK += dS^T Q_i ; dQ_part = dS K
+                PROF(10 + i * 10 + 3);
+                mbar_wait(ds_full, pi);
+                PROF(10 + i * 10 + 4);
+                if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int s = 0; s < 8; ++s)  // dK += dS^T Q
-                    umma_ss(tmem_base + 128, umma_smem_desc(ps_addr + s * 2048, TILE_BYTES, 1024),
+                for (int s = 0; s < 8; ++s)
+                    umma_ss(tmem_base + BF_T_DK, umma_smem_desc(ds_addr + s * 2048, TILE_BYTES, 1024),
                             umma_smem_desc(q_addr + s * 2048, 8192, 1024), idesc_tn, (i | s) != 0);
 #pragma unroll
-                for (int s = 0; s < 8; ++s)  // dQ_part = dS K
-                    umma_ss(tmem_base, umma_smem_desc(ps_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024),
+                for (int s = 0; s < 8; ++s)
+                    umma_ss(tmem_base + BF_T_DQ, umma_smem_desc(ds_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024),
                             umma_smem_desc(k_addr + s * 2048, 8192, 1024), idesc_dq, s != 0);
-                umma_commit(bar_dq);
-                mbar_wait(bar_dq, ph);  // Q_i / dO_i no longer read by the tensor core
+                umma_commit(d_done);
+                umma_commit(&qdo_empty[i & 1]);
+                PROF(10 + i * 10 + 5);
+                // b(i+1)
                 if (i + 1 < nblk) {
-                    mbar_expect_tx(bar_qdo, 2 * TILE_BYTES);
-                    tma_load_3d(sQ, &args.tmQKV, bar_qdo, h * 64, (i + 1) * 128, b);
-                    tma_load_3d(sdO, &args.tmDO, bar_qdo, h * 64, (i + 1) * 128, b);
+                    mbar_wait(dp_free, pi);
+                    tc_fence_after();
+                    issue_b(i + 1);
                 }
             }
         }
     } else {
         // ================================ compute warps ================================
         const int q = warp & 3;      // TMEM lane quadrant
-        const int half = warp >> 2;  // which 64 key columns of the S / dP tile (== which smem tile of PS)
+        const int half = warp >> 2;  // which 64 key columns of the S / dP tile (== which 64-key smem tile)
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int kvalid = T - j * 128 - half * 64;  // columns [0, kvalid) of this thread's 64 are real keys
-        uint8_t* tile_row = sPS + half * TILE_BYTES + row * 128;
+        uint8_t* p_row = sP + half * TILE_BYTES + row * 128;
+        uint8_t* ds_row = sdS + half * TILE_BYTES + row * 128;
         const float c = args.scale_log2e;
-        for (int i = 0; i < nblk; ++i) {
-            const uint32_t ph = i & 1;
+
+        auto dq_readout = [&](int i) {
+            mbar_wait(d_done, i & 1);
+            tc_fence_after();
+            uint32_t dq[32];
+            tmem_ld_32x32(t_row + BF_T_DQ + half * 32, dq);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(dq_free);
             const int t = i * 128 + row;
-            const bool qvalid = t < T;
-            const size_t sidx = (static_cast<size_t>(b) * H + h) * T + (qvalid ? t : 0);
-            const float lse2 = args.lse[sidx] * 1.4426950408889634f;
-            const float sdelta = args.delta[sidx] * args.scale;
-            uint32_t pk[32];  // P of this thread's 64 columns, packed bf16
-            // ---- P = exp2(S*c - lse2) ----
-            mbar_wait(bar_s, ph);
-            tc_fence_after();
+            if (t < T && !(args.debug & 1)) {
+                float* dst = args.dq_accum + (static_cast<size_t>(b) * T + t) * inner + h * 64 + half * 32;
+                if (args.debug & 2) {
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t s[32];
-                tmem_ld_32x32(t_row + half * 64 + hh * 32, s);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float p0 = exp2f(fmaf(__uint_as_float(s[e]), c, -lse2));
-                    float p1 = exp2f(fmaf(__uint_as_float(s[e + 1]), c, -lse2));
-                    if (!qvalid || hh * 32 + e >= kvalid) p0 = 0.0f;
-                    if (!qvalid || hh * 32 + e + 1 >= kvalid) p1 = 0.0f;
-                    pk[hh * 16 + e / 2] = pack_bf16(p0, p1);
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint4 o = make_uint4(pk[hh * 16 + g * 4], pk[hh * 16 + g * 4 + 1], pk[hh * 16 + g * 4 + 2],
-                                               pk[hh * 16 + g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(tile_row + (((hh * 4 + g) ^ (row & 7)) << 4)) = o;
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_p);
-            // ---- dS = P * (dP*scale - delta*scale) ----
-            mbar_wait(bar_dp, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t dp[32];
-                tmem_ld_32x32(t_row + half * 64 + hh * 32, dp);
-                tmem_ld_wait();
-                uint32_t dsk[16];
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const uint32_t pp = pk[hh * 16 + e / 2];
-                    const float d0 = bf16_lo(pp) * fmaf(__uint_as_float(dp[e]), args.scale, -sdelta);
-                    const float d1 = bf16_hi(pp) * fmaf(__uint_as_float(dp[e + 1]), args.scale, -sdelta);
-                    dsk[e / 2] = pack_bf16(d0, d1);
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint4 o = make_uint4(dsk[g * 4], dsk[g * 4 + 1], dsk[g * 4 + 2], dsk[g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(tile_row + (((hh * 4 + g) ^ (row & 7)) << 4)) = o;
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_ds);
-            // ---- dQ_part (already scaled through dS) -> fp32 atomics ----
-            mbar_wait(bar_dq, ph);
-            tc_fence_after();
-            {
-                uint32_t dq[32];
-                tmem_ld_32x32(t_row + half * 32, dq);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(bar_dqr);
-                if (qvalid) {
-                    float* dst = args.dq_accum + (static_cast<size_t>(b) * T + t) * inner + h * 64 + half * 32;
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(dq[e]), __uint_as_float(dq[e + 1]),
+                                                                          __uint_as_float(dq[e + 2]), __uint_as_float(dq[e + 3]));
+                } else {
 #pragma unroll
                     for (int e = 0; e < 32; e += 4)
                         red_add_v4(dst + e, __uint_as_float(dq[e]), __uint_as_float(dq[e + 1]), __uint_as_float(dq[e + 2]),
                                    __uint_as_float(dq[e + 3]));
                 }
             }
+        };
+
+        for (int i = 0; i < nblk; ++i) {
+            const uint32_t pi = i & 1;
+            const int t = i * 128 + row;
+            const bool qvalid = t < T;
+            const size_t sidx = (static_cast<size_t>(b) * H + h) * T + (qvalid ? t : 0);
+            const float lse2 = args.lse[sidx] * 1.4426950408889634f;
+            const float sdelta = args.delta[sidx] * args.scale;
+            const bool full_tile = qvalid && kvalid >= 64;
+            uint32_t pk[32];  // P of this thread's 64 columns, packed bf16
+            // ---- P(i) = exp2(S*c - lse2) ----
+            if (threadIdx.x == 0) PROF(100 + i * 10 + 0);
+            mbar_wait(s_full, pi);
+            if (threadIdx.x == 0) PROF(100 + i * 10 + 1);
+            tc_fence_after();
+            {
+                uint32_t s0[32], s1[32];
+                tmem_ld_32x32(t_row + BF_T_S + half * 64, s0);
+                tmem_ld_32x32(t_row + BF_T_S + half * 64 + 32, s1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(s_free);
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float p0 = ex2_approx(fmaf(__uint_as_float(s0[e]), c, -lse2));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(s0[e + 1]), c, -lse2));
+                    float p2 = ex2_approx(fmaf(__uint_as_float(s1[e]), c, -lse2));
+                    float p3 = ex2_approx(fmaf(__uint_as_float(s1[e + 1]), c, -lse2));
+                    if (!full_tile) {
+                        if (!qvalid || e >= kvalid) p0 = 0.0f;
+                        if (!qvalid || e + 1 >= kvalid) p1 = 0.0f;
+                        if (!qvalid || 32 + e >= kvalid) p2 = 0.0f;
+                        if (!qvalid || 32 + e + 1 >= kvalid) p3 = 0.0f;
+                    }
+                    pk[e / 2] = pack_bf16(p0, p1);
+                    pk[16 + e / 2] = pack_bf16(p2, p3);
+                }
+            }
+            if (i > 0) mbar_wait(p_free, (i - 1) & 1);  // c(i-1) finished reading the P tile
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                *reinterpret_cast<uint4*>(p_row + ((g ^ (row & 7)) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(p_full);
+            if (threadIdx.x == 0) PROF(100 + i * 10 + 2);
+            // ---- dQ read-out of the previous pair (its MMAs had the whole P(i) phase to finish) ----
+            if (i > 0) dq_readout(i - 1);
+            // ---- dS(i) = P * (dP*scale - delta*scale) ----
+            if (threadIdx.x == 0) PROF(100 + i * 10 + 3);
+            mbar_wait(dp_full, pi);
+            if (threadIdx.x == 0) PROF(100 + i * 10 + 4);
+            tc_fence_after();
+            {
+                uint32_t d0[32], d1[32];
+                tmem_ld_32x32(t_row + BF_T_DP + half * 64, d0);
+                tmem_ld_32x32(t_row + BF_T_DP + half * 64 + 32, d1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(dp_free);
+                uint32_t dsk[32];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const uint32_t pa = pk[e / 2], pb = pk[16 + e / 2];
+                    dsk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(d0[e]), args.scale, -sdelta),
+                                           bf16_hi(pa) * fmaf(__uint_as_float(d0[e + 1]), args.scale, -sdelta));
+                    dsk[16 + e / 2] = pack_bf16(bf16_lo(pb) * fmaf(__uint_as_float(d1[e]), args.scale, -sdelta),
+                                                bf16_hi(pb) * fmaf(__uint_as_float(d1[e + 1]), args.scale, -sdelta));
+                }
+                // the dS tile is free: d(i-1) completion was observed in dq_readout(i-1)
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint4 o = make_uint4(dsk[g * 4], dsk[g * 4 + 1], dsk[g * 4 + 2], dsk[g * 4 + 3]);
+                    *reinterpret_cast<uint4*>(ds_row + ((g ^ (row & 7)) << 4)) = o;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(ds_full);
+            if (threadIdx.x == 0) PROF(100 + i * 10 + 5);
         }
-        // ---- epilogue: half 0 stores dK, half 1 stores dV (bf16, through the PS tiles) ----
-        // the last bar_dq wait above guarantees every accumulate MMA has retired
+        dq_readout(nblk - 1);
+        if (threadIdx.x == 0) PROF(150);
+        // ---- epilogue: half 0 stores dK, half 1 stores dV (bf16, staged in the P tiles) ----
+        // d_done of the last pair (observed above) implies every MMA of this CTA has retired
         {
             uint32_t o0[32], o1[32];
-            const uint32_t acc = t_row + 128 + half * 64;
+            const uint32_t acc = t_row + BF_T_DK + half * 64;
             tmem_ld_32x32(acc, o0);
             tmem_ld_32x32(acc + 32, o1);
             tmem_ld_wait();
@@ -731,23 +827,24 @@ __global__ void __launch_bounds__(BF_THREADS, 2) attn_bwd_fused_kernel(const __g
                 o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
                 o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
                 o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-                *reinterpret_cast<uint4*>(tile_row + ((g ^ (row & 7)) << 4)) = o;
+                *reinterpret_cast<uint4*>(p_row + ((g ^ (row & 7)) << 4)) = o;
             }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 256);
         if (threadIdx.x == 0) {
-            tma_store_3d(&args.tmDQKV, sPS, inner + h * 64, j * 128, b);                    // dK
-            tma_store_3d(&args.tmDQKV, sPS + TILE_BYTES, 2 * inner + h * 64, j * 128, b);   // dV
+            tma_store_3d(&args.tmDQKV, sP, inner + h * 64, j * 128, b);                    // dK
+            tma_store_3d(&args.tmDQKV, sP + TILE_BYTES, 2 * inner + h * 64, j * 128, b);   // dV
             tma_store_commit();
             tma_store_wait_all<0>();
+            PROF(151);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 9) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -864,6 +961,10 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
         a.T = d.T;
         a.scale = d.scale;
         a.scale_log2e = d.scale * 1.4426950408889634f;
+        {
+            const char* dbg = getenv("SVIT_ATTN_DEBUG");
+            a.debug = dbg ? atoi(dbg) : 0;
+        }
         const size_t rows = static_cast<size_t>(d.B) * d.T;
         cudaMemsetAsync(d.dq_accum, 0, rows * inner * sizeof(float), stream);
         attn_bwd_fused_kernel<<<d.B * d.H * nblk, BF_THREADS, BF_SMEM, stream>>>(a);
@@ -908,6 +1009,10 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
         return -11;
     }
     return 0;
+}
+
+int debug_read_attn_prof(long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, g_attn_prof, sizeof(long long) * (n < 256 ? n : 256)) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace svit

@@ -15,6 +15,7 @@
 namespace svit {
 const char* last_error();
 unsigned long long launch_count();
+int debug_read_attn_prof(long long* out, int n);
 }
 using namespace svit;
 
@@ -286,6 +287,7 @@ extern "C" {
 const char* svit_last_error(void) { return svit::last_error(); }
 int svit_version(void) { return 100; }
 unsigned long long svit_launch_count(void) { return svit::launch_count(); }
+int svit_debug_attn_prof(long long* host_out, int n) { return svit::debug_read_attn_prof(host_out, n); }
 
 svit_engine* svit_create(const svit_config* cfg) {
     if (cfg == nullptr) {
