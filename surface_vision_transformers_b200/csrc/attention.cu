@@ -18,14 +18,21 @@ constexpr int TILE_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 // =================================================================================================
 // forward
 // =================================================================================================
-// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sP 96K | barriers
+// One CTA per (sample, head); K and V (<= 384 keys) stay in shared memory, Q blocks of 128 rows stream through.
+// TMEM reads cost 64 B/clk/SM, as much as the exponentials themselves, so the scores are read ONCE: the softmax
+// shift is the row's score against key 0 (any shift is exact for softmax; the log-sum-exp is reported with the same
+// shift), and a guard on the row sum falls back to the classic max-shift pass in the (never observed) overflow case.
+// 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the key columns.
+// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sP 96K | sO 16K | row sums / maxima | barriers
 constexpr int FWD_SQ = 0;
 constexpr int FWD_SK = FWD_SQ + TILE_BYTES;
 constexpr int FWD_SV = FWD_SK + 3 * TILE_BYTES;
 constexpr int FWD_SP = FWD_SV + 3 * TILE_BYTES;
-constexpr int FWD_BAR = FWD_SP + 6 * TILE_BYTES;
+constexpr int FWD_SO = FWD_SP + 6 * TILE_BYTES;
+constexpr int FWD_RED = FWD_SO + TILE_BYTES;      // float [2][128]
+constexpr int FWD_BAR = FWD_RED + 2 * 128 * 4;
 constexpr int FWD_SMEM = 1024 + FWD_BAR + 128;
-constexpr int FWD_THREADS = 160;
+constexpr int FWD_THREADS = 288;
 constexpr int FWD_TMEM_O = 384;  // O accumulator columns [384, 448)
 
 struct AttnFwdArgs {
@@ -36,6 +43,12 @@ struct AttnFwdArgs {
     float scale, scale_log2e;
 };
 
+__device__ __forceinline__ float fwd_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -43,6 +56,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     uint8_t* sK = smem + FWD_SK;
     uint8_t* sV = smem + FWD_SV;
     uint8_t* sP = smem + FWD_SP;
+    uint8_t* sO = smem + FWD_SO;
+    float* sRed = reinterpret_cast<float*>(smem + FWD_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
     uint64_t* bar_kv = bars + 0;
     uint64_t* bar_q = bars + 1;
@@ -70,12 +85,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
         mbar_init(bar_kv, 1);
         mbar_init(bar_q, 1);
         mbar_init(bar_s, 1);
-        mbar_init(bar_p, 128);
+        mbar_init(bar_p, 256);
         mbar_init(bar_o, 1);
-        mbar_init(bar_of, 128);
+        mbar_init(bar_of, 256);
         fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ============================ control: TMA + MMA issue ============================
         if (elect_one()) {
             mbar_expect_tx(bar_kv, nkb * 2 * TILE_BYTES);
@@ -132,88 +147,116 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
         }
     } else {
         // ============================ softmax + epilogue warps ============================
-        const int q = warp;  // TMEM lane quadrant
+        const int q = warp & 3;    // TMEM lane quadrant
+        const int hf = warp >> 2;  // key-column half
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const bool leader = threadIdx.x == 0;
         const float c = args.scale_log2e;
-        for (int i = 0; i < nqb; ++i) {
-            const uint32_t ph = i & 1;
-            mbar_wait(bar_s, ph);
-            tc_fence_after();
-            // ---- pass 1: row maximum over the valid keys ----
-            float mx = -INFINITY;
-            for (int c0 = 0; c0 < tk; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
-            }
-            // the previous block's O tile was staged in sP: make sure its TMA store finished reading
-            if (i > 0) {
-                if (leader) tma_store_wait_read<0>();
-                named_bar_sync(1, 128);
-            }
-            // ---- pass 2: p = exp2((s - max) * scale*log2e), row sum, P -> smem (bf16, K-major swizzled) ----
-            const float mc = mx * c;
+        const int split = (tk / 2) & ~31;                 // half 0: columns [0, split), half 1: [split, tk)
+        const int col_lo = hf == 0 ? 0 : split;
+        const int col_hi = hf == 0 ? split : tk;
+
+        // exp2((s - shift) * c) of this thread's columns -> bf16 P tile in smem; returns the partial row sum
+        auto softmax_pass = [&](float shift_c) {
             float sum = 0.0f;
-            for (int c0 = 0; c0 < tk; c0 += 32) {
+            for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_row + c0, r);
                 tmem_ld_wait();
-                float p[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = exp2f(__uint_as_float(r[j]) * c - mc);
-                    p[j] = (c0 + j < T) ? e : 0.0f;
-                }
                 uint8_t* prow = sP + (c0 >> 6) * TILE_BYTES + row * 128;
                 const int cb = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group (0 or 4)
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
+                    float pv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int col = c0 + g * 8 + e;
+                        const float ex = fwd_ex2(fmaf(__uint_as_float(r[g * 8 + e]), c, -shift_c));
+                        pv[e] = (col < T && col < col_hi) ? ex : 0.0f;
+                    }
                     uint4 o;
-                    o.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
-                    o.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
-                    o.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
-                    o.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
+                    o.x = pack_bf16(pv[0], pv[1]);
+                    o.y = pack_bf16(pv[2], pv[3]);
+                    o.z = pack_bf16(pv[4], pv[5]);
+                    o.w = pack_bf16(pv[6], pv[7]);
                     // the row sum uses the bf16-rounded probabilities that the PV product will see
                     sum += bf16_lo(o.x) + bf16_hi(o.x) + bf16_lo(o.y) + bf16_hi(o.y) + bf16_lo(o.z) + bf16_hi(o.z) +
                            bf16_lo(o.w) + bf16_hi(o.w);
+                    // a 32-column group that straddles col_hi belongs to this half only up to col_hi; the other
+                    // half never writes these chunks (its range starts at a multiple of 32)
                     *reinterpret_cast<uint4*>(prow + (((cb + g) ^ (row & 7)) << 4)) = o;
                 }
+            }
+            return sum;
+        };
+
+        for (int i = 0; i < nqb; ++i) {
+            const uint32_t ph = i & 1;
+            mbar_wait(bar_s, ph);
+            tc_fence_after();
+            // ---- single pass with the score against key 0 as the softmax shift ----
+            float shift = __uint_as_float(tmem_ld_32x1(t_row));
+            tmem_ld_wait();
+            float part = softmax_pass(shift * c);
+            sRed[hf * 128 + row] = part;
+            bool bad = named_bar_or(1, 256, false);  // (barrier only: make both halves' partial sums visible)
+            float total = sRed[row] + sRed[128 + row];
+            bad = !(total > 0.0f && total < 1e30f);
+            if (named_bar_or(2, 256, bad)) {
+                // ---- fallback (uniform for the CTA): classic max-shifted softmax ----
+                float mx = -INFINITY;
+                for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < T && c0 + j < col_hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+                }
+                sRed[hf * 128 + row] = mx;
+                named_bar_sync(1, 256);
+                shift = fmaxf(sRed[row], sRed[128 + row]);
+                named_bar_sync(2, 256);
+                part = softmax_pass(shift * c);
+                sRed[hf * 128 + row] = part;
+                named_bar_sync(1, 256);
+                total = sRed[row] + sRed[128 + row];
+                named_bar_sync(2, 256);
             }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(bar_p);
-            // ---- epilogue: O / sum -> bf16 -> staging (first tile of sP) -> TMA store ----
+            // ---- epilogue: O / sum -> bf16 -> staging -> TMA store (each half converts 32 of the 64 columns) ----
             mbar_wait(bar_o, ph);
             tc_fence_after();
-            const float inv = 1.0f / sum;
-            uint32_t o0[32], o1[32];
-            tmem_ld_32x32(t_row + FWD_TMEM_O, o0);
-            tmem_ld_32x32(t_row + FWD_TMEM_O + 32, o1);
+            const float inv = 1.0f / total;
+            uint32_t o0[32];
+            tmem_ld_32x32(t_row + FWD_TMEM_O + hf * 32, o0);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar_of);
-            uint8_t* orow = sP + row * 128;
+            if (i > 0) {
+                if (leader) tma_store_wait_read<0>();  // previous O tile left the staging buffer
+                named_bar_sync(1, 256);
+            }
+            uint8_t* orow = sO + row * 128;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t* src = &o0[g * 8];
                 uint4 o;
                 o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
                 o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
                 o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
                 o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-                *reinterpret_cast<uint4*>(orow + ((g ^ (row & 7)) << 4)) = o;
+                *reinterpret_cast<uint4*>(orow + (((hf * 4 + g) ^ (row & 7)) << 4)) = o;
             }
             const int t = i * 128 + row;
-            if (t < T) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = mx * args.scale + logf(sum);
+            if (hf == 0 && t < T) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = shift * args.scale + logf(total);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(2, 256);
             if (leader) {
-                tma_store_3d(&args.tmO, sP, h * 64, i * 128, b);
+                tma_store_3d(&args.tmO, sO, h * 64, i * 128, b);
                 tma_store_commit();
             }
         }
@@ -221,7 +264,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
