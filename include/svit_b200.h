@@ -130,6 +130,9 @@ int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void
                  int out_f32, int num_sms, void* stream);
 int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int K, int ldy, int ldx, int ldw,
                     int num_sms, void* stream);
+/* same, and dbias[N] += sum over the M rows of dY (bias gradient of the Linear, fused as one extra MMA) */
+int svit_gemm_wgrad_bias(const void* dY, const void* X, float* dW, float* dbias, int M, int N, int K, int ldy, int ldx,
+                         int ldw, int num_sms, void* stream);
 int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, float scale, void* stream);
 /* delta: fp32 [B,H,T] scratch; dq_accum: fp32 [B,T,H*64] scratch (NULL selects the slower two-kernel variant) */
 int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum,

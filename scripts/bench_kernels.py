@@ -55,6 +55,8 @@ if "wgrad" in which:
         dY = (torch.randn(M, N, device=dev) * 0.5).bfloat16(); X = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
         dW = torch.zeros(N, K, device=dev)
         timeit(f"wgrad dW[{N},{K}]", lambda: lib.svit_gemm_wgrad(ptr(dY), ptr(X), ptr(dW), M, N, K, N, K, K, SMS, st()), bytes_=M*(N+K)*2, flops=2.0*M*N*K)
+        db = torch.zeros(N, device=dev)
+        timeit(f"wgrad dW[{N},{K}] + bias", lambda: lib.svit_gemm_wgrad_bias(ptr(dY), ptr(X), ptr(dW), ptr(db), M, N, K, N, K, K, SMS, st()), bytes_=M*(N+K)*2, flops=2.0*M*N*K)
 if "attn" in which:
     inner = H * 64
     qkv = torch.randn(B, T, 3 * inner, device=dev).bfloat16(); out = torch.empty(B, T, inner, device=dev, dtype=torch.bfloat16)

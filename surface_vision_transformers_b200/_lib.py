@@ -53,6 +53,7 @@ SIGNATURES = {
     "svit_sgd_step": (ci, [vp, vp, vp, cll, cf, cf, cf, cf, ci, ci, cf, vp]),
     "svit_gemm_tn": (ci, [vp] * 7 + [ci] * 10 + [vp]),
     "svit_gemm_wgrad": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),
+    "svit_gemm_wgrad_bias": (ci, [vp, vp, vp, vp] + [ci] * 7 + [vp]),
     "svit_attn_fwd": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
     "svit_attn_bwd": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, vp]),
     "svit_layernorm_fwd": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, cf, vp]),

@@ -161,8 +161,8 @@ static int gemm(const svit_engine* e, cudaStream_t st, const void* A, int lda, c
     return launch_gemm_tn(d, e->num_sms, st);
 }
 static int wgrad(const svit_engine* e, cudaStream_t st, const void* dY, int ldy, const void* X, int ldx, float* dW, int ldw,
-                 int M, int N, int K) {
-    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw};
+                 int M, int N, int K, float* dbias = nullptr) {
+    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw, dbias};
     return launch_gemm_wgrad(d, e->num_sms, st);
 }
 
@@ -239,11 +239,10 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_DGELU,
                     0, nullptr, L.u));
         RET_IF(wgrad(e, st, w.g16, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp));
-        RET_IF(launch_colsum_bf16(w.du, gp(FC1_B), M, mlp, mlp, st));
         // da2 = du W1
         RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, M, D, mlp,
                     EPI_STORE, 0));
-        RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D));
+        RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D, gp(FC1_B)));  // + d fc1_b = colsum(du)
         // g_mid = g + LN2'(da2) ; colsum(g_mid) = d out_b
         RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, w.g16, gp(LN2_W), gp(LN2_B), gp(OUT_B), M, D,
                              st));
@@ -513,8 +512,7 @@ int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void
     float* gmt = gbdec + K;
     RET_IF(launch_mpp_loss_bwd(batch_out, K, input, mask, coef, w.dy, Kd, B, e->C, e->N, e->V, st));
     // decoder grads
-    RET_IF(wgrad(e, st, w.dy, Kd, w.xL16, D, gWdec, D, M, K, D));
-    RET_IF(launch_colsum_bf16(w.dy, gbdec, M, K, Kd, st));
+    RET_IF(wgrad(e, st, w.dy, Kd, w.xL16, D, gWdec, D, M, K, D, gbdec));  // + d to_original.bias = colsum(dy)
     // g = dy Wdec   (A = dy [M, K] pitch Kd, B = WdecT [D, K] pitch Kd)
     RET_IF(gemm(e, st, w.dy, Kd, shp(msh, e->msh_wdecT), Kd, w.g, D, M, D, K, EPI_STORE, 1));
     RET_IF(launch_cast_bf16(w.g, w.g16, static_cast<size_t>(M) * D, st));
@@ -553,7 +551,12 @@ int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void
 }
 int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int K, int ldy, int ldx, int ldw, int num_sms,
                     void* stream) {
-    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw};
+    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw, nullptr};
+    return launch_gemm_wgrad(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_gemm_wgrad_bias(const void* dY, const void* X, float* dW, float* dbias, int M, int N, int K, int ldy, int ldx,
+                         int ldw, int num_sms, void* stream) {
+    GemmWgradDesc d{dY, X, dW, M, N, K, ldy, ldx, ldw, dbias};
     return launch_gemm_wgrad(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
 }
 int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, float scale, void* stream) {

@@ -463,27 +463,49 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight-gradient GEMM: dW[N,K] += dY[M,N]^T X[M,K]
+// weight-gradient GEMM: R[p, q] += sum_t P[t, p] * Q[t, q]      (reduction over the token axis t)
+//
+// Both operands are read MN-major straight from the row-major activations (no transposes).  A CTA pair
+// (cta_group::2) owns a 256 (p) x 384 (q) tile of R for one slice of the token axis: every CTA stages its own 128
+// p-columns and half of the q-columns per 64-token block, the leader issues an N=256 and an N=128 MMA per 16 tokens
+// (384 fp32 accumulator columns in each CTA's TMEM), and the partial tile is added to global memory with fp32
+// reductions.  The big tile matters more than anything else here: the kernel is bound by the L2 -> SM feed
+// (~45 B/clk/SM), and 256x384 needs 52 B/clk at full tensor rate where the former 128x192 tile needed 107.
+// The bias gradient (column sums of P) rides along as one extra N=16 MMA against a constant tile of ones.
+// The host picks which of dY / X plays P so that tiles are full; strides (ld_p, ld_q) make either orientation
+// land in dW[N, K].
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_THREADS = 192;
-constexpr int WG_BN = 192;  // tile over the K (input-feature) axis of dW
+constexpr int WG_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int WG_STAGES = 5;
-constexpr int WG_A_BYTES = 64 * 128 * 2;    // 64 tokens x 128 out-features
-constexpr int WG_B_BYTES = 64 * WG_BN * 2;  // 64 tokens x 192 in-features
-constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
-constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
+constexpr int WG_BOX_BYTES = 64 * 64 * 2;           // one TMA box: 64 tokens x 64 features
+constexpr int WG_P_BYTES = 2 * WG_BOX_BYTES;        // 64 tokens x 128 p-features per CTA
+constexpr int WG_Q_BYTES = 3 * WG_BOX_BYTES;        // 64 tokens x up to 192 q-features per CTA
+constexpr int WG_STAGE_BYTES = WG_P_BYTES + WG_Q_BYTES;
+constexpr int WG_ONES_BYTES = 4096;
+constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 256;
+constexpr int WG_TP = 256;        // tile rows (p), pair-wide
+constexpr int WG_TQ = 384;        // tile columns (q)
+constexpr int WG_ONES_COL = 384;  // TMEM column of the bias accumulator
 
 struct WgArgs {
-    CUtensorMap tmY, tmX;
-    float* dW;
-    int M, N, K, ldw;
+    CUtensorMap tmP, tmQ;
+    float* R;
+    float* dbias;         // [Pdim] or nullptr: += column sums of P (added by the q-tile 0 CTAs only)
+    long long ld_p, ld_q;  // R[p, q] lives at R + p * ld_p + q * ld_q
+    int M, Pdim, Qdim;
+    int tiles_q;
     int kb_per_split;
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_constant__ WgArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint8_t* sOnes = smem + WG_STAGES * WG_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + WG_ONES_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + WG_STAGES;
     uint64_t* done_bar = bars + 2 * WG_STAGES;
@@ -491,17 +513,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_k = (args.K + WG_BN - 1) / WG_BN;
-    const int n0 = (blockIdx.x / tiles_k) * 128;
-    const int k0 = (blockIdx.x % tiles_k) * WG_BN;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool is_leader = cta_rank == 0;
+    const int tile = blockIdx.x >> 1;
+    const int p0 = (tile / args.tiles_q) * WG_TP;
+    const int q0 = (tile % args.tiles_q) * WG_TQ;
+    const int nq = min(args.Qdim - q0, WG_TQ);  // valid q columns of this tile
+    const int n_mma0 = nq > 128 ? 256 : 128;    // N of the first MMA; the second one (N = 128) covers q >= 256
+    const bool has_mma1 = nq > 256;
+    const int q_boxes = (n_mma0 >> 7) + (has_mma1 ? 1 : 0);
+    const bool with_bias = args.dbias != nullptr && q0 == 0;
     const int total_kb = (args.M + 63) / 64;
     const int kb_begin = blockIdx.y * args.kb_per_split;
     const int kb_end = min(total_kb, kb_begin + args.kb_per_split);
     const int num_kb = kb_end - kb_begin;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&args.tmY);
-        tma_prefetch_desc(&args.tmX);
+        tma_prefetch_desc(&args.tmP);
+        tma_prefetch_desc(&args.tmQ);
         for (int i = 0; i < WG_STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -509,30 +538,38 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
         mbar_init(done_bar, 1);
         fence_mbar_init();
     }
+    // constant tile of bf16 ones (0x3F80): B operand of the bias MMA; every layout of it reads the same
+    for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += WG_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 256);
-        tmem_relinquish();
+        tmem_alloc_2cta(tmem_slot, 512);
+        tmem_relinquish_2cta();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (num_kb > 0) {
         if (warp == 0) {
             if (elect_one()) {
+                const int pc = p0 + static_cast<int>(cta_rank) * 128;
+                // q columns staged by this CTA: its half of the first MMA's range, then its half of the second's
+                const int qc0 = q0 + static_cast<int>(cta_rank) * (n_mma0 >> 1);
+                const int qc1 = q0 + 256 + static_cast<int>(cta_rank) * 64;
+                const uint32_t stage_tx = static_cast<uint32_t>(WG_P_BYTES + q_boxes * WG_BOX_BYTES);
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+                    if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
                     uint8_t* a = smem + stage * WG_STAGE_BYTES;
-                    uint8_t* b = a + WG_A_BYTES;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) tma_load_2d(a + j * 8192, &args.tmY, &full_bar[stage], n0 + j * 64, kb * 64);
-#pragma unroll
-                    for (int j = 0; j < WG_BN / 64; ++j)
-                        tma_load_2d(b + j * 8192, &args.tmX, &full_bar[stage], k0 + j * 64, kb * 64);
+                    uint8_t* b = a + WG_P_BYTES;
+                    tma_load_2d_2cta(a, &args.tmP, &full_bar[stage], pc, kb * 64);
+                    tma_load_2d_2cta(a + WG_BOX_BYTES, &args.tmP, &full_bar[stage], pc + 64, kb * 64);
+                    tma_load_2d_2cta(b, &args.tmQ, &full_bar[stage], qc0, kb * 64);
+                    if (n_mma0 == 256) tma_load_2d_2cta(b + WG_BOX_BYTES, &args.tmQ, &full_bar[stage], qc0 + 64, kb * 64);
+                    if (has_mma1) tma_load_2d_2cta(b + 2 * WG_BOX_BYTES, &args.tmQ, &full_bar[stage], qc1, kb * 64);
                     if (++stage == WG_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -540,57 +577,80 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
                 }
             }
         } else if (warp == 1) {
-            if (elect_one()) {
-                constexpr uint32_t idesc = umma_idesc_bf16(128, WG_BN, 1, 1);
+            if (is_leader && elect_one()) {
+                const uint32_t idesc0 = umma_idesc_bf16(256, n_mma0, 1, 1);
+                constexpr uint32_t idesc1 = umma_idesc_bf16(256, 128, 1, 1);
+                constexpr uint32_t idesc_ones = umma_idesc_bf16(256, 16, 1, 1);
+                const uint64_t ones_desc = umma_smem_desc(smem_u32(sOnes), 8192, 1024);
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int i = 0; i < num_kb; ++i) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + WG_A_BYTES;
+                    const uint32_t b_addr = a_addr + WG_P_BYTES;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        // MN-major, 128B swizzle: 64-element MN blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO)
+                        // MN-major, 128B swizzle: 64-feature blocks 8192 B apart (LBO), 8-token groups 1024 B apart (SBO)
+                        const uint32_t acc = (i | k) != 0 ? 1u : 0u;
                         const uint64_t ad = umma_smem_desc(a_addr + k * 2048, 8192, 1024);
-                        const uint64_t bd = umma_smem_desc(b_addr + k * 2048, 8192, 1024);
-                        umma_ss(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+                        umma_ss_2cta(tmem_base, ad, umma_smem_desc(b_addr + k * 2048, 8192, 1024), idesc0, acc);
+                        if (has_mma1)
+                            umma_ss_2cta(tmem_base + 256, ad, umma_smem_desc(b_addr + 2 * WG_BOX_BYTES + k * 2048, 8192, 1024),
+                                         idesc1, acc);
+                        if (with_bias) umma_ss_2cta(tmem_base + WG_ONES_COL, ad, ones_desc, idesc_ones, acc);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    umma_commit_2cta(&empty_bar[stage], 3);
                     if (++stage == WG_STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(done_bar);
+                umma_commit_2cta(done_bar, 3);
             }
         } else {
-            // epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1
-            const int q = warp & 3;
-            const int row = q * 32 + lane;
+            // epilogue: warp w owns TMEM lane quadrant w % 4 (32 p-rows) and one half of the q columns
+            const int quad = warp & 3;
+            const int half = (warp - 2) >> 2;
+            const int p = p0 + static_cast<int>(cta_rank) * 128 + quad * 32 + lane;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
             mbar_wait(done_bar, 0);
             tc_fence_after();
-            const int n = n0 + row;
-            float* dst = args.dW + static_cast<size_t>(n) * args.ldw + k0;
+            const bool p_ok = p < args.Pdim;
+            float* dst = args.R + static_cast<long long>(p) * args.ld_p + static_cast<long long>(q0) * args.ld_q;
+            const bool vec = args.ld_q == 1 && (args.ld_p & 3) == 0 && (args.Qdim & 3) == 0 &&
+                             (reinterpret_cast<uintptr_t>(args.R) & 15) == 0;
+            const int c_begin = half * (WG_TQ / 2), c_end = min(nq, c_begin + WG_TQ / 2);
 #pragma unroll 1
-            for (int c0 = 0; c0 < WG_BN; c0 += 32) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + c0 + (static_cast<uint32_t>(q * 32) << 16), r);
+                tmem_ld_32x32(t_row + c0, r);
                 tmem_ld_wait();
-                if (n < args.N) {
+                if (!p_ok) continue;
+                if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (k0 + c0 + j < args.K) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
-                    }
+                    for (int j = 0; j < 32; j += 4)
+                        if (c0 + j < nq)
+                            red_add_v4(dst + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < nq) atomicAdd(dst + static_cast<long long>(c0 + j) * args.ld_q, __uint_as_float(r[j]));
                 }
+            }
+            if (with_bias && half == 0) {
+                const float s = __uint_as_float(tmem_ld_32x1(t_row + WG_ONES_COL));
+                tmem_ld_wait();
+                if (p_ok) atomicAdd(args.dbias + p, s);
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc_2cta(tmem_base, 512);
     }
 }
 
@@ -709,35 +769,66 @@ int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream) 
         }
         configured = true;
     }
+    // orientation: which operand supplies the 256-row side of the tile.  MMA work of a tile = 256 x (128 | 256 | 384).
+    auto mma_area = [](long long pdim, long long qdim) {
+        const long long tp = (pdim + WG_TP - 1) / WG_TP;
+        const long long full_q = qdim / WG_TQ, rem = qdim % WG_TQ;
+        const long long cols = full_q * WG_TQ + (rem == 0 ? 0 : rem <= 128 ? 128 : rem <= 256 ? 256 : 384);
+        return tp * WG_TP * cols;
+    };
+    const bool transposed = d.dbias == nullptr && mma_area(d.K, d.N) < mma_area(d.N, d.K);
     WgArgs a;
     memset(&a, 0, sizeof(a));
     int rc = 0;
-    rc |= make_tmap_2d(&a.tmY, d.dY, TmapDtype::BF16, d.N, d.M, (uint64_t)d.ldy * 2, 64, 64);
-    rc |= make_tmap_2d(&a.tmX, d.X, TmapDtype::BF16, d.K, d.M, (uint64_t)d.ldx * 2, 64, 64);
+    if (!transposed) {
+        rc |= make_tmap_2d(&a.tmP, d.dY, TmapDtype::BF16, d.N, d.M, (uint64_t)d.ldy * 2, 64, 64);
+        rc |= make_tmap_2d(&a.tmQ, d.X, TmapDtype::BF16, d.K, d.M, (uint64_t)d.ldx * 2, 64, 64);
+        a.Pdim = d.N;
+        a.Qdim = d.K;
+        a.ld_p = d.ldw;
+        a.ld_q = 1;
+    } else {
+        rc |= make_tmap_2d(&a.tmP, d.X, TmapDtype::BF16, d.K, d.M, (uint64_t)d.ldx * 2, 64, 64);
+        rc |= make_tmap_2d(&a.tmQ, d.dY, TmapDtype::BF16, d.N, d.M, (uint64_t)d.ldy * 2, 64, 64);
+        a.Pdim = d.K;
+        a.Qdim = d.N;
+        a.ld_p = 1;
+        a.ld_q = d.ldw;
+    }
     if (rc != 0) {
         set_error("gemm_wgrad: tensor map creation failed: %s", tmap_last_error());
         return -3;
     }
-    a.dW = d.dW;
+    a.R = d.dW;
+    a.dbias = d.dbias;
     a.M = d.M;
-    a.N = d.N;
-    a.K = d.K;
-    a.ldw = d.ldw;
-    const int tiles = ((d.N + 127) / 128) * ((d.K + WG_BN - 1) / WG_BN);
+    a.tiles_q = (a.Qdim + WG_TQ - 1) / WG_TQ;
+    const int tiles = ((a.Pdim + WG_TP - 1) / WG_TP) * a.tiles_q;
     const int total_kb = (d.M + 63) / 64;
-    int splits = (2 * num_sms + tiles - 1) / tiles;
+    int splits = (num_sms / 2) / tiles;  // one CTA pair per SM pair and wave
     if (splits > total_kb) splits = total_kb;
     if (splits < 1) splits = 1;
     a.kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + a.kb_per_split - 1) / a.kb_per_split;
-    dim3 grid(tiles, splits);
-    gemm_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(a);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles * 2, splits);
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = WG_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel, a);
     if (e != cudaSuccess) {
         set_error("gemm_wgrad launch failed: %s", cudaGetErrorString(e));
         return -11;
     }
+    count_launch();
     return 0;
 }
 

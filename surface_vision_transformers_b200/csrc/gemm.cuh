@@ -5,7 +5,8 @@
 //               to_out / FeedForward.net in the reference) and, with a transposed bf16 weight shadow,
 //               for every input-gradient GEMM of loss.backward() (tools/train.py:290).
 //   gemm_wgrad: dW[N,K] += dY[M,N]^T * X[M,K] (both operands MN-major, reduction over the token axis,
-//               split over CTAs, fp32 atomics into the flat gradient buffer).
+//               256x384 CTA-pair tiles split over the token axis, fp32 reductions into the flat gradient
+//               buffer; optionally db[N] += column sums of dY from one extra MMA against a tile of ones).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -44,6 +45,7 @@ struct GemmWgradDesc {
     float* dW;       // fp32 [N, K], pitch ldw; accumulated with atomics (caller zeroes)
     int M, N, K;
     int ldy, ldx, ldw;
+    float* dbias = nullptr;  // fp32 [N] or nullptr: += sum over tokens of dY (the Linear's bias gradient)
 };
 int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream);
 

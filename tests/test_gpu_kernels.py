@@ -93,6 +93,25 @@ def test_gemm_wgrad(env, M, N, K):
     assert rel_l2(dW, dY.float().t() @ X.float()) < 1e-4      # fp32 accumulation of exact bf16 products
 
 
+@pytest.mark.parametrize("M,N,K", [(1284, 1536, 384), (700, 612, 384), (2000, 192, 192), (321, 128, 640), (64, 16, 8)])
+def test_gemm_wgrad_bias(env, M, N, K):
+    """dW and the fused bias gradient (column sums of dY via the ones-tile MMA); ragged pitches (ldy > N)."""
+    dev, lib = env["dev"], env["lib"]
+    torch.manual_seed(M + N + K + 1)
+    ldy = (N + 15) // 8 * 8
+    dYp = torch.zeros(M, ldy, device=dev, dtype=torch.bfloat16)
+    dYp[:, :N] = (torch.randn(M, N, device=dev) * 0.5).bfloat16()
+    dYp[:, N:] = 7.0   # padding columns must never be read into the result
+    X = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    dW = torch.zeros(N, K, device=dev)
+    db = torch.zeros(N, device=dev)
+    check(lib.svit_gemm_wgrad_bias(ptr(dYp), ptr(X), ptr(dW), ptr(db), M, N, K, ldy, K, K, env["sms"], stream()), "wgrad_bias")
+    torch.cuda.synchronize()
+    dY = dYp[:, :N].float()
+    assert rel_l2(dW, dY.t() @ X.float()) < 1e-4
+    assert rel_l2(db, dY.sum(0)) < 1e-4
+
+
 def test_gemm_rejects_bad_pitch(env):
     dev, lib = env["dev"], env["lib"]
     A = torch.zeros(8, 100, device=dev, dtype=torch.bfloat16)
