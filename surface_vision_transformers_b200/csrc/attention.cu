@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
         mbar_init(bar_kv, 1);
         mbar_init(bar_q, 1);
         mbar_init(bar_s, 1);
-        mbar_init(bar_p, 256);
+        mbar_init(bar_p, 8);
         mbar_init(bar_o, 1);
-        mbar_init(bar_of, 256);
+        mbar_init(bar_of, 8);
         fence_mbar_init();
     }
     if (warp == 8) {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_p);
+            mbar_arrive_warp(bar_p);
             // ---- epilogue: O / sum -> bf16 -> staging -> TMA store (each half converts 32 of the 64 columns) ----
             mbar_wait(bar_o, ph);
             tc_fence_after();
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             tmem_ld_32x32(t_row + FWD_TMEM_O + hf * 32, o0);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(bar_of);
+            mbar_arrive_warp(bar_of);
             if (i > 0) {
                 if (leader) tma_store_wait_read<0>();  // previous O tile left the staging buffer
                 named_bar_sync(1, 256);
@@ -271,370 +271,125 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 }
 
 // =================================================================================================
-// backward
+// backward: one CTA per (sample, head), every operand loaded exactly once, no atomics
 // =================================================================================================
-// delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   -- one warp per (b,t) row
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int H, int T) {
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp_global >= B * T) return;
-    const int b = warp_global / T, t = warp_global % T;
-    const size_t base = static_cast<size_t>(warp_global) * H * 64;
-    for (int h = 0; h < H; ++h) {
-        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(out + base + h * 64 + lane * 2);
-        const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(dout + base + h * 64 + lane * 2);
-        float s = __bfloat162float(o2.x) * __bfloat162float(d2.x) + __bfloat162float(o2.y) * __bfloat162float(d2.y);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) delta[(static_cast<size_t>(b) * H + h) * T + t] = s;
-    }
-}
-
-// One kernel, two roles (template DQ):
-//   DQ = false : CTA owns key block j -> accumulates dK_j, dV_j over all query blocks
-//   DQ = true  : CTA owns query block i -> accumulates dQ_i over all key blocks
-// Per step: S = Q K^T, dP = dO V^T (TMEM); threads (one query row each) form P = exp(S*scale - lse) and
-// dS = P * (dP - delta) in bf16 shared memory tiles [query][key]; then the accumulate MMAs read them.
-// smem: sQ | sdO | sK | sV (16K each) | sP 32K | sdS 32K | barriers
-constexpr int BWD_SQ = 0;
-constexpr int BWD_SDO = BWD_SQ + TILE_BYTES;
-constexpr int BWD_SK = BWD_SDO + TILE_BYTES;
-constexpr int BWD_SV = BWD_SK + TILE_BYTES;
-constexpr int BWD_SP = BWD_SV + TILE_BYTES;
-constexpr int BWD_SDS = BWD_SP + 2 * TILE_BYTES;
-constexpr int BWD_BAR = BWD_SDS + 2 * TILE_BYTES;
-constexpr int BWD_SMEM = 1024 + BWD_BAR + 128;
-constexpr int BWD_THREADS = 128;
-// TMEM columns: S [0,128) dP [128,256) acc0 [256,320) acc1 [320,384)
+// Keys are processed in blocks of 96 (j, outer loop, K_j / V_j double-buffered by TMA), queries in blocks of 128
+// (i, inner loop, all Q_i / dO_i resident in shared memory).  With 96-column score tiles everything fits in TMEM:
+//   S [0,96)  dP [96,192)  dK_j [192,256)  dV_j [256,320)  dQ_0..2 [320,512)
+// so dQ accumulates on chip across the key blocks (the former kernel red.add-ed fp32 partials into a global
+// scratch buffer and converted them afterwards).  delta = rowsum(dO * O) is computed in the prologue.
+//
+//   tensor core (one issuing thread)      P warps (4, one query row per thread)    dS warps (4, one query row per thread)
+//   a(p): S  = Q_i K_j^T                  P  = exp2(S*scale*log2e - lse*log2e)     dS = P * (dP*scale - delta*scale)
+//   b(p): dP = dO_i V_j^T                    -> bf16 smem tile sP                     -> bf16 smem tile sdS
+//   c(p): dV_j += P^T dO_i                                                         after the last i of block j:
+//   d(p): dK_j += dS^T Q_i ; dQ_i += dS K_j                                           dK_j, dV_j -> bf16 -> TMA store
+// The two warp groups work on different pairs at the same time (the exponentials of pair p+1 overlap the dS
+// arithmetic of pair p), and the MMAs of both neighbours run underneath.  Two MMA-issuing warps keep the two
+// chains independent: warp X issues a(p+1) | c(p), warp Y issues b(p+1) | d(p).  dK_j / dV_j leave through the dS
+// warps at the start of the next key block (plain 128-byte row stores, nothing to wait for); the same point in
+// time is when block j-1's K/V stage is provably free, so a dS-warp thread also issues the TMA load of block j+1
+// (there is no separate producer warp: X issues the initial loads).
+// The dS tile is double-buffered and the dS warps pull P into registers as soon as it is written, so neither the
+// "d(p) retired -> next dS" nor the "P consumed -> next P" hand-back sits on the critical path.
+// A [128 x 96] bf16 tile occupies one full 64-column swizzled tile plus half of a second one; the two dS buffers
+// share that second tile (buffer 1 lives in its columns 32..63, i.e. 64 bytes into every row).
+// smem: sQ[3] sdO[3] (16K each) | sK,sV x2 stages (12K each) | sP 32K | sdS 16K + 16K + 16K shared | barriers (~225 KB)
+constexpr int BK_KEYS = 96;
+constexpr int BK_KV_TILE = BK_KEYS * 128;  // [96 keys x 64 bf16] swizzled tile
+constexpr int BK_SQ = 0;
+constexpr int BK_SDO = BK_SQ + 3 * TILE_BYTES;
+constexpr int BK_SKV = BK_SDO + 3 * TILE_BYTES;  // stage s: K at + s * 2 * BK_KV_TILE, V right behind it
+constexpr int BK_SP = BK_SKV + 4 * BK_KV_TILE;
+constexpr int BK_SDS = BK_SP + 2 * TILE_BYTES;   // buffer b: keys 0..63 in tile b, keys 64..95 in tile 2 at byte 64 * b of each row
+constexpr int BK_BAR = BK_SDS + 3 * TILE_BYTES;
+constexpr int BK_SMEM = 1024 + BK_BAR + 256;
+constexpr int BK_THREADS = 320;  // MMA warps X and Y, 4 P warps, 4 dS warps (10 warps -> 204 registers per thread)
+constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
-    CUtensorMap tmQKV;   // (3*inner, T, B) bf16 box 64x128x1 (loads)
-    CUtensorMap tmDO;    // (inner, T, B) bf16 box 64x128x1
-    CUtensorMap tmDQKV;  // (3*inner, T, B) bf16 box 64x128x1 (stores)
+    CUtensorMap tmQ;    // qkv  (3*inner, T, B) bf16 box 64 x 128: Q_i loads
+    CUtensorMap tmDO;   // dout (inner, T, B)   bf16 box 64 x 128
+    CUtensorMap tmKV;   // qkv                  bf16 box 64 x 96 : K_j, V_j loads
+    CUtensorMap tmDQ;   // dqkv (3*inner, T, B) bf16 box 64 x 128: dQ_i stores
+    __nv_bfloat16* dqkv;  // dK_j / dV_j rows are stored directly
+    const __nv_bfloat16* out;
+    const __nv_bfloat16* dout;
     const float* lse;
-    const float* delta;
     int B, H, T;
     float scale, scale_log2e;
-};
-
-template <bool DQ>
-__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem + BWD_SQ;
-    uint8_t* sdO = smem + BWD_SDO;
-    uint8_t* sK = smem + BWD_SK;
-    uint8_t* sV = smem + BWD_SV;
-    uint8_t* sP = smem + BWD_SP;
-    uint8_t* sdS = smem + BWD_SDS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_BAR);
-    uint64_t* bar_fix = bars + 0;  // resident operands landed
-    uint64_t* bar_ld = bars + 1;   // streamed operands landed
-    uint64_t* bar_s = bars + 2;    // S and dP ready
-    uint64_t* bar_acc = bars + 3;  // accumulate MMAs retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int T = args.T, H = args.H;
-    const int inner = H * 64;
-    const int nblk = (T + 127) / 128;
-    const int fixed = blockIdx.x % nblk;  // key block (DQ=false) or query block (DQ=true)
-    const int bh = blockIdx.x / nblk;
-    const int b = bh / H, h = bh % H;
-    const bool t0 = threadIdx.x == 0;
-
-    if (t0) {
-        tma_prefetch_desc(&args.tmQKV);
-        tma_prefetch_desc(&args.tmDO);
-        tma_prefetch_desc(&args.tmDQKV);
-        mbar_init(bar_fix, 1);
-        mbar_init(bar_ld, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_acc, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int row = warp * 32 + lane;
-
-    const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-    const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // S / dP : K-major x K-major
-    const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);     // dK / dV: A = P^T/dS^T (MN-major), B MN-major
-    const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);     // dQ    : A = dS (K-major),      B = K MN-major
-
-    if (t0) {
-        mbar_expect_tx(bar_fix, 2 * TILE_BYTES);
-        if (DQ) {
-            tma_load_3d(sQ, &args.tmQKV, bar_fix, h * 64, fixed * 128, b);
-            tma_load_3d(sdO, &args.tmDO, bar_fix, h * 64, fixed * 128, b);
-        } else {
-            tma_load_3d(sK, &args.tmQKV, bar_fix, inner + h * 64, fixed * 128, b);
-            tma_load_3d(sV, &args.tmQKV, bar_fix, 2 * inner + h * 64, fixed * 128, b);
-        }
-    }
-    mbar_wait(bar_fix, 0);
-
-    float lse_r = 0.0f, delta_r = 0.0f;
-    bool qvalid = false;
-    if (DQ) {
-        const int t = fixed * 128 + row;
-        qvalid = t < T;
-        if (qvalid) {
-            lse_r = args.lse[(static_cast<size_t>(b) * H + h) * T + t];
-            delta_r = args.delta[(static_cast<size_t>(b) * H + h) * T + t];
-        }
-    }
-
-    for (int step = 0; step < nblk; ++step) {
-        const uint32_t ph = step & 1;
-        const int qb = DQ ? fixed : step;
-        const int kb = DQ ? step : fixed;
-        if (t0) {
-            mbar_expect_tx(bar_ld, 2 * TILE_BYTES);
-            if (DQ) {
-                tma_load_3d(sK, &args.tmQKV, bar_ld, inner + h * 64, kb * 128, b);
-                tma_load_3d(sV, &args.tmQKV, bar_ld, 2 * inner + h * 64, kb * 128, b);
-            } else {
-                tma_load_3d(sQ, &args.tmQKV, bar_ld, h * 64, qb * 128, b);
-                tma_load_3d(sdO, &args.tmDO, bar_ld, h * 64, qb * 128, b);
-            }
-        }
-        if (!DQ) {
-            const int t = qb * 128 + row;
-            qvalid = t < T;
-            lse_r = qvalid ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] : 0.0f;
-            delta_r = qvalid ? args.delta[(static_cast<size_t>(b) * H + h) * T + t] : 0.0f;
-        }
-        mbar_wait(bar_ld, ph);
-        if (t0) {
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                umma_ss(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
-                        idesc_s, k != 0);
-                umma_ss(tmem_base + 128, umma_smem_desc(do_addr + k * 32, 16, 1024),
-                        umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
-            }
-            umma_commit(bar_s);
-        }
-        mbar_wait(bar_s, ph);
-        tc_fence_after();
-        // ---- P and dS for this (query block, key block) pair ----
-        const float lse2 = lse_r * 1.4426950408889634f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t s[32], dp[32];
-            tmem_ld_32x32(t_row + c0, s);
-            tmem_ld_32x32(t_row + 128 + c0, dp);
-            tmem_ld_wait();
-            float p[32], ds[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const bool valid = qvalid && (kb * 128 + c0 + j < T);
-                const float e = exp2f(__uint_as_float(s[j]) * args.scale_log2e - lse2);
-                p[j] = valid ? e : 0.0f;
-                ds[j] = p[j] * (__uint_as_float(dp[j]) - delta_r);
-            }
-            const int tile = c0 >> 6;
-            const int cb = (c0 & 63) >> 3;
-            uint8_t* prow = sP + tile * TILE_BYTES + row * 128;
-            uint8_t* dsrow = sdS + tile * TILE_BYTES + row * 128;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint4 o;
-                const int sw = ((cb + g) ^ (row & 7)) << 4;
-                if (!DQ) {
-                    o.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
-                    o.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
-                    o.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
-                    o.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
-                    *reinterpret_cast<uint4*>(prow + sw) = o;
-                }
-                o.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]);
-                o.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
-                o.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]);
-                o.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(dsrow + sw) = o;
-            }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (t0) {
-            tc_fence_after();
-            if (DQ) {
-                // dQ += dS K : A = dS [q][key] K-major, B = K [key][d] MN-major, 8 K-steps of 16 keys
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ss(tmem_base + 256, umma_smem_desc(ds_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024),
-                            umma_smem_desc(k_addr + s * 2048, 8192, 1024), idesc_dq, (step | s) != 0);
-            } else {
-                // dV += P^T dO ; dK += dS^T Q : A = [q][key] tiles read MN-major (M = key), B = dO / Q MN-major
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    umma_ss(tmem_base + 320, umma_smem_desc(p_addr + s * 2048, TILE_BYTES, 1024),
-                            umma_smem_desc(do_addr + s * 2048, 8192, 1024), idesc_tn, (step | s) != 0);
-                    umma_ss(tmem_base + 256, umma_smem_desc(ds_addr + s * 2048, TILE_BYTES, 1024),
-                            umma_smem_desc(q_addr + s * 2048, 8192, 1024), idesc_tn, (step | s) != 0);
-                }
-            }
-            umma_commit(bar_acc);
-        }
-        mbar_wait(bar_acc, ph);
-        tc_fence_after();
-    }
-
-    // ---- epilogue: accumulators -> bf16 -> staging (sP) -> TMA store into dqkv ----
-    const int nacc = DQ ? 1 : 2;
-    for (int a = 0; a < nacc; ++a) {
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32(t_row + 256 + a * 64, o0);
-        tmem_ld_32x32(t_row + 256 + a * 64 + 32, o1);
-        tmem_ld_wait();
-        const float sc = (a == 0) ? args.scale : 1.0f;  // dQ and dK carry the softmax scale, dV does not
-        uint8_t* orow = sP + a * TILE_BYTES + row * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(src[0]) * sc, __uint_as_float(src[1]) * sc);
-            o.y = pack_bf16(__uint_as_float(src[2]) * sc, __uint_as_float(src[3]) * sc);
-            o.z = pack_bf16(__uint_as_float(src[4]) * sc, __uint_as_float(src[5]) * sc);
-            o.w = pack_bf16(__uint_as_float(src[6]) * sc, __uint_as_float(src[7]) * sc);
-            *reinterpret_cast<uint4*>(orow + ((g ^ (row & 7)) << 4)) = o;
-        }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (t0) {
-        if (DQ) {
-            tma_store_3d(&args.tmDQKV, sP, h * 64, fixed * 128, b);
-        } else {
-            tma_store_3d(&args.tmDQKV, sP, inner + h * 64, fixed * 128, b);                    // dK
-            tma_store_3d(&args.tmDQKV, sP + TILE_BYTES, 2 * inner + h * 64, fixed * 128, b);   // dV
-        }
-        tma_store_commit();
-        tma_store_wait_all<0>();
-    }
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-// =================================================================================================
-// backward, fused and software-pipelined: one CTA per (sample, head, key block j).
-//   tensor core (one issuing thread)            compute warps (8 warps, one query row x 64 key columns per thread)
-//   a(i): S  = Q_i K_j^T                         P(i)  = exp2(S*scale*log2e - lse*log2e)      -> smem tile sP
-//   b(i): dP = dO_i V_j^T                        dS(i) = P * (dP*scale - delta*scale)          -> smem tile sdS
-//   c(i): dV_j += P^T dO_i                       dQ(i) : TMEM partial -> fp32 red.add into dq_accum
-//   d(i): dK_j += dS^T Q_i ; dQ_part = dS K_j
-// Issue order  a(0) b(0) | c(i) a(i+1) d(i) b(i+1) | ...  so the MMAs of pair i+1 / the accumulate MMAs of pair i run
-// while the compute warps are still busy with pair i; Q_i / dO_i are double-buffered by a TMA producer warp.
-// smem: sK | sV | sQ[2] | sdO[2] (16K each) | sP 32K | sdS 32K | barriers  (161 KB, 1 CTA / SM)
-// TMEM: S [0,128) dP [128,256) dK [256,320) dV [320,384) dQ_part [384,448)
-// =================================================================================================
-constexpr int BF_SK = 0;
-constexpr int BF_SV = BF_SK + TILE_BYTES;
-constexpr int BF_SQ = BF_SV + TILE_BYTES;        // 2 stages
-constexpr int BF_SDO = BF_SQ + 2 * TILE_BYTES;   // 2 stages
-constexpr int BF_SP = BF_SDO + 2 * TILE_BYTES;
-constexpr int BF_SDS = BF_SP + 2 * TILE_BYTES;
-constexpr int BF_BAR = BF_SDS + 2 * TILE_BYTES;
-constexpr int BF_SMEM = 1024 + BF_BAR + 256;
-constexpr int BF_THREADS = 320;  // 8 compute warps + TMA warp + MMA warp
-constexpr int BF_T_S = 0, BF_T_DP = 128, BF_T_DK = 256, BF_T_DV = 320, BF_T_DQ = 384;
-
-struct AttnBwdFusedArgs {
-    CUtensorMap tmQKV;   // (3*inner, T, B) bf16 box 64x128x1 (loads)
-    CUtensorMap tmDO;    // (inner, T, B) bf16 box 64x128x1
-    CUtensorMap tmDQKV;  // (3*inner, T, B) bf16 box 64x128x1 (stores of dK, dV)
-    const float* lse;
-    const float* delta;
-    float* dq_accum;     // fp32 [B, T, inner], zeroed by the launcher
-    int B, H, T;
-    float scale, scale_log2e;
-    int debug;  // experiment switches (SVIT_ATTN_DEBUG): 1 = skip dQ atomics, 2 = plain stores
+    int debug;  // SVIT_ATTN_DEBUG: 4 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
 };
 
 __device__ long long g_attn_prof[256];
 #define PROF(slot) do { if ((args.debug & 4) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
+    return bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
+           bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+}
 
-__global__ void __launch_bounds__(BF_THREADS, 1) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedArgs args) {
+__global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem + BF_SK;
-    uint8_t* sV = smem + BF_SV;
-    uint8_t* sQ = smem + BF_SQ;
-    uint8_t* sdO = smem + BF_SDO;
-    uint8_t* sP = smem + BF_SP;
-    uint8_t* sdS = smem + BF_SDS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BF_BAR);
-    uint64_t* bar_kv = bars + 0;
-    uint64_t* qdo_full = bars + 1;    // [2]
-    uint64_t* qdo_empty = bars + 3;   // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* s_free = bars + 6;
-    uint64_t* dp_full = bars + 7;
-    uint64_t* dp_free = bars + 8;
-    uint64_t* p_full = bars + 9;
-    uint64_t* p_free = bars + 10;
-    uint64_t* ds_full = bars + 11;
-    uint64_t* d_done = bars + 12;
-    uint64_t* dq_free = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint8_t* sQ = smem + BK_SQ;
+    uint8_t* sdO = smem + BK_SDO;
+    uint8_t* sKV = smem + BK_SKV;
+    uint8_t* sP = smem + BK_SP;
+    uint8_t* sdS = smem + BK_SDS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BK_BAR);
+    uint64_t* q_full = bars + 0;     // [3] Q_i and dO_i landed (once per CTA)
+    uint64_t* kv_full = bars + 4;    // [2]
+    uint64_t* s_full = bars + 8;     // S in TMEM                      (MMA -> P warps)
+    uint64_t* s_free = bars + 9;     // S copied to registers          (P warps -> MMA)
+    uint64_t* dp_full = bars + 10;   // dP in TMEM                     (MMA -> dS warps)
+    uint64_t* dp_free = bars + 11;   // dP copied to registers         (dS warps -> MMA)
+    uint64_t* p_full = bars + 12;    // P tile written                 (P warps -> MMA, dS warps)
+    uint64_t* p_free = bars + 13;    // c(p) retired and P re-read     (MMA + dS warps -> P warps)
+    uint64_t* ds_full = bars + 14;   // [2] dS tile p & 1 written      (dS warps -> MMA)
+    uint64_t* ds_free = bars + 16;   // [2] d(p) retired               (MMA -> dS warps)
+    uint64_t* dkv_full = bars + 18;  // dK_j, dV_j final               (MMA -> dS warps)
+    uint64_t* dkv_free = bars + 19;  // dK_j, dV_j copied to registers (dS warps -> MMA)
+    uint64_t* dq_full = bars + 20;   // every MMA of the CTA retired   (MMA -> P warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int T = args.T, H = args.H;
     const int inner = H * 64;
-    const int nblk = (T + 127) / 128;
-    const int j = blockIdx.x % nblk;  // key block
-    const int bh = blockIdx.x / nblk;
-    const int b = bh / H, h = bh % H;
+    const int nqb = (T + 127) / 128;
+    const int nkb = (T + BK_KEYS - 1) / BK_KEYS;
+    const int total = nqb * nkb;
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&args.tmQKV);
+        tma_prefetch_desc(&args.tmQ);
         tma_prefetch_desc(&args.tmDO);
-        tma_prefetch_desc(&args.tmDQKV);
-        mbar_init(bar_kv, 1);
+        tma_prefetch_desc(&args.tmKV);
+        tma_prefetch_desc(&args.tmDQ);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&qdo_full[s], 1);
-            mbar_init(&qdo_empty[s], 1);
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&ds_full[s], 4);
+            mbar_init(&ds_free[s], 1);
         }
+        for (int i = 0; i < 3; ++i) mbar_init(&q_full[i], 1);
         mbar_init(s_full, 1);
-        mbar_init(s_free, 256);
+        mbar_init(s_free, 4);
         mbar_init(dp_full, 1);
-        mbar_init(dp_free, 256);
-        mbar_init(p_full, 256);
-        mbar_init(p_free, 1);
-        mbar_init(ds_full, 256);
-        mbar_init(d_done, 1);
-        mbar_init(dq_free, 256);
+        mbar_init(dp_free, 4);
+        mbar_init(p_full, 4);
+        mbar_init(p_free, 5);
+        mbar_init(dkv_full, 2);
+        mbar_init(dkv_free, 4);
+        mbar_init(dq_full, 1);
         fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == 0) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -643,225 +398,201 @@ __global__ void __launch_bounds__(BF_THREADS, 1) attn_bwd_fused_kernel(const __g
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
-        // ================================ TMA producer ================================
+    auto load_kv = [&](int j) {  // K_j, V_j -> stage j & 1 (called by one thread)
+        const int s = j & 1;
+        uint8_t* dst = sKV + s * 2 * BK_KV_TILE;
+        mbar_expect_tx(&kv_full[s], 2 * BK_KV_TILE);
+        tma_load_3d(dst, &args.tmKV, &kv_full[s], inner + h * 64, j * BK_KEYS, b);
+        tma_load_3d(dst + BK_KV_TILE, &args.tmKV, &kv_full[s], 2 * inner + h * 64, j * BK_KEYS, b);
+    };
+
+    if (warp == 0) {
+        // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
         if (elect_one()) {
-            mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
-            tma_load_3d(sK, &args.tmQKV, bar_kv, inner + h * 64, j * 128, b);
-            tma_load_3d(sV, &args.tmQKV, bar_kv, 2 * inner + h * 64, j * 128, b);
-            for (int i = 0; i < nblk; ++i) {
-                const int s = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
-                mbar_wait(&qdo_empty[s], ph ^ 1);
-                mbar_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
-                tma_load_3d(sQ + s * TILE_BYTES, &args.tmQKV, &qdo_full[s], h * 64, i * 128, b);
-                tma_load_3d(sdO + s * TILE_BYTES, &args.tmDO, &qdo_full[s], h * 64, i * 128, b);
-            }
+            auto load_q = [&](int i) {
+                mbar_expect_tx(&q_full[i], 2 * TILE_BYTES);
+                tma_load_3d(sQ + i * TILE_BYTES, &args.tmQ, &q_full[i], h * 64, i * 128, b);
+                tma_load_3d(sdO + i * TILE_BYTES, &args.tmDO, &q_full[i], h * 64, i * 128, b);
+            };
+            load_q(0);
+            load_kv(0);
+            for (int i = 1; i < nqb; ++i) load_q(i);
+            if (nkb > 1) load_kv(1);
         }
-    } else if (warp == 9) {
-        // ================================ MMA issuer ================================
+    }
+    if (warp < 2) {
+        // ================================ MMA issuers ================================
+        // warp 0 (X): a(p+1) = S, c(p) = dV.   warp 1 (Y): b(p+1) = dP, d(p) = dQ, dK.
+        // Descriptors are (lo, hi) 32-bit pairs; a K-step adds a constant to lo (see ptx.cuh).
         if (elect_one()) {
-            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-            const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S / dP : K-major x K-major
+            const bool X = warp == 0;
+            constexpr uint32_t hi = umma_desc_hi(1024);
             const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);   // dK / dV: A = P^T / dS^T (MN-major), B MN-major
             const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ    : A = dS (K-major), B = K (MN-major)
-            auto issue_a = [&](int i) {  // S = Q_i K^T
-                const uint32_t q_addr = smem_u32(sQ + (i & 1) * TILE_BYTES);
+            // K-major operand tile (Q, dO, K, V): K-step = 32 B;  MN-major operand: K-step = 16 rows = 2048 B
+            const uint32_t kmaj0 = umma_desc_lo(smem_u32(X ? sQ : sdO), 16);          // A of a / b, + slot * TILE
+            const uint32_t kv0 = umma_desc_lo(smem_u32(sKV + (X ? 0 : BK_KV_TILE)), 16);  // B of a (K_j) / b (V_j), + stage
+            const uint32_t tr0 = umma_desc_lo(smem_u32(X ? sP : sdS), TILE_BYTES);    // A of c / dK: P^T / dS^T (+ dS buffer)
+            const uint32_t mn0 = umma_desc_lo(smem_u32(X ? sdO : sQ), 8192);          // B of c / dK: dO_i / Q_i, + slot * TILE
+            const uint32_t dsk0 = umma_desc_lo(smem_u32(sdS), 16);                    // A of dQ: dS, K-major (+ dS buffer)
+            const uint32_t kmn0 = umma_desc_lo(smem_u32(sKV), 8192);                  // B of dQ: K_j MN-major, + stage
+            auto keys_in = [&](int j) { return min(BK_KEYS, T - j * BK_KEYS); };
+            auto rows_in = [&](int i) { return min(128, T - i * 128); };
+            auto issue_ab = [&](int j, int i) {  // X: S = Q_i K_j^T      Y: dP = dO_i V_j^T
+                const uint32_t a_lo = kmaj0 + i * (TILE_BYTES >> 4);
+                const uint32_t b_lo = kv0 + (j & 1) * (2 * BK_KV_TILE >> 4);
+                const uint32_t idesc = umma_idesc_bf16(128, (keys_in(j) + 15) & ~15, 0, 0);
+                const uint32_t d = tmem_base + (X ? BK_T_S : BK_T_DP);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ss(tmem_base + BF_T_S, umma_smem_desc(q_addr + k * 32, 16, 1024),
-                            umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
-                umma_commit(s_full);
+                for (int k = 0; k < 4; ++k) umma_ss_lohi(d, a_lo + k * 2, b_lo + k * 2, hi, idesc, k != 0);
+                umma_commit(X ? s_full : dp_full);
             };
-            auto issue_b = [&](int i) {  // dP = dO_i V^T
-                const uint32_t do_addr = smem_u32(sdO + (i & 1) * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ss(tmem_base + BF_T_DP, umma_smem_desc(do_addr + k * 32, 16, 1024),
-                            umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
-                umma_commit(dp_full);
-            };
-            PROF(0);
-            mbar_wait(bar_kv, 0);
-            mbar_wait(&qdo_full[0], 0);
-            PROF(1);
+            if (X) PROF(0);
+            mbar_wait(&q_full[0], 0);
+            mbar_wait(&kv_full[0], 0);
+            if (X) PROF(1);
             tc_fence_after();
-            issue_a(0);
-            issue_b(0);
-            PROF(2);
-            for (int i = 0; i < nblk; ++i) {
-                const uint32_t pi = i & 1;
-                const uint32_t q_addr = smem_u32(sQ + (i & 1) * TILE_BYTES);
-                const uint32_t do_addr = smem_u32(sdO + (i & 1) * TILE_BYTES);
-                // c(i): dV += P^T dO_i
-                PROF(10 + i * 10 + 0);
-                mbar_wait(p_full, pi);
-                PROF(10 + i * 10 + 1);
-                tc_fence_after();
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ss(tmem_base + BF_T_DV, umma_smem_desc(p_addr + s * 2048, TILE_BYTES, 1024),
-                            umma_smem_desc(do_addr + s * 2048, 8192, 1024), idesc_tn, (i | s) != 0);
-                umma_commit(p_free);
-                PROF(10 + i * 10 + 2);
-                // a(i+1)
-                if (i + 1 < nblk) {
-                    mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-                    mbar_wait(s_free, pi);
+            issue_ab(0, 0);
+            int p = 0;
+            for (int j = 0; j < nkb; ++j) {
+                const int ks_k = (keys_in(j) + 15) >> 4;  // K steps over the keys of this block
+                for (int i = 0; i < nqb; ++i, ++p) {
+                    const uint32_t pp = p & 1;
+                    const bool has_next = p + 1 < total;
+                    const int jn = (i + 1 < nqb) ? j : j + 1;
+                    const int in = (i + 1 < nqb) ? i + 1 : 0;
+                    const int ks_q = (rows_in(i) + 15) >> 4;  // K steps over the queries of this block
+                    if (has_next) {
+                        mbar_wait(X ? s_free : dp_free, pp);
+                        if (in == 0) mbar_wait(&kv_full[jn & 1], (jn >> 1) & 1);
+                        mbar_wait(&q_full[in], 0);
+                        tc_fence_after();
+                        issue_ab(jn, in);
+                    }
+                    if (p < 8) PROF((X ? 10 : 12) + p * 4);
+                    if (X) mbar_wait(p_full, pp);
+                    else mbar_wait(&ds_full[pp], (p >> 1) & 1);
+                    if (p < 8) PROF((X ? 11 : 13) + p * 4);
+                    if (i == 0 && j > 0) mbar_wait(dkv_free, (j - 1) & 1);  // dK_{j-1}, dV_{j-1} were copied out
                     tc_fence_after();
-                    issue_a(i + 1);
-                }
-                // d(i): dK += dS^T Q_i ; dQ_part = dS K
-                PROF(10 + i * 10 + 3);
-                mbar_wait(ds_full, pi);
-                PROF(10 + i * 10 + 4);
-                if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
-                tc_fence_after();
+                    const uint32_t b_lo = mn0 + i * (TILE_BYTES >> 4);
+                    if (X) {
+                        // c(p): dV_j += P^T dO_i
 #pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ss(tmem_base + BF_T_DK, umma_smem_desc(ds_addr + s * 2048, TILE_BYTES, 1024),
-                            umma_smem_desc(q_addr + s * 2048, 8192, 1024), idesc_tn, (i | s) != 0);
+                        for (int s = 0; s < 8; ++s)
+                            if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DV, tr0 + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
+                        umma_commit(p_free);
+                    } else {
+                        // d(p): dQ_i += dS K_j ; dK_j += dS^T Q_i
+                        const uint32_t k_lo = kmn0 + (j & 1) * (2 * BK_KV_TILE >> 4);
 #pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ss(tmem_base + BF_T_DQ, umma_smem_desc(ds_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024),
-                            umma_smem_desc(k_addr + s * 2048, 8192, 1024), idesc_dq, s != 0);
-                umma_commit(d_done);
-                umma_commit(&qdo_empty[i & 1]);
-                PROF(10 + i * 10 + 5);
-                // b(i+1)
-                if (i + 1 < nblk) {
-                    mbar_wait(dp_free, pi);
-                    tc_fence_after();
-                    issue_b(i + 1);
+                        for (int s = 0; s < 6; ++s)
+                            if (s < ks_k)
+                                umma_ss_lohi(tmem_base + BK_T_DQ + i * 64,
+                                             (s < 4 ? dsk0 + pp * (TILE_BYTES >> 4) + s * 2
+                                                    : dsk0 + (2 * TILE_BYTES >> 4) + pp * 4 + (s - 4) * 2),
+                                             k_lo + s * 128, hi, idesc_dq, (j | s) != 0);
+                        // dS^T as MN-major A: keys 0..63 from tile pp, keys 64..127 from the shared tile (LBO spans the gap)
+                        const uint32_t dst_lo = umma_desc_lo(smem_u32(sdS) + pp * TILE_BYTES, (2 - pp) * TILE_BYTES + pp * 64);
+#pragma unroll
+                        for (int s = 0; s < 8; ++s)
+                            if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DK, dst_lo + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
+                        umma_commit(&ds_free[pp]);
+                    }
+                    if (i == nqb - 1) umma_commit(dkv_full);
                 }
             }
+            if (!X) umma_commit(dq_full);
+            if (X) PROF(2);
         }
-    } else {
-        // ================================ compute warps ================================
-        const int q = warp & 3;      // TMEM lane quadrant
-        const int half = warp >> 2;  // which 64 key columns of the S / dP tile (== which 64-key smem tile)
+    } else if (warp < 6) {
+        // ================================ P warps ================================
+        const int q = warp & 3;  // TMEM lane quadrant
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int kvalid = T - j * 128 - half * 64;  // columns [0, kvalid) of this thread's 64 are real keys
-        uint8_t* p_row = sP + half * TILE_BYTES + row * 128;
-        uint8_t* ds_row = sdS + half * TILE_BYTES + row * 128;
         const float c = args.scale_log2e;
-
-        auto dq_readout = [&](int i) {
-            mbar_wait(d_done, i & 1);
-            tc_fence_after();
-            uint32_t dq[32];
-            tmem_ld_32x32(t_row + BF_T_DQ + half * 32, dq);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(dq_free);
+        const int sw = row & 7;
+        float lse2[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
             const int t = i * 128 + row;
-            if (t < T && !(args.debug & 1)) {
-                float* dst = args.dq_accum + (static_cast<size_t>(b) * T + t) * inner + h * 64 + half * 32;
-                if (args.debug & 2) {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(dq[e]), __uint_as_float(dq[e + 1]),
-                                                                          __uint_as_float(dq[e + 2]), __uint_as_float(dq[e + 3]));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        red_add_v4(dst + e, __uint_as_float(dq[e]), __uint_as_float(dq[e + 1]), __uint_as_float(dq[e + 2]),
-                                   __uint_as_float(dq[e + 3]));
-                }
-            }
-        };
-
-        for (int i = 0; i < nblk; ++i) {
-            const uint32_t pi = i & 1;
-            const int t = i * 128 + row;
-            const bool qvalid = t < T;
-            const size_t sidx = (static_cast<size_t>(b) * H + h) * T + (qvalid ? t : 0);
-            const float lse2 = args.lse[sidx] * 1.4426950408889634f;
-            const float sdelta = args.delta[sidx] * args.scale;
-            const bool full_tile = qvalid && kvalid >= 64;
-            uint32_t pk[32];  // P of this thread's 64 columns, packed bf16
-            // ---- P(i) = exp2(S*c - lse2) ----
-            if (threadIdx.x == 0) PROF(100 + i * 10 + 0);
-            mbar_wait(s_full, pi);
-            if (threadIdx.x == 0) PROF(100 + i * 10 + 1);
-            tc_fence_after();
-            {
-                uint32_t s0[32], s1[32];
-                tmem_ld_32x32(t_row + BF_T_S + half * 64, s0);
-                tmem_ld_32x32(t_row + BF_T_S + half * 64 + 32, s1);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(s_free);
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float p0 = ex2_approx(fmaf(__uint_as_float(s0[e]), c, -lse2));
-                    float p1 = ex2_approx(fmaf(__uint_as_float(s0[e + 1]), c, -lse2));
-                    float p2 = ex2_approx(fmaf(__uint_as_float(s1[e]), c, -lse2));
-                    float p3 = ex2_approx(fmaf(__uint_as_float(s1[e + 1]), c, -lse2));
-                    if (!full_tile) {
-                        if (!qvalid || e >= kvalid) p0 = 0.0f;
-                        if (!qvalid || e + 1 >= kvalid) p1 = 0.0f;
-                        if (!qvalid || 32 + e >= kvalid) p2 = 0.0f;
-                        if (!qvalid || 32 + e + 1 >= kvalid) p3 = 0.0f;
-                    }
-                    pk[e / 2] = pack_bf16(p0, p1);
-                    pk[16 + e / 2] = pack_bf16(p2, p3);
-                }
-            }
-            if (i > 0) mbar_wait(p_free, (i - 1) & 1);  // c(i-1) finished reading the P tile
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                *reinterpret_cast<uint4*>(p_row + ((g ^ (row & 7)) << 4)) = o;
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(p_full);
-            if (threadIdx.x == 0) PROF(100 + i * 10 + 2);
-            // ---- dQ read-out of the previous pair (its MMAs had the whole P(i) phase to finish) ----
-            if (i > 0) dq_readout(i - 1);
-            // ---- dS(i) = P * (dP*scale - delta*scale) ----
-            if (threadIdx.x == 0) PROF(100 + i * 10 + 3);
-            mbar_wait(dp_full, pi);
-            if (threadIdx.x == 0) PROF(100 + i * 10 + 4);
-            tc_fence_after();
-            {
-                uint32_t d0[32], d1[32];
-                tmem_ld_32x32(t_row + BF_T_DP + half * 64, d0);
-                tmem_ld_32x32(t_row + BF_T_DP + half * 64 + 32, d1);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(dp_free);
-                uint32_t dsk[32];
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const uint32_t pa = pk[e / 2], pb = pk[16 + e / 2];
-                    dsk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(d0[e]), args.scale, -sdelta),
-                                           bf16_hi(pa) * fmaf(__uint_as_float(d0[e + 1]), args.scale, -sdelta));
-                    dsk[16 + e / 2] = pack_bf16(bf16_lo(pb) * fmaf(__uint_as_float(d1[e]), args.scale, -sdelta),
-                                                bf16_hi(pb) * fmaf(__uint_as_float(d1[e + 1]), args.scale, -sdelta));
-                }
-                // the dS tile is free: d(i-1) completion was observed in dq_readout(i-1)
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint4 o = make_uint4(dsk[g * 4], dsk[g * 4 + 1], dsk[g * 4 + 2], dsk[g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(ds_row + ((g ^ (row & 7)) << 4)) = o;
-                }
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(ds_full);
-            if (threadIdx.x == 0) PROF(100 + i * 10 + 5);
+            lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : 0.0f;
         }
-        dq_readout(nblk - 1);
-        if (threadIdx.x == 0) PROF(150);
-        // ---- epilogue: half 0 stores dK, half 1 stores dV (bf16, staged in the P tiles) ----
-        // d_done of the last pair (observed above) implies every MMA of this CTA has retired
-        {
+        int p = 0;
+        for (int j = 0; j < nkb; ++j) {
+            const int kvalid = min(BK_KEYS, T - j * BK_KEYS);
+#pragma unroll 1
+            for (int i = 0; i < nqb; ++i, ++p) {
+                const bool qvalid = i * 128 + row < T;
+                const bool warp_any = i * 128 + q * 32 < T;  // at least one real query row in this warp
+                const float l2 = i == 0 ? lse2[0] : (i == 1 ? lse2[1] : lse2[2]);
+                uint32_t pk[48];  // P of this thread's 96 columns, packed bf16
+                if (threadIdx.x == 64 && p < 8) PROF(100 + p * 4);
+                mbar_wait(s_full, p & 1);
+                if (threadIdx.x == 64 && p < 8) PROF(101 + p * 4);
+                tc_fence_after();
+                {
+                    // 16-column chunks; the TMEM load of chunk ch+1 is in flight while chunk ch is exponentiated
+                    const int nch = warp_any ? (kvalid + 15) >> 4 : 0;  // chunks that hold real keys (warp-uniform)
+                    const bool full = qvalid && kvalid == BK_KEYS;
+                    uint32_t ca[16], cb[16];
+                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_S, ca);
+#pragma unroll
+                    for (int ch = 0; ch < 6; ++ch) {
+                        uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
+                        uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
+                        if (ch < nch) {
+                            tmem_ld_wait();
+                            if (ch + 1 < nch) {
+                                tmem_ld_32x16(t_row + BK_T_S + (ch + 1) * 16, nxt);
+                            } else {
+                                tc_fence_before();
+                                mbar_arrive_warp(s_free);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 16; e += 2) {
+                                float a0 = ex2_approx(fmaf(__uint_as_float(cur[e]), c, -l2));
+                                float a1 = ex2_approx(fmaf(__uint_as_float(cur[e + 1]), c, -l2));
+                                if (!full) {
+                                    if (!qvalid || ch * 16 + e >= kvalid) a0 = 0.0f;
+                                    if (!qvalid || ch * 16 + e + 1 >= kvalid) a1 = 0.0f;
+                                }
+                                pk[ch * 8 + e / 2] = pack_bf16(a0, a1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) pk[ch * 8 + e] = 0u;
+                        }
+                    }
+                    if (nch == 0) {
+                        tc_fence_before();
+                        mbar_arrive_warp(s_free);
+                    }
+                }
+                if (p > 0) mbar_wait(p_free, (p - 1) & 1);  // c(p-1) retired and the dS warps re-read P(p-1)
+                uint8_t* prow = sP + row * 128;
+#pragma unroll
+                for (int g = 0; g < 12; ++g) {
+                    const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                    *reinterpret_cast<uint4*>(prow + (g >> 3) * TILE_BYTES + (((g & 7) ^ sw) << 4)) = o;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive_warp(p_full);
+                if (threadIdx.x == 64 && p < 8) PROF(102 + p * 4);
+                if (lane == 0 && p < 6) PROF(190 + p * 4 + (warp - 2));
+            }
+        }
+        // ---- epilogue: dQ_i -> bf16 -> staging (sP tiles, then the K/V stage) -> TMA store ----
+        mbar_wait(dq_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < nqb; ++i) {
+            if (i * 128 + q * 32 >= T) continue;  // rows past T are clipped by the store anyway
             uint32_t o0[32], o1[32];
-            const uint32_t acc = t_row + BF_T_DK + half * 64;
-            tmem_ld_32x32(acc, o0);
-            tmem_ld_32x32(acc + 32, o1);
+            tmem_ld_32x32(t_row + BK_T_DQ + i * 64, o0);
+            tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + 32, o1);
             tmem_ld_wait();
+            uint8_t* orow = (i < 2 ? sP + i * TILE_BYTES : sdS) + row * 128;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
@@ -870,41 +601,159 @@ __global__ void __launch_bounds__(BF_THREADS, 1) attn_bwd_fused_kernel(const __g
                 o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
                 o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
                 o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-                *reinterpret_cast<uint4*>(p_row + ((g ^ (row & 7)) << 4)) = o;
+                *reinterpret_cast<uint4*>(orow + ((g ^ sw) << 4)) = o;
             }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (threadIdx.x == 0) {
-            tma_store_3d(&args.tmDQKV, sP, inner + h * 64, j * 128, b);                    // dK
-            tma_store_3d(&args.tmDQKV, sP + TILE_BYTES, 2 * inner + h * 64, j * 128, b);   // dV
+        named_bar_sync(1, 128);
+        if (warp == 2 && lane == 0) {
+            for (int i = 0; i < nqb; ++i)
+                tma_store_3d(&args.tmDQ, i < 2 ? sP + i * TILE_BYTES : sdS, h * 64, i * 128, b);
             tma_store_commit();
             tma_store_wait_all<0>();
-            PROF(151);
+            PROF(3);
         }
+    } else {
+        // ================================ dS warps ================================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int sw = row & 7;
+        // delta * scale of this thread's query rows: rowsum(dO * O) over the 64 head dimensions
+        float sdelta[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int t = i * 128 + row;
+            float acc = 0.0f;
+            if (i < nqb && t < T) {
+                const size_t off = (static_cast<size_t>(b) * T + t) * inner + h * 64;
+                const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
+                const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) acc += dot8_bf16(po[g], pd[g]);
+            }
+            sdelta[i] = acc * args.scale;
+        }
+        // key block j is complete: dK_j, dV_j -> bf16 -> one 128-byte row per thread straight to global memory
+        // (TMEM lane = key index inside the block)
+        auto store_dkv = [&](int j) {
+            const int kv = min(BK_KEYS, T - j * BK_KEYS);
+            mbar_wait(dkv_full, j & 1);
+            tc_fence_after();
+            const bool key_warp = q * 32 < kv;
+#pragma unroll 1
+            for (int a = 0; a < 2; ++a) {  // a = 0: dK_j, a = 1: dV_j
+                uint32_t o0[32], o1[32];
+                if (key_warp) {
+                    tmem_ld_32x32(t_row + BK_T_DK + a * 64, o0);
+                    tmem_ld_32x32(t_row + BK_T_DK + a * 64 + 32, o1);
+                    tmem_ld_wait();
+                }
+                if (a == 1) {
+                    tc_fence_before();
+                    mbar_arrive_warp(dkv_free);
+                }
+                if (key_warp && row < kv) {
+                    uint4* dst = reinterpret_cast<uint4*>(args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner +
+                                                          (1 + a) * inner + h * 64);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
+                        o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
+                        o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
+                        o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+                        dst[g] = o;
+                    }
+                }
+            }
+        };
+        int p = 0;
+        for (int j = 0; j < nkb; ++j) {
+            const int kvalid = min(BK_KEYS, T - j * BK_KEYS);
+#pragma unroll 1
+            for (int i = 0; i < nqb; ++i, ++p) {
+                const bool warp_any = i * 128 + q * 32 < T;
+                const float sd = i == 0 ? sdelta[0] : (i == 1 ? sdelta[1] : sdelta[2]);
+                const uint32_t pp = p & 1;
+                // ---- P(p): smem -> registers right away, so the P warps get their tile back early ----
+                uint32_t pk[48];  // packed bf16 P, overwritten in place by dS
+                if (threadIdx.x == 192 && p < 8) PROF(150 + p * 4);
+                mbar_wait(p_full, pp);
+                {
+                    const uint8_t* prow = sP + row * 128;  // (rows of all-invalid warps hold the zeros the P warps wrote)
+#pragma unroll
+                    for (int g = 0; g < 12; ++g) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(prow + (g >> 3) * TILE_BYTES + (((g & 7) ^ sw) << 4));
+                        pk[g * 4] = v.x;
+                        pk[g * 4 + 1] = v.y;
+                        pk[g * 4 + 2] = v.z;
+                        pk[g * 4 + 3] = v.w;
+                    }
+                }
+                mbar_arrive_warp(p_free);
+                // ---- dS = P * (dP * scale - delta * scale), masked entries of P are exact zeros ----
+                mbar_wait(dp_full, pp);
+                if (threadIdx.x == 192 && p < 8) PROF(151 + p * 4);
+                tc_fence_after();
+                {
+                    // chunks past nch hold P = 0 -> the packed zeros already are the right dS
+                    const int nch = warp_any ? (kvalid + 15) >> 4 : 0;
+                    uint32_t ca[16], cb[16];
+                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_DP, ca);
+#pragma unroll
+                    for (int ch = 0; ch < 6; ++ch) {
+                        uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
+                        uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
+                        if (ch < nch) {
+                            tmem_ld_wait();
+                            if (ch + 1 < nch) {
+                                tmem_ld_32x16(t_row + BK_T_DP + (ch + 1) * 16, nxt);
+                            } else {
+                                tc_fence_before();
+                                mbar_arrive_warp(dp_free);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 16; e += 2) {
+                                const uint32_t pa = pk[ch * 8 + e / 2];
+                                pk[ch * 8 + e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(cur[e]), args.scale, -sd),
+                                                               bf16_hi(pa) * fmaf(__uint_as_float(cur[e + 1]), args.scale, -sd));
+                            }
+                        }
+                    }
+                    if (nch == 0) {
+                        tc_fence_before();
+                        mbar_arrive_warp(dp_free);
+                    }
+                }
+                if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired: this dS buffer may be overwritten
+                uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;       // keys 0..63
+                uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;        // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
+#pragma unroll
+                for (int g = 0; g < 12; ++g) {
+                    const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                    if (g < 8) *reinterpret_cast<uint4*>(dsrow0 + ((g ^ sw) << 4)) = o;
+                    else *reinterpret_cast<uint4*>(dsrow1 + ((((g - 8) + 4 * pp) ^ sw) << 4)) = o;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive_warp(&ds_full[pp]);
+                if (threadIdx.x == 192 && p < 8) PROF(152 + p * 4);
+                if (lane == 0 && p < 6) PROF(220 + p * 4 + (warp - 6));
+                if (i == 0 && j > 0) {
+                    store_dkv(j - 1);  // by now d(j-1, last) has long retired
+                    // every MMA of block j-1 has retired (dkv_full), so its K/V stage can take block j+1
+                    if (warp == 6 && lane == 0 && j + 1 < nkb) load_kv(j + 1);
+                }
+            }
+        }
+        store_dkv(nkb - 1);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
-    }
-}
-
-// dqkv[b, t, 0:inner] = bf16(dq_accum[b, t, :])
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t rows, int inner) {
-    const int per_row = inner >> 2;
-    const size_t total = rows * per_row;
-    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const size_t r = idx / per_row;
-        const int cidx = static_cast<int>(idx - r * per_row);
-        const float4 v = reinterpret_cast<const float4*>(acc)[idx];
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-        uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&lo);
-        o.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(dqkv + r * 3 * inner + cidx * 4) = o;
     }
 }
 
@@ -962,90 +811,41 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     if (check_attn_shape(d.B, d.H, d.T)) return -1;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-        cudaError_t e3 = cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(attn_bwd) failed");
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_bwd) failed: %s", cudaGetErrorString(e));
             return -10;
         }
         configured = true;
     }
     const int inner = d.H * 64;
-    {
-        const int rows = d.B * d.T;
-        const int threads = 256;
-        const int blocks = (rows * 32 + threads - 1) / threads;
-        attn_delta_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.out),
-                                                          reinterpret_cast<const __nv_bfloat16*>(d.dout), d.delta, d.B,
-                                                          d.H, d.T);
-        count_launch();
-    }
-    const int nblk = (d.T + 127) / 128;
-    if (d.dq_accum != nullptr) {
-        AttnBwdFusedArgs a;
-        memset(&a, 0, sizeof(a));
-        int rc = 0;
-        rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
-                           (uint64_t)d.T * 3 * inner * 2, 64, 128);
-        rc |= make_tmap_3d(&a.tmDO, d.dout, TmapDtype::BF16, inner, d.T, d.B, (uint64_t)inner * 2,
-                           (uint64_t)d.T * inner * 2, 64, 128);
-        rc |= make_tmap_3d(&a.tmDQKV, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
-                           (uint64_t)d.T * 3 * inner * 2, 64, 128);
-        if (rc) {
-            set_error("attn_bwd: tensor map creation failed: %s", tmap_last_error());
-            return -3;
-        }
-        a.lse = d.lse;
-        a.delta = d.delta;
-        a.dq_accum = d.dq_accum;
-        a.B = d.B;
-        a.H = d.H;
-        a.T = d.T;
-        a.scale = d.scale;
-        a.scale_log2e = d.scale * 1.4426950408889634f;
-        {
-            const char* dbg = getenv("SVIT_ATTN_DEBUG");
-            a.debug = dbg ? atoi(dbg) : 0;
-        }
-        const size_t rows = static_cast<size_t>(d.B) * d.T;
-        cudaMemsetAsync(d.dq_accum, 0, rows * inner * sizeof(float), stream);
-        attn_bwd_fused_kernel<<<d.B * d.H * nblk, BF_THREADS, BF_SMEM, stream>>>(a);
-        size_t cblocks = (rows * (inner / 4) + 255) / 256;
-        if (cblocks > 148 * 16) cblocks = 148 * 16;
-        attn_dq_convert_kernel<<<static_cast<int>(cblocks), 256, 0, stream>>>(d.dq_accum,
-                                                                             reinterpret_cast<__nv_bfloat16*>(d.dqkv), rows, inner);
-        count_launch(2);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            set_error("attn_bwd (fused) launch failed: %s", cudaGetErrorString(e));
-            return -11;
-        }
-        return 0;
-    }
     AttnBwdArgs a;
     memset(&a, 0, sizeof(a));
+    const uint64_t p_qkv = (uint64_t)3 * inner * 2, p_o = (uint64_t)inner * 2;
     int rc = 0;
-    rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
-                       (uint64_t)d.T * 3 * inner * 2, 64, 128);
-    rc |= make_tmap_3d(&a.tmDO, d.dout, TmapDtype::BF16, inner, d.T, d.B, (uint64_t)inner * 2, (uint64_t)d.T * inner * 2,
-                       64, 128);
-    rc |= make_tmap_3d(&a.tmDQKV, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
-                       (uint64_t)d.T * 3 * inner * 2, 64, 128);
+    rc |= make_tmap_3d(&a.tmQ, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_qkv, (uint64_t)d.T * p_qkv, 64, 128);
+    rc |= make_tmap_3d(&a.tmDO, d.dout, TmapDtype::BF16, inner, d.T, d.B, p_o, (uint64_t)d.T * p_o, 64, 128);
+    rc |= make_tmap_3d(&a.tmKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_qkv, (uint64_t)d.T * p_qkv, 64, BK_KEYS);
+    rc |= make_tmap_3d(&a.tmDQ, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_qkv, (uint64_t)d.T * p_qkv, 64, 128);
     if (rc) {
         set_error("attn_bwd: tensor map creation failed: %s", tmap_last_error());
         return -3;
     }
+    a.out = reinterpret_cast<const __nv_bfloat16*>(d.out);
+    a.dout = reinterpret_cast<const __nv_bfloat16*>(d.dout);
+    a.dqkv = reinterpret_cast<__nv_bfloat16*>(d.dqkv);
     a.lse = d.lse;
-    a.delta = d.delta;
     a.B = d.B;
     a.H = d.H;
     a.T = d.T;
     a.scale = d.scale;
     a.scale_log2e = d.scale * 1.4426950408889634f;
-    attn_bwd_kernel<false><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
-    attn_bwd_kernel<true><<<d.B * d.H * nblk, BWD_THREADS, BWD_SMEM, stream>>>(a);
-    count_launch(2);
+    {
+        static const char* dbg = getenv("SVIT_ATTN_DEBUG");
+        a.debug = dbg ? atoi(dbg) : 0;
+    }
+    attn_bwd_kernel<<<d.B * d.H, BK_THREADS, BK_SMEM, stream>>>(a);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("attn_bwd launch failed: %s", cudaGetErrorString(e));

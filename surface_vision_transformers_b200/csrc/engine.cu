@@ -54,7 +54,7 @@ struct Ws {
     float* x0;
     std::vector<LayerWs> L;
     // backward temporaries
-    float *g, *delta, *dWp, *rvec, *dq32;
+    float *g, *dWp, *rvec;
     bf16 *g16, *du, *da, *dO, *dqkv;
     // mpp
     bf16 *xL16, *dy;
@@ -107,8 +107,6 @@ static void carve(const svit_engine* e, int B, int training, int mpp, int with_e
         w->da = bp.take<bf16>(M * e->D);
         w->dO = bp.take<bf16>(M * e->I);
         w->dqkv = bp.take<bf16>(M * 3 * e->I);
-        w->delta = bp.take<float>(BHT);
-        w->dq32 = bp.take<float>(M * e->I);
         w->dWp = bp.take<float>(static_cast<size_t>(e->D) * e->Kp);
         w->rvec = bp.take<float>(e->D);
     } else {
@@ -134,7 +132,7 @@ static void carve(const svit_engine* e, int B, int training, int mpp, int with_e
         }
         w->g = nullptr;
         w->g16 = w->du = w->da = w->dO = w->dqkv = nullptr;
-        w->delta = w->dWp = w->rvec = w->dq32 = nullptr;
+        w->dWp = w->rvec = nullptr;
     }
     if (mpp) {
         w->xL16 = bp.take<bf16>(M * e->D);
@@ -249,7 +247,7 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         // ---- Attention ----
         RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
         RET_IF(wgrad(e, st, w.g16, D, L.O, I, gp(OUT_W), I, M, D, I));
-        AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, w.delta, w.dqkv, w.B, e->H, e->T, scale, w.dq32};
+        AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, nullptr, w.dqkv, w.B, e->H, e->T, scale, nullptr};
         RET_IF(launch_attn_bwd(bd, st));
         RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
                     EPI_STORE, 0));

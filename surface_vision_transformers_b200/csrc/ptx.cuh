@@ -46,6 +46,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one arrival per warp: every lane has finished (and fenced) its part, lane 0 signals.  256 single-thread arrivals on
+// one barrier serialise in the shared-memory atomic unit; 8 warp arrivals do not.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -57,11 +63,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint expires)
+// instead of returning after a few dozen clocks -- a waiting warp then costs no issue slots and no MIO traffic.
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > SVIT_SPIN_LIMIT) {
+        if ((++spins & 63) == 0 && clock64() - t0 > SVIT_SPIN_LIMIT) {
             printf("svit: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, smem_u32(bar), parity);
             __trap();
@@ -276,6 +296,26 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;
     return d;
+}
+// The same descriptor as two 32-bit halves: only the low word depends on the address, so an issuing thread advances
+// it with one 32-bit add (byte offset >> 4) instead of rebuilding 64-bit values (which ptxas does in the vector
+// datapath and then moves to uniform registers one R2UR at a time, ~90 clk per MMA).
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ void umma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
 //   c_format[4,6)=1 (f32)  a_format[7,10)=1 (bf16)  b_format[10,13)=1  a_major bit15  b_major bit16
