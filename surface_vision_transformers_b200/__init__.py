@@ -4,10 +4,11 @@ Public API mirrors the reference (SD3004/surface-vision-transformers):
     SiT                         <- models/sit.py::SiT
     masked_patch_pretraining    <- models/mpp.py::masked_patch_pretraining
 plus the pieces the north star adds around them: FusedAdamW / FusedSGD (optim), DataParallel (ddp),
-gather_patches / index tables (gather).
+gather_patches / index tables (gather), DevicePrefetcher (loader: overlapped host -> device batch staging).
 """
 from .sit import SiT, Transformer  # noqa: F401
 from .mpp import masked_patch_pretraining, get_mask_from_prob, prob_mask_like  # noqa: F401
 from .optim import FusedAdamW, FusedSGD  # noqa: F401
 from .ddp import DataParallel  # noqa: F401
 from .gather import gather_patches, load_index_table  # noqa: F401
+from .loader import DevicePrefetcher  # noqa: F401

@@ -236,3 +236,21 @@ def test_raw_mesh_ingestion_matches_prepatched():
         a = model(patched)
         b = model.forward_mesh(mesh, table, mean, std)
     assert rel_l2(b, a) < 2e-3
+
+
+@pytest.mark.parametrize("depth,nbatches", [(2, 7), (3, 5), (2, 1)])
+def test_device_prefetcher_order_and_content(depth, nbatches):
+    """Batches come out bit-identical and in order while a slow consumer keeps the compute stream busy (the copy of
+    batch i+1 runs on the side stream meanwhile and must never overwrite a batch that is still being read)."""
+    torch.manual_seed(0)
+    host = [(torch.randn(64, 4, 20, 15).pin_memory(), torch.rand(64).pin_memory()) for _ in range(nbatches)]
+    w = torch.randn(2048, 2048, device=DEV)
+    seen = []
+    for x, y in svit.DevicePrefetcher(iter(host), DEV, depth=depth):
+        for _ in range(10):           # slow consumer
+            w = torch.tanh(w @ w * 1e-3)
+        seen.append((x.clone(), y.clone()))
+    torch.cuda.synchronize()
+    assert len(seen) == nbatches
+    for (x, y), (hx, hy) in zip(seen, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
