@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 // so dQ accumulates on chip across the key blocks (the former kernel red.add-ed fp32 partials into a global
 // scratch buffer and converted them afterwards).  delta = rowsum(dO * O) is computed in the prologue.
 //
-//   tensor core (one issuing thread)      P warps (4, one query row per thread)    dS warps (4, one query row per thread)
+//   tensor core (two issuing warps)       P warps (8, one row x 48 keys per thread)   dS warps (8, one row x 48 keys per thread)
 //   a(p): S  = Q_i K_j^T                  P  = exp2(S*scale*log2e - lse*log2e)     dS = P * (dP*scale - delta*scale)
 //   b(p): dP = dO_i V_j^T                    -> bf16 smem tile sP                     -> bf16 smem tile sdS
 //   c(p): dV_j += P^T dO_i                                                         after the last i of block j:
@@ -304,7 +304,7 @@ constexpr int BK_SP = BK_SKV + 4 * BK_KV_TILE;
 constexpr int BK_SDS = BK_SP + 2 * TILE_BYTES;   // buffer b: keys 0..63 in tile b, keys 64..95 in tile 2 at byte 64 * b of each row
 constexpr int BK_BAR = BK_SDS + 3 * TILE_BYTES;
 constexpr int BK_SMEM = 1024 + BK_BAR + 256;
-constexpr int BK_THREADS = 320;  // MMA warps X and Y, 4 P warps, 4 dS warps (10 warps -> 204 registers per thread)
+constexpr int BK_THREADS = 576;  // MMA warps X and Y, 8 P warps, 8 dS warps
 constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
@@ -374,18 +374,18 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         tma_prefetch_desc(&args.tmDQ);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&kv_full[s], 1);
-            mbar_init(&ds_full[s], 4);
+            mbar_init(&ds_full[s], 8);
             mbar_init(&ds_free[s], 1);
         }
         for (int i = 0; i < 3; ++i) mbar_init(&q_full[i], 1);
         mbar_init(s_full, 1);
-        mbar_init(s_free, 4);
+        mbar_init(s_free, 8);
         mbar_init(dp_full, 1);
-        mbar_init(dp_free, 4);
-        mbar_init(p_full, 4);
-        mbar_init(p_free, 5);
+        mbar_init(dp_free, 8);
+        mbar_init(p_full, 8);
+        mbar_init(p_free, 9);
         mbar_init(dkv_full, 2);
-        mbar_init(dkv_free, 4);
+        mbar_init(dkv_free, 8);
         mbar_init(dq_full, 1);
         fence_mbar_init();
     }
@@ -505,13 +505,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             if (!X) umma_commit(dq_full);
             if (X) PROF(2);
         }
-    } else if (warp < 6) {
+    } else if (warp < 10) {
         // ================================ P warps ================================
-        const int q = warp & 3;  // TMEM lane quadrant
+        // 8 warps: warp (q, half) owns TMEM lane quadrant q (one query row per thread) and key columns [48 half, 48 half + 48)
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const float c = args.scale_log2e;
         const int sw = row & 7;
+        const bool prof_thread = threadIdx.x == 64;
         float lse2[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -520,31 +523,31 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         }
         int p = 0;
         for (int j = 0; j < nkb; ++j) {
-            const int kvalid = min(BK_KEYS, T - j * BK_KEYS);
+            const int kvalid = min(BK_KEYS, T - j * BK_KEYS) - half * 48;  // real keys among this thread's 48 columns
 #pragma unroll 1
             for (int i = 0; i < nqb; ++i, ++p) {
                 const bool qvalid = i * 128 + row < T;
                 const bool warp_any = i * 128 + q * 32 < T;  // at least one real query row in this warp
                 const float l2 = i == 0 ? lse2[0] : (i == 1 ? lse2[1] : lse2[2]);
-                uint32_t pk[48];  // P of this thread's 96 columns, packed bf16
-                if (threadIdx.x == 64 && p < 8) PROF(100 + p * 4);
+                uint32_t pk[24];  // P of this thread's 48 columns, packed bf16
+                if (prof_thread && p < 8) PROF(100 + p * 4);
                 mbar_wait(s_full, p & 1);
-                if (threadIdx.x == 64 && p < 8) PROF(101 + p * 4);
+                if (prof_thread && p < 8) PROF(101 + p * 4);
                 tc_fence_after();
                 {
                     // 16-column chunks; the TMEM load of chunk ch+1 is in flight while chunk ch is exponentiated
-                    const int nch = warp_any ? (kvalid + 15) >> 4 : 0;  // chunks that hold real keys (warp-uniform)
-                    const bool full = qvalid && kvalid == BK_KEYS;
+                    const int nch = (warp_any && kvalid > 0) ? min(3, (kvalid + 15) >> 4) : 0;  // warp-uniform
+                    const bool full = qvalid && kvalid >= 48;
                     uint32_t ca[16], cb[16];
-                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_S, ca);
+                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_S + half * 48, ca);
 #pragma unroll
-                    for (int ch = 0; ch < 6; ++ch) {
+                    for (int ch = 0; ch < 3; ++ch) {
                         uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
                         uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
                         if (ch < nch) {
                             tmem_ld_wait();
                             if (ch + 1 < nch) {
-                                tmem_ld_32x16(t_row + BK_T_S + (ch + 1) * 16, nxt);
+                                tmem_ld_32x16(t_row + BK_T_S + half * 48 + (ch + 1) * 16, nxt);
                             } else {
                                 tc_fence_before();
                                 mbar_arrive_warp(s_free);
@@ -572,40 +575,39 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 if (p > 0) mbar_wait(p_free, (p - 1) & 1);  // c(p-1) retired and the dS warps re-read P(p-1)
                 uint8_t* prow = sP + row * 128;
 #pragma unroll
-                for (int g = 0; g < 12; ++g) {
+                for (int g = 0; g < 6; ++g) {
+                    const int gc = half * 6 + g;  // 16-byte chunk index among the 12 of this row
                     const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(prow + (g >> 3) * TILE_BYTES + (((g & 7) ^ sw) << 4)) = o;
+                    *reinterpret_cast<uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4)) = o;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive_warp(p_full);
-                if (threadIdx.x == 64 && p < 8) PROF(102 + p * 4);
-                if (lane == 0 && p < 6) PROF(190 + p * 4 + (warp - 2));
+                if (prof_thread && p < 8) PROF(102 + p * 4);
             }
         }
-        // ---- epilogue: dQ_i -> bf16 -> staging (sP tiles, then the K/V stage) -> TMA store ----
+        // ---- epilogue: dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store; each half converts 32 columns ----
         mbar_wait(dq_full, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int i = 0; i < nqb; ++i) {
             if (i * 128 + q * 32 >= T) continue;  // rows past T are clipped by the store anyway
-            uint32_t o0[32], o1[32];
-            tmem_ld_32x32(t_row + BK_T_DQ + i * 64, o0);
-            tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + 32, o1);
+            uint32_t o0[32];
+            tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + half * 32, o0);
             tmem_ld_wait();
             uint8_t* orow = (i < 2 ? sP + i * TILE_BYTES : sdS) + row * 128;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t* src = &o0[g * 8];
                 uint4 o;
                 o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
                 o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
                 o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
                 o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-                *reinterpret_cast<uint4*>(orow + ((g ^ sw) << 4)) = o;
+                *reinterpret_cast<uint4*>(orow + (((half * 4 + g) ^ sw) << 4)) = o;
             }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (warp == 2 && lane == 0) {
             for (int i = 0; i < nqb; ++i)
                 tma_store_3d(&args.tmDQ, i < 2 ? sP + i * TILE_BYTES : sdS, h * 64, i * 128, b);
@@ -615,10 +617,13 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         }
     } else {
         // ================================ dS warps ================================
+        // 8 warps with the same (q, half) split as the P warps
         const int q = warp & 3;
+        const int half = (warp - 10) >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int sw = row & 7;
+        const bool prof_thread = threadIdx.x == 320;
         // delta * scale of this thread's query rows: rowsum(dO * O) over the 64 head dimensions
         float sdelta[3];
 #pragma unroll
@@ -634,58 +639,58 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             }
             sdelta[i] = acc * args.scale;
         }
-        // key block j is complete: dK_j, dV_j -> bf16 -> one 128-byte row per thread straight to global memory
-        // (TMEM lane = key index inside the block)
+        // key block j is complete: dK_j, dV_j -> bf16 -> 64 bytes per thread straight to global memory
+        // (TMEM lane = key index inside the block; each half converts 32 of the 64 head dimensions)
         auto store_dkv = [&](int j) {
             const int kv = min(BK_KEYS, T - j * BK_KEYS);
             mbar_wait(dkv_full, j & 1);
             tc_fence_after();
             const bool key_warp = q * 32 < kv;
+            __nv_bfloat16* base = args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner + h * 64 + half * 32;
 #pragma unroll 1
-            for (int a = 0; a < 2; ++a) {  // a = 0: dK_j, a = 1: dV_j
-                uint32_t o0[32], o1[32];
+            for (int part = 0; part < 4; ++part) {  // (dK | dV) x (16 columns)
+                const int a = part >> 1, c16 = (part & 1) * 16;
+                uint32_t o[16];
                 if (key_warp) {
-                    tmem_ld_32x32(t_row + BK_T_DK + a * 64, o0);
-                    tmem_ld_32x32(t_row + BK_T_DK + a * 64 + 32, o1);
+                    tmem_ld_32x16(t_row + BK_T_DK + a * 64 + half * 32 + c16, o);
                     tmem_ld_wait();
                 }
-                if (a == 1) {
+                if (part == 3) {
                     tc_fence_before();
                     mbar_arrive_warp(dkv_free);
                 }
                 if (key_warp && row < kv) {
-                    uint4* dst = reinterpret_cast<uint4*>(args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner +
-                                                          (1 + a) * inner + h * 64);
+                    uint4* dst = reinterpret_cast<uint4*>(base + (1 + a) * inner + c16);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const uint32_t* src = g < 4 ? &o0[g * 8] : &o1[(g - 4) * 8];
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-                        o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-                        o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-                        o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-                        dst[g] = o;
+                    for (int g = 0; g < 2; ++g) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+                        v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                        v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                        v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                        dst[g] = v;
                     }
                 }
             }
         };
         int p = 0;
         for (int j = 0; j < nkb; ++j) {
-            const int kvalid = min(BK_KEYS, T - j * BK_KEYS);
+            const int kvalid = min(BK_KEYS, T - j * BK_KEYS) - half * 48;
 #pragma unroll 1
             for (int i = 0; i < nqb; ++i, ++p) {
                 const bool warp_any = i * 128 + q * 32 < T;
                 const float sd = i == 0 ? sdelta[0] : (i == 1 ? sdelta[1] : sdelta[2]);
                 const uint32_t pp = p & 1;
                 // ---- P(p): smem -> registers right away, so the P warps get their tile back early ----
-                uint32_t pk[48];  // packed bf16 P, overwritten in place by dS
-                if (threadIdx.x == 192 && p < 8) PROF(150 + p * 4);
+                uint32_t pk[24];  // packed bf16 P, overwritten in place by dS
+                if (prof_thread && p < 8) PROF(150 + p * 4);
                 mbar_wait(p_full, pp);
                 {
                     const uint8_t* prow = sP + row * 128;  // (rows of all-invalid warps hold the zeros the P warps wrote)
 #pragma unroll
-                    for (int g = 0; g < 12; ++g) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(prow + (g >> 3) * TILE_BYTES + (((g & 7) ^ sw) << 4));
+                    for (int g = 0; g < 6; ++g) {
+                        const int gc = half * 6 + g;
+                        const uint4 v = *reinterpret_cast<const uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4));
                         pk[g * 4] = v.x;
                         pk[g * 4 + 1] = v.y;
                         pk[g * 4 + 2] = v.z;
@@ -695,21 +700,25 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 mbar_arrive_warp(p_free);
                 // ---- dS = P * (dP * scale - delta * scale), masked entries of P are exact zeros ----
                 mbar_wait(dp_full, pp);
-                if (threadIdx.x == 192 && p < 8) PROF(151 + p * 4);
+                if (prof_thread && p < 8) PROF(151 + p * 4);
                 tc_fence_after();
+                if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired long ago: this dS buffer is free
+                uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;       // keys 0..63
+                uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;        // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
                 {
                     // chunks past nch hold P = 0 -> the packed zeros already are the right dS
-                    const int nch = warp_any ? (kvalid + 15) >> 4 : 0;
+                    const int nch = (warp_any && kvalid > 0) ? min(3, (kvalid + 15) >> 4) : 0;
                     uint32_t ca[16], cb[16];
-                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_DP, ca);
+                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_DP + half * 48, ca);
 #pragma unroll
-                    for (int ch = 0; ch < 6; ++ch) {
+                    for (int ch = 0; ch < 3; ++ch) {
                         uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
                         uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
+                        uint32_t ds[8];
                         if (ch < nch) {
                             tmem_ld_wait();
                             if (ch + 1 < nch) {
-                                tmem_ld_32x16(t_row + BK_T_DP + (ch + 1) * 16, nxt);
+                                tmem_ld_32x16(t_row + BK_T_DP + half * 48 + (ch + 1) * 16, nxt);
                             } else {
                                 tc_fence_before();
                                 mbar_arrive_warp(dp_free);
@@ -717,9 +726,19 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
 #pragma unroll
                             for (int e = 0; e < 16; e += 2) {
                                 const uint32_t pa = pk[ch * 8 + e / 2];
-                                pk[ch * 8 + e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(cur[e]), args.scale, -sd),
-                                                               bf16_hi(pa) * fmaf(__uint_as_float(cur[e + 1]), args.scale, -sd));
+                                ds[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(cur[e]), args.scale, -sd),
+                                                      bf16_hi(pa) * fmaf(__uint_as_float(cur[e + 1]), args.scale, -sd));
                             }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) ds[e] = 0u;
+                        }
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const int gc = half * 6 + ch * 2 + g;
+                            const uint4 o = make_uint4(ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]);
+                            if (gc < 8) *reinterpret_cast<uint4*>(dsrow0 + ((gc ^ sw) << 4)) = o;
+                            else *reinterpret_cast<uint4*>(dsrow1 + ((((gc - 8) + 4 * pp) ^ sw) << 4)) = o;
                         }
                     }
                     if (nch == 0) {
@@ -727,23 +746,13 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                         mbar_arrive_warp(dp_free);
                     }
                 }
-                if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired: this dS buffer may be overwritten
-                uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;       // keys 0..63
-                uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;        // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
-#pragma unroll
-                for (int g = 0; g < 12; ++g) {
-                    const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                    if (g < 8) *reinterpret_cast<uint4*>(dsrow0 + ((g ^ sw) << 4)) = o;
-                    else *reinterpret_cast<uint4*>(dsrow1 + ((((g - 8) + 4 * pp) ^ sw) << 4)) = o;
-                }
                 fence_proxy_async_smem();
                 mbar_arrive_warp(&ds_full[pp]);
-                if (threadIdx.x == 192 && p < 8) PROF(152 + p * 4);
-                if (lane == 0 && p < 6) PROF(220 + p * 4 + (warp - 6));
+                if (prof_thread && p < 8) PROF(152 + p * 4);
                 if (i == 0 && j > 0) {
                     store_dkv(j - 1);  // by now d(j-1, last) has long retired
-                    // every MMA of block j-1 has retired (dkv_full), so its K/V stage can take block j+1
-                    if (warp == 6 && lane == 0 && j + 1 < nkb) load_kv(j + 1);
+                    // every MMA of block j-1 has retired (dk_full, and X's are causally earlier): refill its K/V stage
+                    if (warp == 10 && lane == 0 && j + 1 < nkb) load_kv(j + 1);
                 }
             }
         }
