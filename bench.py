@@ -347,9 +347,21 @@ def main():
         flops = 2.0 * M * H4 * D
         ach = flops / (k_ms * 1e-3) / 1e12
         step_tf = value / world * wl["gflop_per_sample"] / 1e3
+        # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/), same shape only
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
+                prof = json.load(f)["gemm_tn_fc1_gelu"]
+            if kind != "infer" and (M, H4, D) == (82176, 1536, 384):
+                traffic = prof["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         roof = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,EPI_GELU,192> (fc1 + bias + exact GELU, M=%d N=%d K=%d)" % (M, H4, D),
                     achieved=ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=ach / peaks["tflops_burst"],
-                    traffic=None, peak_source=peaks["source"] + " (burst: kernel timed alone)",
+                    traffic=traffic, traffic_source="profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + "
+                    "dram__bytes_write.sum, one ncu --set full launch)" if traffic else None,
+                    algorithmic_bytes=2.0 * M * D + 2.0 * H4 * D + (2 if mode == 1 else 1) * 2.0 * M * H4,
+                    peak_source=peaks["source"] + " (burst: kernel timed alone)",
                     us_per_launch=k_ms * 1e3, flops_per_launch=flops,
                     step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
                     step_frac_of_nominal_2250=step_tf / 2250.0)

@@ -86,24 +86,30 @@ struct TnArgs {
     int M, N, K;
 };
 
-template <int MODE>
+constexpr int ARES_KB = 6;  // A-resident mode: up to 6 K blocks (K <= 384) of the A row block stay in shared memory
+
+template <int MODE, bool ARES>
 struct EpiTraits {
     static constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU);
     // staging boxes per epilogue warp: in-place aux/out rotation of 3, two outputs double-buffered, or one output x2
-    static constexpr int NBUF = HAS_AUX ? 3 : (MODE == EPI_GELU ? 4 : 2);
+    // (the A-resident variant gives 96 KB to the A row block and makes do with 2 boxes per warp)
+    static constexpr int NBUF = ARES ? 2 : (HAS_AUX ? 3 : (MODE == EPI_GELU ? 4 : 2));
 };
 
-template <int BN, int CG, int MODE>
+template <int BN, int CG, int MODE, bool ARES>
 struct TnCfg {
     static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;  // with a CTA pair every CTA holds half of the B rows
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int EPI_BYTES = EPI_WARPS * EpiTraits<MODE>::NBUF * WBUF_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * EpiTraits<MODE, ARES>::NBUF * WBUF_BYTES;
     static constexpr int FIXED_BYTES = 1024 /*align slack*/ + EPI_BYTES + EPI_WARPS * 256 /*bias*/ + 1024 /*barriers*/;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
+    // A and B share one ring (stage = A block + B block) -- or A keeps ARES_KB fixed slots and only B is a ring
+    static constexpr int STAGE_BYTES = ARES ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int A_SLOTS_FIXED = ARES ? ARES_KB : 0;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED_BYTES - A_SLOTS_FIXED * A_STAGE_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static_assert(STAGES >= 2, "not enough shared memory for the operand pipeline");
+    static constexpr int A_SLOTS = ARES ? ARES_KB : STAGES;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = FIXED_BYTES + STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = FIXED_BYTES + A_SLOTS * A_STAGE_BYTES + STAGES * B_STAGE_BYTES;
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile --
@@ -116,10 +122,15 @@ struct TnCfg {
 // (tcgen05.ld), applies the fused epilogue, writes a 32 x 128 B swizzled box into its private staging ring and
 // issues its own TMA store.  Residual / pre-activation tiles are prefetched two units ahead into the same ring by
 // the aux-loader warp and overwritten in place by the result.
-template <typename OutT, int MODE, int BN, int CG>
+//
+// ARES (A-resident, K <= 384): the kernel is bound by the L2 -> SM feed (~45 B/clk/SM), so when the whole K extent
+// of a 128-row A block fits in shared memory (96 KB) it is loaded ONCE and every N tile of that row block streams
+// only its B tile past it.  Tiles are then handed out as contiguous m-major ranges (one range per cluster) so that a
+// cluster re-loads A only when it crosses into the next row block.
+template <typename OutT, int MODE, int BN, int CG, bool ARES>
 __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_constant__ TnArgs args) {
-    using Cfg = TnCfg<BN, CG, MODE>;
-    using ET = EpiTraits<MODE>;
+    using Cfg = TnCfg<BN, CG, MODE, ARES>;
+    using ET = EpiTraits<MODE, ARES>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int UC = 128 / (int)sizeof(OutT);  // columns per epilogue unit (one 128-byte row of the staging box)
     constexpr int UNITS = BN / UC;
@@ -130,8 +141,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;                       // [EPI_WARPS][NBUF][4 KB]
+    uint8_t* sB = smem + Cfg::A_SLOTS * A_STAGE_BYTES;
+    uint8_t* sEpi = sB + STAGES * Cfg::B_STAGE_BYTES;                       // [EPI_WARPS][NBUF][4 KB]
     float* sBias = reinterpret_cast<float*>(sEpi + Cfg::EPI_BYTES);         // [EPI_WARPS][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + EPI_WARPS * 64);
     uint64_t* full_bar = bars;                  // [STAGES]
@@ -140,7 +151,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
     uint64_t* tempty_bar = tfull_bar + 2;       // [2]
     uint64_t* afull_bar = tempty_bar + 2;       // [EPI_WARPS][3]
     uint64_t* aempty_bar = afull_bar + EPI_WARPS * 3;  // [EPI_WARPS][3]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + EPI_WARPS * 3);
+    uint64_t* ares_full = aempty_bar + EPI_WARPS * 3;  // [ARES_KB] resident A block kb landed
+    uint64_t* ares_empty = ares_full + ARES_KB;        // [ARES_KB] last MMA of the row block that reads it retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ares_empty + ARES_KB);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -152,8 +165,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
     const int num_kb = (K + BK - 1) / BK;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool is_leader = cta_rank == 0;
-    const int first_tile = blockIdx.x / CG;      // cluster index
-    const int tile_stride = gridDim.x / CG;      // number of clusters
+    // tile schedule: round-robin over clusters, or (ARES) one contiguous m-major range per cluster
+    const int num_clusters = gridDim.x / CG, cluster_id = blockIdx.x / CG;
+    const int first_tile = ARES ? static_cast<int>(static_cast<long long>(cluster_id) * num_tiles / num_clusters) : cluster_id;
+    const int end_tile = ARES ? static_cast<int>(static_cast<long long>(cluster_id + 1) * num_tiles / num_clusters) : num_tiles;
+    const int tile_stride = ARES ? 1 : num_clusters;
     const int row_off = static_cast<int>(cta_rank) * BM;
 
     if (threadIdx.x == 0) {
@@ -173,6 +189,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         for (int i = 0; i < EPI_WARPS * 3; ++i) {
             mbar_init(&afull_bar[i], 1);
             mbar_init(&aempty_bar[i], 1);
+        }
+        for (int i = 0; i < ARES_KB; ++i) {
+            mbar_init(&ares_full[i], 1);
+            mbar_init(&ares_empty[i], 1);
         }
         fence_mbar_init();
     }
@@ -195,18 +215,50 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+            int cur_m = -1, visits = 0;  // ARES: row block whose A is resident, number of row blocks loaded so far
+            for (int tile = first_tile; tile < end_tile; tile += tile_stride) {
                 const int m0 = (tile / tiles_n) * TM + row_off;
                 const int n0 = (tile % tiles_n) * BN + static_cast<int>(cta_rank) * (BN / CG);
+                if constexpr (ARES) {
+                    const bool new_m = (tile / tiles_n) != cur_m;
+                    if (new_m) {
+                        cur_m = tile / tiles_n;
+                        ++visits;
+                    }
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        if (new_m) {
+                            mbar_wait(&ares_empty[kb], (visits & 1));  // visit v waits for completion v-2 (parity v & 1)
+                            if constexpr (CG == 2) {
+                                if (is_leader) mbar_expect_tx(&ares_full[kb], 2 * A_STAGE_BYTES);
+                                tma_load_2d_2cta(sA + kb * A_STAGE_BYTES, &args.tmA, &ares_full[kb], kb * BK, m0);
+                            } else {
+                                mbar_expect_tx(&ares_full[kb], A_STAGE_BYTES);
+                                tma_load_2d(sA + kb * A_STAGE_BYTES, &args.tmA, &ares_full[kb], kb * BK, m0);
+                            }
+                        }
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if constexpr (CG == 2) {
+                            if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_STAGE_BYTES);
+                            tma_load_2d_2cta(sB + stage * Cfg::B_STAGE_BYTES, &args.tmB, &full_bar[stage], kb * BK, n0);
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], Cfg::B_STAGE_BYTES);
+                            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &args.tmB, &full_bar[stage], kb * BK, n0);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                } else {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if constexpr (CG == 2) {
                         // both CTAs' bytes are credited to the leader's barrier, which the leader arms for the pair
-                        if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
                         tma_load_2d_2cta(sA + stage * A_STAGE_BYTES, &args.tmA, &full_bar[stage], kb * BK, m0);
                         tma_load_2d_2cta(sB + stage * Cfg::B_STAGE_BYTES, &args.tmB, &full_bar[stage], kb * BK, n0);
                     } else {
-                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
                         tma_load_2d(sA + stage * A_STAGE_BYTES, &args.tmA, &full_bar[stage], kb * BK, m0);
                         tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &args.tmB, &full_bar[stage], kb * BK, n0);
                     }
@@ -214,6 +266,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                         stage = 0;
                         phase ^= 1;
                     }
+                }
                 }
             }
         }
@@ -224,16 +277,27 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+            int cur_m = -1, visits = 0;
+            for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
+                bool new_m = false, last_of_m = false;
+                if constexpr (ARES) {
+                    new_m = (tile / tiles_n) != cur_m;
+                    if (new_m) {
+                        cur_m = tile / tiles_n;
+                        ++visits;
+                    }
+                    last_of_m = (tile + 1 >= end_tile) || ((tile + 1) / tiles_n != cur_m);
+                }
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    if (ARES && new_m) mbar_wait(&ares_full[kb], (visits & 1) ^ 1);
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(sA + (ARES ? kb : stage) * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
@@ -244,6 +308,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     }
                     if constexpr (CG == 2) umma_commit_2cta(&empty_bar[stage], 3);
                     else umma_commit(&empty_bar[stage]);
+                    if (ARES && last_of_m) {  // this row block's A slot kb may be refilled
+                        if constexpr (CG == 2) umma_commit_2cta(&ares_empty[kb], 3);
+                        else umma_commit(&ares_empty[kb]);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -259,14 +327,14 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         if (HAS_AUX && elect_one()) {
             int kcnt[2] = {0, 0};  // jobs issued so far per parity group
             int it = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+            for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
                 const int m0 = (tile / tiles_n) * TM + row_off;
                 const int n0 = (tile % tiles_n) * BN;
                 for (int u = 0; u < UNITS; ++u) {
                     const int p = (it * UNITS + u) & 1;
                     const int k = kcnt[p]++;
-                    const int slot = k % 3;
-                    const uint32_t ph = (k / 3) & 1;
+                    const int slot = k % NBUF;
+                    const uint32_t ph = (k / NBUF) & 1;
 #pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
                         const int w = p * 4 + q;
@@ -287,7 +355,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         float* wbias = sBias + ew * 64;
         const int sw = lane & 7;       // swizzle key of this thread's row inside a 32-row box
         int it = 0, k = 0;             // k = jobs done by this warp
-        for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+        for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
             const int m0 = (tile / tiles_n) * TM + row_off + q * 32;  // first row of this warp's slice
             const int n0 = (tile % tiles_n) * BN;
             const int as = it & 1;
@@ -346,9 +414,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                 uint8_t* obuf;
                 uint8_t* obuf2 = nullptr;
                 if constexpr (HAS_AUX) {
-                    const int slot = k % 3;
+                    const int slot = k % NBUF;
                     obuf = wbuf + slot * WBUF_BYTES;
-                    mbar_wait(&afull_bar[ew * 3 + slot], (k / 3) & 1);
+                    mbar_wait(&afull_bar[ew * 3 + slot], (k / NBUF) & 1);
                     const uint8_t* arow = obuf + lane * 128;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -375,9 +443,14 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     }
                     __syncwarp();  // every lane has consumed the aux box before it is overwritten in place
                 } else if constexpr (MODE == EPI_GELU) {
-                    obuf = wbuf + (k & 1) * 2 * WBUF_BYTES;
+                    if constexpr (NBUF == 4) {
+                        obuf = wbuf + (k & 1) * 2 * WBUF_BYTES;
+                        if (lane == 0) tma_store_wait_read<1>();  // the store that used this pair two jobs ago has drained
+                    } else {
+                        obuf = wbuf;
+                        if (lane == 0) tma_store_wait_read<0>();  // single pair of boxes: the previous store has drained
+                    }
                     obuf2 = obuf + WBUF_BYTES;
-                    if (lane == 0) tma_store_wait_read<1>();  // the store that used this pair two jobs ago has drained
                     __syncwarp();
                 } else {
                     obuf = wbuf + (k & 1) * WBUF_BYTES;
@@ -434,7 +507,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                         // aux loader (it then prefetches the tile of job k+2 into it)
                         if (k > 0) {
                             tma_store_wait_read<1>();
-                            mbar_arrive(&aempty_bar[ew * 3 + (k - 1) % 3]);
+                            mbar_arrive(&aempty_bar[ew * 3 + (k - 1) % NBUF]);
                         }
                     }
                 }
@@ -657,10 +730,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <typename OutT, int MODE, int BN, int CG>
+template <typename OutT, int MODE, int BN, int CG, bool ARES>
 static int launch_tn_inst(const TnArgs& a, int num_sms, cudaStream_t stream) {
-    using Cfg = TnCfg<BN, CG, MODE>;
-    auto kfn = gemm_tn_kernel<OutT, MODE, BN, CG>;
+    using Cfg = TnCfg<BN, CG, MODE, ARES>;
+    auto kfn = gemm_tn_kernel<OutT, MODE, BN, CG, ARES>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -695,18 +768,18 @@ static int launch_tn_inst(const TnArgs& a, int num_sms, cudaStream_t stream) {
     return 0;
 }
 
-template <int CG>
+template <int CG, bool ARES>
 static int dispatch_tn(const GemmTnDesc& d, const TnArgs& a, int num_sms, cudaStream_t stream) {
     constexpr int BN = 192;
     if (d.out_f32) {
-        if (d.mode == EPI_STORE) return launch_tn_inst<float, EPI_STORE, BN, CG>(a, num_sms, stream);
-        if (d.mode == EPI_RESID) return launch_tn_inst<float, EPI_RESID, BN, CG>(a, num_sms, stream);
+        if (d.mode == EPI_STORE) return launch_tn_inst<float, EPI_STORE, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_RESID) return launch_tn_inst<float, EPI_RESID, BN, CG, ARES>(a, num_sms, stream);
     } else {
-        if (d.mode == EPI_STORE) return launch_tn_inst<__nv_bfloat16, EPI_STORE, BN, CG>(a, num_sms, stream);
-        if (d.mode == EPI_GELU) return launch_tn_inst<__nv_bfloat16, EPI_GELU, BN, CG>(a, num_sms, stream);
-        if (d.mode == EPI_RESID) return launch_tn_inst<__nv_bfloat16, EPI_RESID, BN, CG>(a, num_sms, stream);
-        if (d.mode == EPI_DGELU) return launch_tn_inst<__nv_bfloat16, EPI_DGELU, BN, CG>(a, num_sms, stream);
-        if (d.mode == EPI_GELU_ONLY) return launch_tn_inst<__nv_bfloat16, EPI_GELU_ONLY, BN, CG>(a, num_sms, stream);
+        if (d.mode == EPI_STORE) return launch_tn_inst<__nv_bfloat16, EPI_STORE, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_GELU) return launch_tn_inst<__nv_bfloat16, EPI_GELU, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_RESID) return launch_tn_inst<__nv_bfloat16, EPI_RESID, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_DGELU) return launch_tn_inst<__nv_bfloat16, EPI_DGELU, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_GELU_ONLY) return launch_tn_inst<__nv_bfloat16, EPI_GELU_ONLY, BN, CG, ARES>(a, num_sms, stream);
     }
     set_error("gemm_tn: unsupported mode %d for out_f32=%d", d.mode, d.out_f32);
     return -4;
@@ -748,7 +821,14 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
         set_error("gemm_tn: tensor map creation failed: %s", tmap_last_error());
         return -3;
     }
-    return cg == 2 ? dispatch_tn<2>(d, a, num_sms, stream) : dispatch_tn<1>(d, a, num_sms, stream);
+    // A-resident variant: the whole K extent of a row block fits in 6 K blocks and there are several N tiles to reuse it
+    static const int force_ares = getenv("SVIT_GEMM_ARES") ? atoi(getenv("SVIT_GEMM_ARES")) : -1;
+    // (measured: -3 % for the plain store epilogue; the GELU / aux epilogues lose more from their halved staging rings)
+    bool ares = cg == 2 && d.K <= ARES_KB * BK && (d.N + BN - 1) / BN >= 3 && d.mode == EPI_STORE;
+    if (force_ares == 0) ares = false;
+    if (force_ares == 1 && d.K <= ARES_KB * BK) ares = true;
+    if (cg == 2) return ares ? dispatch_tn<2, true>(d, a, num_sms, stream) : dispatch_tn<2, false>(d, a, num_sms, stream);
+    return ares ? dispatch_tn<1, true>(d, a, num_sms, stream) : dispatch_tn<1, false>(d, a, num_sms, stream);
 }
 
 int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream) {

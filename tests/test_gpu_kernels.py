@@ -43,7 +43,13 @@ def dgelu(x):
     (1284, 1536, 384, 3, False, False, False),     # dgrad * gelu'
     (1284, 384, 640, 0, True, False, True),        # patch embedding + cls/pos table
     (5136, 612, 384, 0, True, True, False),        # MPP decoder (N not a tile multiple)
-    (20544, 1152, 384, 0, False, False, False),    # several persistent waves
+    (20544, 1152, 384, 0, False, False, False),    # several persistent waves (CTA pairs, A-resident schedule)
+    (20544, 1536, 384, 1, False, True, False),     # fc1 + GELU at pair-tile size (A-resident only with SVIT_GEMM_ARES=1)
+    (20544, 1536, 384, 3, False, False, False),    # dgrad * gelu' at pair-tile size
+    (20544, 1536, 384, 4, False, True, False),     # GELU only at pair-tile size
+    (20544, 612, 384, 0, True, True, False),       # A-resident: fp32 out, N not a tile multiple
+    (19999, 1000, 328, 0, False, True, False),     # A-resident: ragged M, N and K (K not a multiple of 64)
+    (20544, 768, 192, 1, False, True, False),      # A-resident: SiT-tiny fc1 (3 K blocks)
     (100, 100, 72, 0, True, True, False),          # ragged M, N, K
     (1, 192, 64, 0, True, True, False),            # single row
 ])
