@@ -159,6 +159,40 @@ def test_attention_fwd_bwd(env, B, H, T):
             assert rel_l2(got, want) < 2 * TOL
 
 
+@pytest.mark.parametrize("kind", ["large_random", "ascending_keys", "descending_keys"])
+def test_attention_fwd_extreme_logits(env, kind):
+    """The online softmax with lazy rescaling stays exact when later key chunks raise the row maximum by far more than
+    2^8 (ascending keys force the rescale of O in every chunk), when the first chunk dominates, and for very peaked
+    random rows.  Output and log-sum-exp against the fp32 reference on the same bf16 inputs."""
+    dev, lib = env["dev"], env["lib"]
+    torch.manual_seed(7)
+    B, H, T = 2, 2, 321
+    inner = H * 64
+    scale = 64 ** -0.5
+    if kind == "large_random":
+        qkv = torch.randn(B, T, 3 * inner, device=dev) * 6.0
+    else:
+        u = torch.nn.functional.normalize(torch.randn(64, device=dev), dim=0)
+        ramp = torch.linspace(0.0, 1.0, T, device=dev)
+        if kind == "descending_keys":
+            ramp = ramp.flip(0)
+        q = (u * 40.0).expand(B, T, H, 64) + torch.randn(B, T, H, 64, device=dev)
+        k = (u * 60.0)[None, None, None, :] * ramp[None, :, None, None] + torch.randn(B, T, H, 64, device=dev)
+        v = torch.randn(B, T, H, 64, device=dev)
+        qkv = torch.cat([t.reshape(B, T, inner) for t in (q, k, v)], dim=-1)
+    qkv = qkv.bfloat16()
+    out = torch.full((B, T, inner), float("nan"), device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, T, device=dev)
+    check(lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, scale, stream()), "attn_fwd")
+    q, k, v = [t.reshape(B, T, H, 64).permute(0, 2, 1, 3).float() for t in qkv.chunk(3, dim=-1)]
+    dots = q @ k.transpose(-1, -2) * scale
+    ref = (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, T, inner)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert rel_l2(out, ref) < TOL
+    assert rel_l2(lse, torch.logsumexp(dots, -1)) < 1e-3
+
+
 def test_attention_rejects_long_sequences(env):
     lib = env["lib"]
     assert lib.svit_attn_fwd(vp(256), vp(256), vp(256), 1, 1, 385, 0.125, stream()) != 0
