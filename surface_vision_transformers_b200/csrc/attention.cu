@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 // so dQ accumulates on chip across the key blocks (the former kernel red.add-ed fp32 partials into a global
 // scratch buffer and converted them afterwards).  delta = rowsum(dO * O) is computed in the prologue.
 //
-//   tensor core (two issuing warps)       P warps (8, one row x 48 keys per thread)   dS warps (8, one row x 48 keys per thread)
+//   tensor core (two issuing warps)       P warps (4, one row x 96 keys per thread)   dS warps (8, one row x 48 keys per thread)
 //   a(p): S  = Q_i K_j^T                  P  = exp2(S*scale*log2e - lse*log2e)     dS = P * (dP*scale - delta*scale)
 //   b(p): dP = dO_i V_j^T                    -> bf16 smem tile sP                     -> bf16 smem tile sdS
 //   c(p): dV_j += P^T dO_i                                                         after the last i of block j:
@@ -304,7 +304,7 @@ constexpr int BK_SP = BK_SKV + 4 * BK_KV_TILE;
 constexpr int BK_SDS = BK_SP + 2 * TILE_BYTES;   // buffer b: keys 0..63 in tile b, keys 64..95 in tile 2 at byte 64 * b of each row
 constexpr int BK_BAR = BK_SDS + 3 * TILE_BYTES;
 constexpr int BK_SMEM = 1024 + BK_BAR + 256;
-constexpr int BK_THREADS = 576;  // MMA warps X and Y, 8 P warps, 8 dS warps
+constexpr int BK_THREADS = 448;  // MMA warps X and Y, 4 P warps, 8 dS warps (14 warps: 4 per sub-partition -> 128 registers)
 constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
@@ -334,6 +334,41 @@ __device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
            bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
 }
 
+// Key block j is complete: one of its accumulators (dK_j or dV_j) -> bf16 -> 64 bytes per thread straight to global
+// memory.  TMEM lane = key index inside the block; each (quadrant, half) warp converts 32 of the 64 head dimensions.
+// Called where few registers are live (top of a P-warp iteration, end of a dS-warp iteration): spills inside the
+// hot loops are fatal (local-memory traffic crawls while the tensor core streams operands from shared memory).
+template <int PARTS>  // PARTS x 16 accumulator columns per thread
+__device__ __forceinline__ void bwd_store_acc(uint32_t t_acc, __nv_bfloat16* dst_row, bool key_warp, bool row_ok, uint64_t* full_bar,
+                                           uint32_t full_parity, uint64_t* free_bar) {
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int part = 0; part < PARTS; ++part) {
+        uint32_t o[16];
+        if (key_warp) {
+            tmem_ld_32x16(t_acc + part * 16, o);
+            tmem_ld_wait();
+        }
+        if (part == PARTS - 1) {
+            tc_fence_before();
+            mbar_arrive_warp(free_bar);
+        }
+        if (key_warp && row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(dst_row + part * 16);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+                v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                dst[g] = v;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -353,10 +388,12 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     uint64_t* p_free = bars + 13;    // c(p) retired and P re-read     (MMA + dS warps -> P warps)
     uint64_t* ds_full = bars + 14;   // [2] dS tile p & 1 written      (dS warps -> MMA)
     uint64_t* ds_free = bars + 16;   // [2] d(p) retired               (MMA -> dS warps)
-    uint64_t* dkv_full = bars + 18;  // dK_j, dV_j final               (MMA -> dS warps)
-    uint64_t* dkv_free = bars + 19;  // dK_j, dV_j copied to registers (dS warps -> MMA)
-    uint64_t* dq_full = bars + 20;   // every MMA of the CTA retired   (MMA -> P warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint64_t* dv_full = bars + 18;   // dV_j final (c(j, last) retired)  (MMA X -> P warps)
+    uint64_t* dv_free = bars + 19;   // dV_j copied to registers         (P warps -> MMA X)
+    uint64_t* dk_full = bars + 20;   // dK_j final (d(j, last) retired)  (MMA Y -> dS warps)
+    uint64_t* dk_free = bars + 21;   // dK_j copied to registers         (dS warps -> MMA Y)
+    uint64_t* dq_full = bars + 22;   // every MMA of the CTA retired     (MMA -> P warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -379,13 +416,15 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         }
         for (int i = 0; i < 3; ++i) mbar_init(&q_full[i], 1);
         mbar_init(s_full, 1);
-        mbar_init(s_free, 8);
+        mbar_init(s_free, 4);
         mbar_init(dp_full, 1);
         mbar_init(dp_free, 8);
-        mbar_init(p_full, 8);
+        mbar_init(p_full, 4);
         mbar_init(p_free, 9);
-        mbar_init(dkv_full, 2);
-        mbar_init(dkv_free, 8);
+        mbar_init(dv_full, 1);
+        mbar_init(dv_free, 4);
+        mbar_init(dk_full, 1);
+        mbar_init(dk_free, 8);
         mbar_init(dq_full, 1);
         fence_mbar_init();
     }
@@ -473,7 +512,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                     if (X) mbar_wait(p_full, pp);
                     else mbar_wait(&ds_full[pp], (p >> 1) & 1);
                     if (p < 8) PROF((X ? 11 : 13) + p * 4);
-                    if (i == 0 && j > 0) mbar_wait(dkv_free, (j - 1) & 1);  // dK_{j-1}, dV_{j-1} were copied out
+                    if (i == 0 && j > 0) mbar_wait(X ? dv_free : dk_free, (j - 1) & 1);  // dV_{j-1} / dK_{j-1} were copied out
                     tc_fence_after();
                     const uint32_t b_lo = mn0 + i * (TILE_BYTES >> 4);
                     if (X) {
@@ -499,17 +538,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                             if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DK, dst_lo + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
                         umma_commit(&ds_free[pp]);
                     }
-                    if (i == nqb - 1) umma_commit(dkv_full);
+                    if (i == nqb - 1) umma_commit(X ? dv_full : dk_full);
                 }
             }
             if (!X) umma_commit(dq_full);
             if (X) PROF(2);
         }
-    } else if (warp < 10) {
+    } else if (warp < 6) {
         // ================================ P warps ================================
-        // 8 warps: warp (q, half) owns TMEM lane quadrant q (one query row per thread) and key columns [48 half, 48 half + 48)
+        // 4 warps: warp q owns TMEM lane quadrant q, one query row x 96 key columns per thread
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const float c = args.scale_log2e;
@@ -521,33 +559,41 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             const int t = i * 128 + row;
             lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : 0.0f;
         }
+        auto store_dv = [&](int j) {  // dV_j: TMEM lane = key row, 64 head dimensions per thread
+            const int kvp = min(BK_KEYS, T - j * BK_KEYS);
+            bwd_store_acc<4>(t_row + BK_T_DV,
+                             args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner + 2 * inner + h * 64,
+                             q * 32 < kvp, row < kvp, dv_full, j & 1, dv_free);
+        };
         int p = 0;
         for (int j = 0; j < nkb; ++j) {
-            const int kvalid = min(BK_KEYS, T - j * BK_KEYS) - half * 48;  // real keys among this thread's 48 columns
+            const int kvalid = min(BK_KEYS, T - j * BK_KEYS);
 #pragma unroll 1
             for (int i = 0; i < nqb; ++i, ++p) {
                 const bool qvalid = i * 128 + row < T;
                 const bool warp_any = i * 128 + q * 32 < T;  // at least one real query row in this warp
                 const float l2 = i == 0 ? lse2[0] : (i == 1 ? lse2[1] : lse2[2]);
-                uint32_t pk[24];  // P of this thread's 48 columns, packed bf16
+                // dV_{j-1} became final when c(j-1, last) retired: copy it out first so that c(j, 0) can start at once
+                if (i == 0 && j > 0) store_dv(j - 1);
+                uint32_t pk[48];  // P of this thread's 96 columns, packed bf16
                 if (prof_thread && p < 8) PROF(100 + p * 4);
                 mbar_wait(s_full, p & 1);
                 if (prof_thread && p < 8) PROF(101 + p * 4);
                 tc_fence_after();
                 {
                     // 16-column chunks; the TMEM load of chunk ch+1 is in flight while chunk ch is exponentiated
-                    const int nch = (warp_any && kvalid > 0) ? min(3, (kvalid + 15) >> 4) : 0;  // warp-uniform
-                    const bool full = qvalid && kvalid >= 48;
+                    const int nch = warp_any ? (kvalid + 15) >> 4 : 0;  // warp-uniform
+                    const bool full = qvalid && kvalid == BK_KEYS;
                     uint32_t ca[16], cb[16];
-                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_S + half * 48, ca);
+                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_S, ca);
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
+                    for (int ch = 0; ch < 6; ++ch) {
                         uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
                         uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
                         if (ch < nch) {
                             tmem_ld_wait();
                             if (ch + 1 < nch) {
-                                tmem_ld_32x16(t_row + BK_T_S + half * 48 + (ch + 1) * 16, nxt);
+                                tmem_ld_32x16(t_row + BK_T_S + (ch + 1) * 16, nxt);
                             } else {
                                 tc_fence_before();
                                 mbar_arrive_warp(s_free);
@@ -575,39 +621,42 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 if (p > 0) mbar_wait(p_free, (p - 1) & 1);  // c(p-1) retired and the dS warps re-read P(p-1)
                 uint8_t* prow = sP + row * 128;
 #pragma unroll
-                for (int g = 0; g < 6; ++g) {
-                    const int gc = half * 6 + g;  // 16-byte chunk index among the 12 of this row
+                for (int g = 0; g < 12; ++g) {
                     const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4)) = o;
+                    *reinterpret_cast<uint4*>(prow + (g >> 3) * TILE_BYTES + (((g & 7) ^ sw) << 4)) = o;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive_warp(p_full);
                 if (prof_thread && p < 8) PROF(102 + p * 4);
             }
         }
-        // ---- epilogue: dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store; each half converts 32 columns ----
+        store_dv(nkb - 1);
+        // ---- epilogue: dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store ----
         mbar_wait(dq_full, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int i = 0; i < nqb; ++i) {
             if (i * 128 + q * 32 >= T) continue;  // rows past T are clipped by the store anyway
-            uint32_t o0[32];
-            tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + half * 32, o0);
-            tmem_ld_wait();
             uint8_t* orow = (i < 2 ? sP + i * TILE_BYTES : sdS) + row * 128;
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                uint32_t o0[32];
+                tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + part * 32, o0);
+                tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint32_t* src = &o0[g * 8];
-                uint4 o;
-                o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-                o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-                o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-                o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-                *reinterpret_cast<uint4*>(orow + (((half * 4 + g) ^ sw) << 4)) = o;
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t* src = &o0[g * 8];
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
+                    o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
+                    o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
+                    o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+                    *reinterpret_cast<uint4*>(orow + (((part * 4 + g) ^ sw) << 4)) = o;
+                }
             }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
+        named_bar_sync(1, 128);
         if (warp == 2 && lane == 0) {
             for (int i = 0; i < nqb; ++i)
                 tma_store_3d(&args.tmDQ, i < 2 ? sP + i * TILE_BYTES : sdS, h * 64, i * 128, b);
@@ -619,11 +668,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         // ================================ dS warps ================================
         // 8 warps with the same (q, half) split as the P warps
         const int q = warp & 3;
-        const int half = (warp - 10) >> 2;
+        const int half = (warp - 6) >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int sw = row & 7;
-        const bool prof_thread = threadIdx.x == 320;
+        const bool prof_thread = threadIdx.x == 192;
         // delta * scale of this thread's query rows: rowsum(dO * O) over the 64 head dimensions
         float sdelta[3];
 #pragma unroll
@@ -639,39 +688,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             }
             sdelta[i] = acc * args.scale;
         }
-        // key block j is complete: dK_j, dV_j -> bf16 -> 64 bytes per thread straight to global memory
-        // (TMEM lane = key index inside the block; each half converts 32 of the 64 head dimensions)
-        auto store_dkv = [&](int j) {
-            const int kv = min(BK_KEYS, T - j * BK_KEYS);
-            mbar_wait(dkv_full, j & 1);
-            tc_fence_after();
-            const bool key_warp = q * 32 < kv;
-            __nv_bfloat16* base = args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner + h * 64 + half * 32;
-#pragma unroll 1
-            for (int part = 0; part < 4; ++part) {  // (dK | dV) x (16 columns)
-                const int a = part >> 1, c16 = (part & 1) * 16;
-                uint32_t o[16];
-                if (key_warp) {
-                    tmem_ld_32x16(t_row + BK_T_DK + a * 64 + half * 32 + c16, o);
-                    tmem_ld_wait();
-                }
-                if (part == 3) {
-                    tc_fence_before();
-                    mbar_arrive_warp(dkv_free);
-                }
-                if (key_warp && row < kv) {
-                    uint4* dst = reinterpret_cast<uint4*>(base + (1 + a) * inner + c16);
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
-                        v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
-                        v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
-                        v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
-                        dst[g] = v;
-                    }
-                }
-            }
+        auto store_dk = [&](int j) {
+            const int kvp = min(BK_KEYS, T - j * BK_KEYS);
+            bwd_store_acc<2>(t_row + BK_T_DK + half * 32,
+                             args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner + inner + h * 64 + half * 32,
+                             q * 32 < kvp, row < kvp, dk_full, j & 1, dk_free);
         };
         int p = 0;
         for (int j = 0; j < nkb; ++j) {
@@ -750,13 +771,13 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 mbar_arrive_warp(&ds_full[pp]);
                 if (prof_thread && p < 8) PROF(152 + p * 4);
                 if (i == 0 && j > 0) {
-                    store_dkv(j - 1);  // by now d(j-1, last) has long retired
-                    // every MMA of block j-1 has retired (dk_full, and X's are causally earlier): refill its K/V stage
-                    if (warp == 10 && lane == 0 && j + 1 < nkb) load_kv(j + 1);
+                    store_dk(j - 1);  // by now d(j-1, last) has long retired
+                    // every MMA of block j-1 has retired (dk_full; X's are causally earlier): refill its K/V stage
+                    if (warp == 6 && lane == 0 && j + 1 < nkb) load_kv(j + 1);
                 }
             }
         }
-        store_dkv(nkb - 1);
+        store_dk(nkb - 1);
     }
     tc_fence_before();
     __syncthreads();
