@@ -74,8 +74,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int WBUF_BYTES = 32 * 128;        // one epilogue-warp staging box: 32 rows x 128 B (128B-swizzled)
-constexpr int TN_THREADS = 384;             // 4 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
+#ifndef SVIT_EPI_WARPS
+#define SVIT_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = SVIT_EPI_WARPS;   // multiple of 4: EPI_NP warps per TMEM lane quadrant
+constexpr int EPI_NP = EPI_WARPS / 4;
+constexpr int TN_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + the epilogue warps
 constexpr int SMEM_LIMIT = 232448;          // 227 KB
 
 struct TnArgs {
@@ -93,7 +97,7 @@ struct EpiTraits {
     static constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU);
     // staging boxes per epilogue warp: in-place aux/out rotation of 3, two outputs double-buffered, or one output x2
     // (the A-resident variant gives 96 KB to the A row block and makes do with 2 boxes per warp)
-    static constexpr int NBUF = ARES ? 2 : (HAS_AUX ? 3 : (MODE == EPI_GELU ? 4 : 2));
+    static constexpr int NBUF = (ARES || EPI_WARPS > 8) ? 2 : (HAS_AUX ? 3 : 2);
 };
 
 template <int BN, int CG, int MODE, bool ARES>
@@ -325,13 +329,13 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         // ===================== aux (residual / pre-activation) loader =====================
         // serves the per-warp rings in job order; job k of a warp lands in ring slot k % 3
         if (HAS_AUX && elect_one()) {
-            int kcnt[2] = {0, 0};  // jobs issued so far per parity group
+            int kcnt[EPI_NP] = {};  // jobs issued so far per warp group
             int it = 0;
             for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
                 const int m0 = (tile / tiles_n) * TM + row_off;
                 const int n0 = (tile % tiles_n) * BN;
                 for (int u = 0; u < UNITS; ++u) {
-                    const int p = (it * UNITS + u) & 1;
+                    const int p = (it * UNITS + u) % EPI_NP;
                     const int k = kcnt[p]++;
                     const int slot = k % NBUF;
                     const uint32_t ph = (k / NBUF) & 1;
@@ -348,12 +352,14 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         }
     } else if (warp >= 4) {
         // ===================== epilogue: 8 independent warps =====================
-        const int ew = warp - 4;       // 0..7
+        const int ew = warp - 4;       // 0 .. EPI_WARPS-1
         const int q = ew & 3;          // TMEM lane quadrant == 32-row slice of the tile
-        const int p = ew >> 2;         // unit parity owned by this warp
+        const int p = ew >> 2;         // this warp owns the units u with (it * UNITS + u) % EPI_NP == p
         uint8_t* wbuf = sEpi + ew * NBUF * WBUF_BYTES;
         float* wbias = sBias + ew * 64;
         const int sw = lane & 7;       // swizzle key of this thread's row inside a 32-row box
+        constexpr int CPH = 32 * (int)sizeof(OutT) / 16;  // 16-byte chunks per 32-column half of a unit (4 bf16, 8 fp32)
+        constexpr int EPC = 16 / (int)sizeof(OutT);       // elements per chunk
         int it = 0, k = 0;             // k = jobs done by this warp
         for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
             const int m0 = (tile / tiles_n) * TM + row_off + q * 32;  // first row of this warp's slice
@@ -362,13 +368,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
             const uint32_t aphase = (it >> 1) & 1;
             const uint32_t t_addr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
             const int grow = m0 + lane;
-            // units of this tile owned by this warp: u with ((it*UNITS + u) & 1) == p
-            const int u_first = ((it * UNITS) & 1) == p ? 0 : 1;
+            const int u_first = ((p - it * UNITS) % EPI_NP + EPI_NP) % EPI_NP;
             int u_last = -1;
-            for (int u = u_first; u < UNITS; u += 2) u_last = u;
+            for (int u = u_first; u < UNITS; u += EPI_NP) u_last = u;
             bool waited = false;
 #pragma unroll 1
-            for (int u = u_first; u < UNITS; u += 2, ++k) {
+            for (int u = u_first; u < UNITS; u += EPI_NP, ++k) {
                 const int c0 = n0 + u * UC;
                 // bias slice of this unit -> warp-private shared memory (broadcast reads below)
                 __syncwarp();
@@ -379,37 +384,6 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     tc_fence_after();
                     waited = true;
                 }
-                float v[UC];
-#pragma unroll
-                for (int hh = 0; hh < UC / 32; ++hh) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_addr + u * UC + hh * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[hh * 32 + j] = __uint_as_float(r[j]) + wbias[hh * 32 + j];
-                }
-                if (u == u_last) {
-                    // this warp's slice of the accumulator is fully read: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
-                        else mbar_arrive(&tempty_bar[as]);
-                    }
-                }
-                if (MODE == EPI_STORE && args.rowtab != nullptr) {
-                    const float* tr = args.rowtab + static_cast<size_t>(grow % args.rowtab_period) * N + c0;
-#pragma unroll
-                    for (int j = 0; j < UC; j += 4) {
-                        if (c0 + j < N) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(tr + j);
-                            v[j] += t4.x;
-                            v[j + 1] += t4.y;
-                            v[j + 2] += t4.z;
-                            v[j + 3] += t4.w;
-                        }
-                    }
-                }
                 // ---- pick the staging box(es) of this job ----
                 uint8_t* obuf;
                 uint8_t* obuf2 = nullptr;
@@ -417,31 +391,6 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     const int slot = k % NBUF;
                     obuf = wbuf + slot * WBUF_BYTES;
                     mbar_wait(&afull_bar[ew * 3 + slot], (k / NBUF) & 1);
-                    const uint8_t* arow = obuf + lane * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint4 a4 = *reinterpret_cast<const uint4*>(arow + ((c ^ sw) << 4));
-                        if (sizeof(OutT) == 4) {
-                            v[(c * 4 + 0) % UC] += __uint_as_float(a4.x);
-                            v[(c * 4 + 1) % UC] += __uint_as_float(a4.y);
-                            v[(c * 4 + 2) % UC] += __uint_as_float(a4.z);
-                            v[(c * 4 + 3) % UC] += __uint_as_float(a4.w);
-                        } else {
-                            const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
-                                if (MODE == EPI_DGELU) {
-                                    v[(c * 8 + e * 2) % UC] *= dgelu_f(lo);
-                                    v[(c * 8 + e * 2 + 1) % UC] *= dgelu_f(hi);
-                                } else {
-                                    v[(c * 8 + e * 2) % UC] += lo;
-                                    v[(c * 8 + e * 2 + 1) % UC] += hi;
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();  // every lane has consumed the aux box before it is overwritten in place
                 } else if constexpr (MODE == EPI_GELU) {
                     if constexpr (NBUF == 4) {
                         obuf = wbuf + (k & 1) * 2 * WBUF_BYTES;
@@ -458,41 +407,102 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     __syncwarp();
                 }
                 uint8_t* orow = obuf + lane * 128;
-                if (sizeof(OutT) == 4) {
+                // ---- the unit in 32-column halves: TMEM -> registers -> fused epilogue -> staging box ----
+#pragma unroll 1
+                for (int hh = 0; hh < UC / 32; ++hh) {
+                    float v[32];
+                    {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_addr + u * UC + hh * 32, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4 o;
-                        o.x = __float_as_uint(v[(c * 4 + 0) % UC]);
-                        o.y = __float_as_uint(v[(c * 4 + 1) % UC]);
-                        o.z = __float_as_uint(v[(c * 4 + 2) % UC]);
-                        o.w = __float_as_uint(v[(c * 4 + 3) % UC]);
-                        *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = o;
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + wbias[hh * 32 + j];
                     }
-                } else {
-                    if (MODE != EPI_GELU_ONLY) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            uint4 o;
-                            o.x = pack_bf16(v[(c * 8 + 0) % UC], v[(c * 8 + 1) % UC]);
-                            o.y = pack_bf16(v[(c * 8 + 2) % UC], v[(c * 8 + 3) % UC]);
-                            o.z = pack_bf16(v[(c * 8 + 4) % UC], v[(c * 8 + 5) % UC]);
-                            o.w = pack_bf16(v[(c * 8 + 6) % UC], v[(c * 8 + 7) % UC]);
-                            *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = o;
+                    if (u == u_last && hh == UC / 32 - 1) {
+                        // this warp's slice of the accumulator is fully read: hand the TMEM stage back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
+                            else mbar_arrive(&tempty_bar[as]);
                         }
                     }
-                    if (MODE == EPI_GELU || MODE == EPI_GELU_ONLY) {
-                        uint8_t* orow2 = (MODE == EPI_GELU) ? obuf2 + lane * 128 : orow;
+                    if (MODE == EPI_STORE && args.rowtab != nullptr) {
+                        const float* tr = args.rowtab + static_cast<size_t>(grow % args.rowtab_period) * N + c0 + hh * 32;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            float g[8];
+                        for (int j = 0; j < 32; j += 4) {
+                            if (c0 + hh * 32 + j < N) {
+                                const float4 t4 = *reinterpret_cast<const float4*>(tr + j);
+                                v[j] += t4.x;
+                                v[j + 1] += t4.y;
+                                v[j + 2] += t4.z;
+                                v[j + 3] += t4.w;
+                            }
+                        }
+                    }
+                    if constexpr (HAS_AUX) {
+                        // residual / pre-activation: read this half of the aux box (each lane only touches its own row,
+                        // so the result can overwrite it in place)
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) g[e] = gelu_f(v[(c * 8 + e) % UC]);
+                        for (int c = 0; c < CPH; ++c) {
+                            const uint4 a4 = *reinterpret_cast<const uint4*>(orow + (((hh * CPH + c) ^ sw) << 4));
+                            if (sizeof(OutT) == 4) {
+                                v[c * 4 + 0] += __uint_as_float(a4.x);
+                                v[c * 4 + 1] += __uint_as_float(a4.y);
+                                v[c * 4 + 2] += __uint_as_float(a4.z);
+                                v[c * 4 + 3] += __uint_as_float(a4.w);
+                            } else {
+                                const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
+                                    if (MODE == EPI_DGELU) {
+                                        v[c * 8 + e * 2] *= dgelu_f(lo);
+                                        v[c * 8 + e * 2 + 1] *= dgelu_f(hi);
+                                    } else {
+                                        v[c * 8 + e * 2] += lo;
+                                        v[c * 8 + e * 2 + 1] += hi;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (sizeof(OutT) == 4) {
+#pragma unroll
+                        for (int c = 0; c < CPH; ++c) {
                             uint4 o;
-                            o.x = pack_bf16(g[0], g[1]);
-                            o.y = pack_bf16(g[2], g[3]);
-                            o.z = pack_bf16(g[4], g[5]);
-                            o.w = pack_bf16(g[6], g[7]);
-                            *reinterpret_cast<uint4*>(orow2 + ((c ^ sw) << 4)) = o;
+                            o.x = __float_as_uint(v[c * 4 + 0]);
+                            o.y = __float_as_uint(v[c * 4 + 1]);
+                            o.z = __float_as_uint(v[c * 4 + 2]);
+                            o.w = __float_as_uint(v[c * 4 + 3]);
+                            *reinterpret_cast<uint4*>(orow + (((hh * CPH + c) ^ sw) << 4)) = o;
+                        }
+                    } else {
+                        if (MODE != EPI_GELU_ONLY) {
+#pragma unroll
+                            for (int c = 0; c < CPH; ++c) {
+                                uint4 o;
+                                o.x = pack_bf16(v[c * 8 + 0], v[c * 8 + 1]);
+                                o.y = pack_bf16(v[c * 8 + 2], v[c * 8 + 3]);
+                                o.z = pack_bf16(v[c * 8 + 4], v[c * 8 + 5]);
+                                o.w = pack_bf16(v[c * 8 + 6], v[c * 8 + 7]);
+                                *reinterpret_cast<uint4*>(orow + (((hh * CPH + c) ^ sw) << 4)) = o;
+                            }
+                        }
+                        if (MODE == EPI_GELU || MODE == EPI_GELU_ONLY) {
+                            uint8_t* orow2 = (MODE == EPI_GELU) ? obuf2 + lane * 128 : orow;
+#pragma unroll
+                            for (int c = 0; c < CPH; ++c) {
+                                float g[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) g[e] = gelu_f(v[c * 8 + e]);
+                                uint4 o;
+                                o.x = pack_bf16(g[0], g[1]);
+                                o.y = pack_bf16(g[2], g[3]);
+                                o.z = pack_bf16(g[4], g[5]);
+                                o.w = pack_bf16(g[6], g[7]);
+                                *reinterpret_cast<uint4*>(orow2 + (((hh * CPH + c) ^ sw) << 4)) = o;
+                            }
                         }
                     }
                 }
@@ -504,7 +514,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     tma_store_commit();
                     if constexpr (HAS_AUX) {
                         // the store of the previous job has finished reading its box: give that slot back to the
-                        // aux loader (it then prefetches the tile of job k+2 into it)
+                        // aux loader (it then prefetches the tile of a later job into it)
                         if (k > 0) {
                             tma_store_wait_read<1>();
                             mbar_arrive(&aempty_bar[ew * 3 + (k - 1) % NBUF]);
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                 }
             }
             if (u_last < 0) {
-                // no unit of this tile belongs to this warp (UNITS == 1): still release the accumulator stage
+                // no unit of this tile belongs to this warp: still release the accumulator stage
                 if (!waited) mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_before();
                 __syncwarp();
@@ -826,9 +836,9 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
     // (measured: -3 % for the plain store epilogue; the GELU / aux epilogues lose more from their halved staging rings)
     bool ares = cg == 2 && d.K <= ARES_KB * BK && (d.N + BN - 1) / BN >= 3 && d.mode == EPI_STORE;
     if (force_ares == 0) ares = false;
-    if (force_ares == 1 && d.K <= ARES_KB * BK) ares = true;
+    if (force_ares == 1 && d.K <= ARES_KB * BK && cg == 2) ares = true;
     if (cg == 2) return ares ? dispatch_tn<2, true>(d, a, num_sms, stream) : dispatch_tn<2, false>(d, a, num_sms, stream);
-    return ares ? dispatch_tn<1, true>(d, a, num_sms, stream) : dispatch_tn<1, false>(d, a, num_sms, stream);
+    return dispatch_tn<1, false>(d, a, num_sms, stream);  // (the A-resident variant exists for CTA pairs only)
 }
 
 int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream) {
