@@ -45,37 +45,63 @@ int launch_gather_patches(const float* mesh, const int32_t* table, float* out, i
     return 0;
 }
 
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
 // =================================================================================================
 // a2/a8: pack patches (+ MPP corruption, + optional fused gather / z-score)
 // =================================================================================================
-__global__ void pack_patches_kernel(const PackDesc d) {
+// One thread per 8 consecutive output elements (one 16-byte store); the operand row is channel-major (k = c * V + v),
+// so the 8 inputs of a thread are consecutive floats of one channel (or straddle one channel boundary).
+__global__ void __launch_bounds__(256) pack_patches_kernel(const PackDesc d) {
     const int T = d.N + 1;
-    const int row = blockIdx.x;  // b*T + t
-    const int b = row / T, t = row % T;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d.A) + static_cast<size_t>(row) * d.Kp;
+    const int nvec = d.Kp >> 3;
+    const size_t total = static_cast<size_t>(d.B) * T * nvec;
     const int CV = d.C * d.V;
-    if (t == 0) {
-        for (int k = threadIdx.x; k < d.Kp; k += blockDim.x) dst[k] = __float2bfloat16(0.0f);
-        return;
-    }
-    int n = t - 1;
-    const size_t bn = static_cast<size_t>(b) * d.N + n;
-    const bool replace = d.replace_sel != nullptr && d.replace_sel[bn] != 0;
-    if (!replace && d.swap_sel != nullptr && d.swap_sel[bn] != 0) n = static_cast<int>(d.swap_src[bn]);
-    for (int k = threadIdx.x; k < d.Kp; k += blockDim.x) {
-        float val = 0.0f;
-        if (k < CV) {
-            const int c = k / d.V, v = k - c * d.V;
-            if (replace) {
-                val = d.mask_token[v * d.C + c];
-            } else if (d.table != nullptr) {
-                val = __ldg(d.x + (static_cast<size_t>(b) * d.C + c) * d.n_mesh + d.table[static_cast<size_t>(v) * d.N + n]);
-                if (d.ch_mean != nullptr) val = (val - d.ch_mean[c]) / d.ch_std[c];
-            } else {
-                val = __ldg(d.x + ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v);
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t row = idx / nvec;  // b*T + t
+        const int i = static_cast<int>(idx - row * nvec);
+        const int b = static_cast<int>(row / T), t = static_cast<int>(row - static_cast<size_t>(b) * T);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.A) + row * d.Kp) + i;
+        if (t == 0) {
+            *dst = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        int n = t - 1;
+        const size_t bn = static_cast<size_t>(b) * d.N + n;
+        const bool replace = d.replace_sel != nullptr && d.replace_sel[bn] != 0;
+        if (!replace && d.swap_sel != nullptr && d.swap_sel[bn] != 0) n = static_cast<int>(d.swap_src[bn]);
+        float val[8];
+        const int k0 = i * 8;
+        int c = k0 / d.V, v = k0 - c * d.V;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = 0.0f;
+            if (k0 + e < CV) {
+                if (replace) {
+                    x = d.mask_token[v * d.C + c];
+                } else if (d.table != nullptr) {
+                    x = __ldg(d.x + (static_cast<size_t>(b) * d.C + c) * d.n_mesh + d.table[static_cast<size_t>(v) * d.N + n]);
+                    if (d.ch_mean != nullptr) x = (x - d.ch_mean[c]) / d.ch_std[c];
+                } else {
+                    x = __ldg(d.x + ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v);
+                }
+            }
+            val[e] = x;
+            if (++v == d.V) {
+                v = 0;
+                ++c;
             }
         }
-        dst[k] = __float2bfloat16(val);
+        uint4 o;
+        o.x = pack2_bf16(val[0], val[1]);
+        o.y = pack2_bf16(val[2], val[3]);
+        o.z = pack2_bf16(val[4], val[5]);
+        o.w = pack2_bf16(val[6], val[7]);
+        *dst = o;
     }
 }
 
@@ -85,7 +111,10 @@ int launch_pack_patches(const PackDesc& d, cudaStream_t st) {
         set_error("pack_patches: Kp=%d must be a multiple of 8 and >= C*V=%d", d.Kp, d.C * d.V);
         return -2;
     }
-    pack_patches_kernel<<<d.B * (d.N + 1), 256, 0, st>>>(d);
+    const size_t total = static_cast<size_t>(d.B) * (d.N + 1) * (d.Kp / 8);
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    pack_patches_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d);
     SVIT_CHECK_LAUNCH("pack_patches");
     return 0;
 }
@@ -565,19 +594,58 @@ int launch_prepare_rowtab(const float* pos, const float* cls, const float* bias,
 // =================================================================================================
 // patch-embedding backward reductions
 // =================================================================================================
+// dpos[t, :] += sum_b g0[b, t, :] ; dcls += row t = 0 ; dbias += rows t >= 1.
+// grid (T, batch slices): every block sums its slice of the batch for one token position (float4 loads, 4 independent
+// accumulator chains per thread) and adds the partial sums atomically.
 __global__ void embed_bwd_kernel(const float* __restrict__ g0, float* __restrict__ dpos, float* __restrict__ dcls,
                                  float* __restrict__ dbias, int B, int T, int D) {
     const int t = blockIdx.x;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float s = 0.0f;
-        for (int b = 0; b < B; ++b) s += g0[(static_cast<size_t>(b) * T + t) * D + d];
-        atomicAdd(&dpos[static_cast<size_t>(t) * D + d], s);
-        if (t == 0) atomicAdd(&dcls[d], s);
-        else atomicAdd(&dbias[d], s);
+    const int per = (B + gridDim.y - 1) / gridDim.y;
+    const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+    if ((D & 3) == 0) {
+        for (int d4 = threadIdx.x; d4 < (D >> 2); d4 += blockDim.x) {
+            float4 acc[4] = {};
+            int b = b0;
+            for (; b + 4 <= b1; b += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4*>(g0 + (static_cast<size_t>(b + u) * T + t) * D) + d4);
+                    acc[u].x += v.x;
+                    acc[u].y += v.y;
+                    acc[u].z += v.z;
+                    acc[u].w += v.w;
+                }
+            }
+            for (; b < b1; ++b) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(g0 + (static_cast<size_t>(b) * T + t) * D) + d4);
+                acc[0].x += v.x;
+                acc[0].y += v.y;
+                acc[0].z += v.z;
+                acc[0].w += v.w;
+            }
+            const float sx[4] = {acc[0].x + acc[1].x + acc[2].x + acc[3].x, acc[0].y + acc[1].y + acc[2].y + acc[3].y,
+                                 acc[0].z + acc[1].z + acc[2].z + acc[3].z, acc[0].w + acc[1].w + acc[2].w + acc[3].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d = d4 * 4 + e;
+                atomicAdd(&dpos[static_cast<size_t>(t) * D + d], sx[e]);
+                atomicAdd(t == 0 ? &dcls[d] : &dbias[d], sx[e]);
+            }
+        }
+    } else {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float s = 0.0f;
+            for (int b = b0; b < b1; ++b) s += g0[(static_cast<size_t>(b) * T + t) * D + d];
+            atomicAdd(&dpos[static_cast<size_t>(t) * D + d], s);
+            atomicAdd(t == 0 ? &dcls[d] : &dbias[d], s);
+        }
     }
 }
 int launch_embed_bwd(const float* g0, float* dpos, float* dcls, float* dbias, int B, int T, int D, cudaStream_t st) {
-    embed_bwd_kernel<<<T, 128, 0, st>>>(g0, dpos, dcls, dbias, B, T, D);
+    int slices = (4 * 148 + T - 1) / T;  // ~4 blocks per SM
+    if (slices > B) slices = B;
+    if (slices < 1) slices = 1;
+    embed_bwd_kernel<<<dim3(T, slices), 128, 0, st>>>(g0, dpos, dcls, dbias, B, T, D);
     SVIT_CHECK_LAUNCH("embed_bwd");
     return 0;
 }
