@@ -36,10 +36,10 @@ if "gemm" in which:
     def gemm(name, N, K, mode, f32):
         A = (torch.randn(M, K, device=dev) * 0.5).bfloat16(); W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
         bias = torch.zeros(N, device=dev); odt = torch.float32 if f32 else torch.bfloat16
-        o = torch.empty(M, N, device=dev, dtype=odt); o2 = torch.empty(M, N, device=dev, dtype=odt) if mode == 1 else None
-        aux = torch.randn(M, N, device=dev).to(odt) if mode in (2, 3) else None
+        o = torch.empty(M, N, device=dev, dtype=odt); o2 = torch.empty(M, N, device=dev, dtype=odt) if mode in (1, 5) else None
+        aux = torch.randn(M, N, device=dev).to(odt) if mode in (2, 3, 6) else None
         osz = 4 if f32 else 2
-        by = M*K*2 + N*K*2 + M*N*osz*(2 if mode == 1 else 1) + (M*N*osz if aux is not None else 0)
+        by = M*K*2 + N*K*2 + M*N*osz*(2 if mode in (1, 5) else 1) + (M*N*osz if aux is not None else 0)
         timeit(name, lambda: lib.svit_gemm_tn(ptr(A), ptr(W), ptr(o), ptr(o2), ptr(aux), ptr(bias), vp(0), 1, M, N, K, K, K, N, mode, int(f32), SMS, st()),
                bytes_=by, flops=2.0*M*N*K)
     gemm("gemm qkv   [M,384]x[1152] store bf16", 1152, 384, 0, False)
@@ -47,7 +47,9 @@ if "gemm" in which:
     gemm("gemm fc1   [M,384]x[1536] gelu x2", 1536, 384, 1, False)
     gemm("gemm fc1   [M,384]x[1536] gelu only", 1536, 384, 4, False)
     gemm("gemm fc2   [M,1536]x[384] resid f32", 384, 1536, 2, True)
+    gemm("gemm fc1   [M,384]x[1536] gelu' + gelu", 1536, 384, 5, False)
     gemm("gemm dfc2  [M,384]x[1536] dgelu", 1536, 384, 3, False)
+    gemm("gemm dfc2  [M,384]x[1536] * stored gelu'", 1536, 384, 6, False)
     gemm("gemm dfc1  [M,1536]x[384] store bf16", 384, 1536, 0, False)
     gemm("gemm dqkv  [M,1152]x[384] store bf16", 384, 1152, 0, False)
 if "wgrad" in which:

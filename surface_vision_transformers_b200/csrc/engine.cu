@@ -207,8 +207,9 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
                     pp(OUT_B), xin));
         RET_IF(launch_ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
         if (w.training) {
+            // training keeps gelu'(u) (in L.u) instead of u: the backward epilogue is then a single multiply
             RET_IF(gemm(e, st, L.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, L.u, mlp, M, mlp, D,
-                        EPI_GELU, 0, pp(FC1_B), nullptr, L.h));
+                        EPI_GELU_GRAD, 0, pp(FC1_B), nullptr, L.h));
         } else {
             RET_IF(gemm(e, st, L.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, L.h, mlp, M, mlp, D,
                         EPI_GELU_ONLY, 0, pp(FC1_B)));
@@ -233,8 +234,8 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         auto pp = [&](int which) { return P + e->poff[pidx_layer(l, which)]; };
         auto gp = [&](int which) { return G + e->poff[pidx_layer(l, which)]; };
         // ---- FeedForward ----
-        // du = (g W2) * gelu'(u)
-        RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_DGELU,
+        // du = (g W2) * gelu'(u)      (L.u holds gelu'(u), stored by the forward epilogue)
+        RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_MUL,
                     0, nullptr, L.u));
         RET_IF(wgrad(e, st, w.g16, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp));
         // da2 = du W1

@@ -61,6 +61,13 @@ __device__ __forceinline__ float gelu_f(float x) {
     float E;
     return x * gauss_cdf(x, E);
 }
+// gelu(x) and gelu'(x) from one evaluation of Phi and the Gaussian
+__device__ __forceinline__ float gelu_and_grad(float x, float& grad) {
+    float E;
+    const float cdf = gauss_cdf(x, E);
+    grad = fmaf(x * 0.3989422804014327f, E, cdf);
+    return x * cdf;
+}
 __device__ __forceinline__ float dgelu_f(float x) {
     float E;
     const float cdf = gauss_cdf(x, E);
@@ -94,7 +101,8 @@ constexpr int ARES_KB = 6;  // A-resident mode: up to 6 K blocks (K <= 384) of t
 
 template <int MODE, bool ARES>
 struct EpiTraits {
-    static constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU);
+    static constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU || MODE == EPI_MUL);
+    static constexpr bool TWO_OUT = (MODE == EPI_GELU || MODE == EPI_GELU_GRAD);
     // staging boxes per epilogue warp: in-place aux/out rotation of 3, two outputs double-buffered, or one output x2
     // (the A-resident variant gives 96 KB to the A row block and makes do with 2 boxes per warp)
     static constexpr int NBUF = (ARES || EPI_WARPS > 8) ? 2 : (HAS_AUX ? 3 : 2);
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         tma_prefetch_desc(&args.tmA);
         tma_prefetch_desc(&args.tmB);
         tma_prefetch_desc(&args.tmOut);
-        if (MODE == EPI_GELU) tma_prefetch_desc(&args.tmOut2);
+        if (ET::TWO_OUT) tma_prefetch_desc(&args.tmOut2);
         if (HAS_AUX) tma_prefetch_desc(&args.tmAux);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     const int slot = k % NBUF;
                     obuf = wbuf + slot * WBUF_BYTES;
                     mbar_wait(&afull_bar[ew * 3 + slot], (k / NBUF) & 1);
-                } else if constexpr (MODE == EPI_GELU) {
+                } else if constexpr (ET::TWO_OUT) {
                     if constexpr (NBUF == 4) {
                         obuf = wbuf + (k & 1) * 2 * WBUF_BYTES;
                         if (lane == 0) tma_store_wait_read<1>();  // the store that used this pair two jobs ago has drained
@@ -459,6 +467,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                                     if (MODE == EPI_DGELU) {
                                         v[c * 8 + e * 2] *= dgelu_f(lo);
                                         v[c * 8 + e * 2 + 1] *= dgelu_f(hi);
+                                    } else if (MODE == EPI_MUL) {
+                                        v[c * 8 + e * 2] *= lo;
+                                        v[c * 8 + e * 2 + 1] *= hi;
                                     } else {
                                         v[c * 8 + e * 2] += lo;
                                         v[c * 8 + e * 2 + 1] += hi;
@@ -478,6 +489,26 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                             *reinterpret_cast<uint4*>(orow + (((hh * CPH + c) ^ sw) << 4)) = o;
                         }
                     } else {
+                        if constexpr (MODE == EPI_GELU_GRAD) {
+                            uint8_t* orow2 = obuf2 + lane * 128;
+#pragma unroll
+                            for (int c = 0; c < CPH; ++c) {
+                                float g[8], dg[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) g[e] = gelu_and_grad(v[c * 8 + e], dg[e]);
+                                uint4 o;
+                                o.x = pack_bf16(dg[0], dg[1]);
+                                o.y = pack_bf16(dg[2], dg[3]);
+                                o.z = pack_bf16(dg[4], dg[5]);
+                                o.w = pack_bf16(dg[6], dg[7]);
+                                *reinterpret_cast<uint4*>(orow + (((hh * CPH + c) ^ sw) << 4)) = o;
+                                o.x = pack_bf16(g[0], g[1]);
+                                o.y = pack_bf16(g[2], g[3]);
+                                o.z = pack_bf16(g[4], g[5]);
+                                o.w = pack_bf16(g[6], g[7]);
+                                *reinterpret_cast<uint4*>(orow2 + (((hh * CPH + c) ^ sw) << 4)) = o;
+                            }
+                        } else {
                         if (MODE != EPI_GELU_ONLY) {
 #pragma unroll
                             for (int c = 0; c < CPH; ++c) {
@@ -504,13 +535,14 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                                 *reinterpret_cast<uint4*>(orow2 + (((hh * CPH + c) ^ sw) << 4)) = o;
                             }
                         }
+                        }
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(&args.tmOut, obuf, c0, m0);
-                    if (MODE == EPI_GELU) tma_store_2d(&args.tmOut2, obuf2, c0, m0);
+                    if (ET::TWO_OUT) tma_store_2d(&args.tmOut2, obuf2, c0, m0);
                     tma_store_commit();
                     if constexpr (HAS_AUX) {
                         // the store of the previous job has finished reading its box: give that slot back to the
@@ -790,6 +822,8 @@ static int dispatch_tn(const GemmTnDesc& d, const TnArgs& a, int num_sms, cudaSt
         if (d.mode == EPI_RESID) return launch_tn_inst<__nv_bfloat16, EPI_RESID, BN, CG, ARES>(a, num_sms, stream);
         if (d.mode == EPI_DGELU) return launch_tn_inst<__nv_bfloat16, EPI_DGELU, BN, CG, ARES>(a, num_sms, stream);
         if (d.mode == EPI_GELU_ONLY) return launch_tn_inst<__nv_bfloat16, EPI_GELU_ONLY, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_GELU_GRAD) return launch_tn_inst<__nv_bfloat16, EPI_GELU_GRAD, BN, CG, ARES>(a, num_sms, stream);
+        if (d.mode == EPI_MUL) return launch_tn_inst<__nv_bfloat16, EPI_MUL, BN, CG, ARES>(a, num_sms, stream);
     }
     set_error("gemm_tn: unsupported mode %d for out_f32=%d", d.mode, d.out_f32);
     return -4;
@@ -824,8 +858,8 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
     const TmapDtype odt = d.out_f32 ? TmapDtype::F32 : TmapDtype::BF16;
     const int osz = d.out_f32 ? 4 : 2;
     rc |= make_tmap_2d(&a.tmOut, d.out, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
-    if (d.mode == EPI_GELU) rc |= make_tmap_2d(&a.tmOut2, d.out2, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
-    if (d.mode == EPI_RESID || d.mode == EPI_DGELU)
+    if (d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD) rc |= make_tmap_2d(&a.tmOut2, d.out2, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
+    if (d.mode == EPI_RESID || d.mode == EPI_DGELU || d.mode == EPI_MUL)
         rc |= make_tmap_2d(&a.tmAux, d.aux, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
     if (rc != 0) {
         set_error("gemm_tn: tensor map creation failed: %s", tmap_last_error());

@@ -19,14 +19,18 @@ enum EpiMode : int {
     EPI_RESID = 2,  // out = acc + bias + aux                                    (aux/out same dtype)
     EPI_DGELU = 3,  // out = acc * gelu'(aux)                                    (aux/out bf16)
     EPI_GELU_ONLY = 4,  // out = gelu(acc + bias)   (inference: pre-activation not kept)
+    EPI_GELU_GRAD = 5,  // out = gelu'(acc + bias); out2 = gelu(acc + bias)  (training: the backward pass only ever needs
+                        //       gelu'(u), so the forward epilogue -- which has exp(-u^2/2) and Phi(u) at hand -- stores that
+                        //       instead of u and the backward epilogue shrinks to one multiply)
+    EPI_MUL = 6,        // out = acc * aux                                   (aux/out bf16)
 };
 
 struct GemmTnDesc {
     const void* A;      // bf16 [M, K], row pitch lda elements
     const void* B;      // bf16 [N, K], row pitch ldb elements
     void* out;          // OutT [M, N], row pitch ldo elements
-    void* out2;         // EPI_GELU only: bf16 [M, N] (pitch ldo)
-    const void* aux;    // EPI_RESID / EPI_DGELU: same dtype/pitch as out
+    void* out2;         // EPI_GELU / EPI_GELU_GRAD: bf16 [M, N] (pitch ldo)
+    const void* aux;    // EPI_RESID / EPI_DGELU / EPI_MUL: same dtype/pitch as out
     const float* bias;  // [N] or nullptr
     const float* rowtab;  // [period, N] fp32 or nullptr (EPI_STORE only)
     int rowtab_period;

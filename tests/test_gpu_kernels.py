@@ -41,6 +41,10 @@ def dgelu(x):
     (1284, 1536, 384, 4, False, True, False),      # fc1 + bias + GELU (inference)
     (1284, 384, 1536, 2, True, True, False),       # fc2 + bias + residual
     (1284, 1536, 384, 3, False, False, False),     # dgrad * gelu'
+    (1284, 1536, 384, 5, False, True, False),      # fc1 + bias -> gelu' and gelu (what training stores)
+    (20544, 1536, 384, 5, False, True, False),
+    (1284, 1536, 384, 6, False, False, False),     # dgrad * stored gelu'
+    (20544, 1536, 384, 6, False, False, False),
     (1284, 384, 640, 0, True, False, True),        # patch embedding + cls/pos table
     (5136, 612, 384, 0, True, True, False),        # MPP decoder (N not a tile multiple)
     (20544, 1152, 384, 0, False, False, False),    # several persistent waves (CTA pairs, A-resident schedule)
@@ -61,8 +65,8 @@ def test_gemm_tn(env, M, N, K, mode, f32, bias, rowtab):
     b = torch.randn(N, device=dev) if bias else None
     odt = torch.float32 if f32 else torch.bfloat16
     out = torch.full((M, N), float("nan"), device=dev, dtype=odt)
-    out2 = torch.full((M, N), float("nan"), device=dev, dtype=odt) if mode == 1 else None
-    aux = torch.randn(M, N, device=dev).to(odt) if mode in (2, 3) else None
+    out2 = torch.full((M, N), float("nan"), device=dev, dtype=odt) if mode in (1, 5) else None
+    aux = torch.randn(M, N, device=dev).to(odt) if mode in (2, 3, 6) else None
     period = 7
     rt = torch.randn(period, N, device=dev) if rowtab else None
     check(lib.svit_gemm_tn(ptr(A), ptr(B), ptr(out), ptr(out2), ptr(aux), ptr(b), ptr(rt), period, M, N, K, K, K, N, mode,
@@ -80,6 +84,11 @@ def test_gemm_tn(env, M, N, K, mode, f32, bias, rowtab):
         ref = acc + aux.float()
     elif mode == 3:
         ref = acc * dgelu(aux.float())
+    elif mode == 5:
+        assert rel_l2(out2, torch.nn.functional.gelu(acc)) < TOL
+        ref = dgelu(acc)
+    elif mode == 6:
+        ref = acc * aux.float()
     else:
         ref = torch.nn.functional.gelu(acc)
     assert torch.isfinite(out.float()).all()
