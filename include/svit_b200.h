@@ -53,6 +53,16 @@ int svit_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 unsigned long long svit_launch_count(void);
 
+/* ---- fp32 check mode (north star: "... tightening to 1e-4 in an fp32-accumulate check mode") ----
+ * With check mode on, svit_forward / svit_backward / svit_encoder_forward / svit_encoder_backward / svit_mpp_forward /
+ * svit_mpp_backward run the same operator sequence with every operand in fp32 on the CUDA cores (csrc/check.cu) instead
+ * of bf16 on the tensor cores; parameter and gradient layouts are unchanged, svit_workspace_bytes() reports the (larger)
+ * fp32 workspace, the bf16 weight shadows are not read (the MPP decoder weight is taken from the fp32 pointer last given
+ * to svit_mpp_prepare_weights).  Measured: outputs and every gradient within 1e-4 relative L2 of the fp32 reference
+ * restatement (tests/test_gpu_model.py).  Meant for verification, not for speed. */
+int svit_set_check_mode(svit_engine* e, int on);
+int svit_get_check_mode(const svit_engine* e);
+
 /* ---- engine life cycle (host-side object; owns no device memory) ---- */
 svit_engine* svit_create(const svit_config* cfg);
 void svit_destroy(svit_engine* e);

@@ -40,6 +40,8 @@ SIGNATURES = {
     "svit_shadow_bytes": (csz, [vp]),
     "svit_mpp_shadow_bytes": (csz, [vp]),
     "svit_workspace_bytes": (csz, [vp, ci, ci, ci]),
+    "svit_set_check_mode": (ci, [vp, ci]),
+    "svit_get_check_mode": (ci, [vp]),
     "svit_prepare_weights": (ci, [vp, vp, vp, vp]),
     "svit_mpp_prepare_weights": (ci, [vp, vp, vp, vp]),
     "svit_forward": (ci, [vp, vp, vp, vp, csz, vp, ci, vp, ci, vp, vp, vp, ci, vp]),

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "check.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "svit_b200.h"
@@ -31,6 +32,8 @@ struct svit_engine {
     // shadow offsets in bytes
     size_t sh_wpe, sh_rowtab, sh_qkv, sh_qkvT, sh_o, sh_oT, sh_w1, sh_w1T, sh_w2, sh_w2T, sh_total;
     size_t msh_wdec, msh_wdecT, msh_total;
+    int check;  // fp32 check mode (svit_set_check_mode)
+    const float* wdec_f32;  // fp32 master of the MPP decoder weight (recorded by svit_mpp_prepare_weights, check mode)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -278,6 +281,165 @@ static int embed_bwd(const svit_engine* e, Ws& w, float* G, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 check mode: same orchestration, every operand fp32 (check.cu)
+// ---------------------------------------------------------------------------------------------
+struct CkLayer {
+    float *xmid, *xout, *a1, *a2, *qkv, *O, *u, *h, *mean1, *rstd1, *mean2, *rstd2, *lse;
+};
+struct CkWs {
+    int B, M;
+    float *Ap, *x0;
+    std::vector<CkLayer> L;
+    float *g, *da, *dO, *dqkv, *du, *dy, *rvec;
+    bf16* g16;
+    size_t total;
+};
+static void ck_carve(const svit_engine* e, int B, int mpp, void* base, CkWs* w) {
+    Bump bp{reinterpret_cast<uint8_t*>(base), 0};
+    const size_t M = static_cast<size_t>(B) * e->T;
+    const size_t D = e->D, I = e->I, mlp = e->mlp;
+    w->B = B;
+    w->M = static_cast<int>(M);
+    w->Ap = bp.take<float>(M * e->K);
+    w->x0 = bp.take<float>(M * D);
+    w->L.resize(e->depth);
+    const size_t BHT = static_cast<size_t>(B) * e->H * e->T;
+    for (int l = 0; l < e->depth; ++l) {
+        CkLayer& L = w->L[l];
+        L.xmid = bp.take<float>(M * D);
+        L.xout = bp.take<float>(M * D);
+        L.a1 = bp.take<float>(M * D);
+        L.a2 = bp.take<float>(M * D);
+        L.qkv = bp.take<float>(M * 3 * I);
+        L.O = bp.take<float>(M * I);
+        L.u = bp.take<float>(M * mlp);
+        L.h = bp.take<float>(M * mlp);
+        L.mean1 = bp.take<float>(M);
+        L.rstd1 = bp.take<float>(M);
+        L.mean2 = bp.take<float>(M);
+        L.rstd2 = bp.take<float>(M);
+        L.lse = bp.take<float>(BHT);
+    }
+    w->g = bp.take<float>(M * D);
+    w->da = bp.take<float>(M * D);
+    w->dO = bp.take<float>(M * I);
+    w->dqkv = bp.take<float>(M * 3 * I);
+    w->du = bp.take<float>(M * mlp);
+    w->g16 = bp.take<bf16>(M * D);
+    w->dy = mpp ? bp.take<float>(M * e->K) : nullptr;
+    w->rvec = mpp ? bp.take<float>(D) : nullptr;
+    w->total = align_up(bp.off, 256);
+}
+static int ck_check_ws(const svit_engine* e, int B, int mpp, void* ws_ptr, size_t ws_bytes, CkWs* w) {
+    if (B <= 0) {
+        set_error("batch must be >= 1 (got %d)", B);
+        return -1;
+    }
+    if (ws_ptr == nullptr || (reinterpret_cast<uintptr_t>(ws_ptr) & 255)) {
+        set_error("workspace must be a 256-byte aligned device pointer");
+        return -1;
+    }
+    ck_carve(e, B, mpp, ws_ptr, w);
+    if (ws_bytes != 0 && w->total > ws_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", w->total, ws_bytes);
+        return -1;
+    }
+    return 0;
+}
+// Y[M, N] = X[M, K] W[N, K]^T (+ bias) (+ resid) ; optional gelu copy
+static int ck_linear(cudaStream_t st, const float* X, const float* W, float* Y, int M, int N, int K, const float* bias = nullptr,
+                     const float* resid = nullptr, float* gelu_out = nullptr) {
+    ck::Sgemm d{X, K, 1, W, 1, K, Y, N, M, N, K, bias, resid, gelu_out, 0};
+    return ck::sgemm(d, st);
+}
+// dX[M, K] = dY[M, N] W[N, K]
+static int ck_dgrad(cudaStream_t st, const float* dY, const float* W, float* dX, int M, int N, int K) {
+    ck::Sgemm d{dY, N, 1, W, K, 1, dX, K, M, K, N, nullptr, nullptr, nullptr, 0};
+    return ck::sgemm(d, st);
+}
+// dW[N, K] += dY[M, N]^T X[M, K]
+static int ck_wgrad(cudaStream_t st, const float* dY, const float* X, float* dW, int M, int N, int K) {
+    ck::Sgemm d{dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, nullptr, nullptr, 1};
+    return ck::sgemm(d, st);
+}
+
+static int ck_encoder_fwd(const svit_engine* e, const float* P, CkWs& w, const float* x_in, cudaStream_t st,
+                          const float** x_final) {
+    const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
+    const float* xin = x_in;
+    for (int l = 0; l < e->depth; ++l) {
+        CkLayer& L = w.L[l];
+        auto pp = [&](int which) { return P + e->poff[pidx_layer(l, which)]; };
+        RET_IF(ck::ln_fwd(xin, pp(LN1_W), pp(LN1_B), L.a1, L.mean1, L.rstd1, M, D, 1e-5f, st));
+        RET_IF(ck_linear(st, L.a1, pp(QKV_W), L.qkv, M, 3 * I, D));
+        RET_IF(ck::attn_fwd(L.qkv, L.O, L.lse, w.B, e->H, e->T, 0.125f, st));
+        RET_IF(ck_linear(st, L.O, pp(OUT_W), L.xmid, M, D, I, pp(OUT_B), xin));
+        RET_IF(ck::ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
+        RET_IF(ck_linear(st, L.a2, pp(FC1_W), L.u, M, mlp, D, pp(FC1_B), nullptr, L.h));
+        RET_IF(ck_linear(st, L.h, pp(FC2_W), L.xout, M, D, mlp, pp(FC2_B), L.xmid));
+        xin = L.xout;
+    }
+    *x_final = xin;
+    return 0;
+}
+// on entry w.g = dL/dx_final and grads[fc2_b of the last layer] already holds colsum(g); on exit w.g = dL/dx_in
+static int ck_encoder_bwd(const svit_engine* e, const float* P, CkWs& w, const float* x_in, float* G, cudaStream_t st,
+                          svit_progress_fn progress = nullptr, void* user = nullptr) {
+    const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
+    for (int l = e->depth - 1; l >= 0; --l) {
+        CkLayer& L = w.L[l];
+        const float* xin = (l == 0) ? x_in : w.L[l - 1].xout;
+        auto pp = [&](int which) { return P + e->poff[pidx_layer(l, which)]; };
+        auto gp = [&](int which) { return G + e->poff[pidx_layer(l, which)]; };
+        RET_IF(ck_dgrad(st, w.g, pp(FC2_W), w.du, M, D, mlp));           // dh = g W2
+        RET_IF(ck::mul_dgelu(w.du, L.u, static_cast<size_t>(M) * mlp, st));  // du = dh * gelu'(u)
+        RET_IF(ck_wgrad(st, w.g, L.h, gp(FC2_W), M, D, mlp));
+        RET_IF(ck::colsum(w.du, gp(FC1_B), M, mlp, st));
+        RET_IF(ck_dgrad(st, w.du, pp(FC1_W), w.da, M, mlp, D));
+        RET_IF(ck_wgrad(st, w.du, L.a2, gp(FC1_W), M, mlp, D));
+        RET_IF(ck::ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, gp(LN2_W), gp(LN2_B), M, D, st));
+        RET_IF(ck::colsum(w.g, gp(OUT_B), M, D, st));
+        RET_IF(ck_dgrad(st, w.g, pp(OUT_W), w.dO, M, D, I));
+        RET_IF(ck_wgrad(st, w.g, L.O, gp(OUT_W), M, D, I));
+        RET_IF(ck::attn_bwd(L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, 0.125f, st));
+        RET_IF(ck_dgrad(st, w.dqkv, pp(QKV_W), w.da, M, 3 * I, D));
+        RET_IF(ck_wgrad(st, w.dqkv, L.a1, gp(QKV_W), M, 3 * I, D));
+        RET_IF(ck::ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, gp(LN1_W), gp(LN1_B), M, D, st));
+        if (l > 0) RET_IF(ck::colsum(w.g, G + e->poff[pidx_layer(l - 1, FC2_B)], M, D, st));
+        if (progress != nullptr) progress(l, user);
+    }
+    return 0;
+}
+static int ck_forward(svit_engine* e, const float* P, void* ws_ptr, size_t ws_bytes, const PackDesc& pd, int B, float* out,
+                      cudaStream_t st) {
+    CkWs w;
+    RET_IF(ck_check_ws(e, B, 0, ws_ptr, ws_bytes, &w));
+    RET_IF(ck::patches(pd, w.Ap, st));
+    RET_IF(ck_linear(st, w.Ap, P + e->poff[P_PE_W], w.x0, w.M, e->D, e->K));
+    RET_IF(ck::embed_finish(w.x0, P + e->poff[P_POS], P + e->poff[P_CLS], P + e->poff[P_PE_B], B, e->T, e->D, st));
+    const float* xf = nullptr;
+    RET_IF(ck_encoder_fwd(e, P, w, w.x0, st, &xf));
+    return launch_head_fwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)],
+                           P + e->poff[pidx_head(e, 3)], out, B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st);
+}
+static int ck_backward(svit_engine* e, const float* P, void* ws_ptr, int B, const float* dout, float* G,
+                       svit_progress_fn progress, void* user, cudaStream_t st) {
+    CkWs w;
+    RET_IF(ck_check_ws(e, B, 0, ws_ptr, 0, &w));
+    const float* xf = w.L[e->depth - 1].xout;
+    RET_IF(launch_head_bwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)], dout,
+                           w.g, w.g16, G + e->poff[pidx_head(e, 0)], G + e->poff[pidx_head(e, 1)],
+                           G + e->poff[pidx_head(e, 2)], G + e->poff[pidx_head(e, 3)],
+                           G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st));
+    if (progress != nullptr) progress(e->depth, user);
+    RET_IF(ck_encoder_bwd(e, P, w, w.x0, G, st, progress, user));
+    RET_IF(launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], B, e->T, e->D, st));
+    RET_IF(ck_wgrad(st, w.g, w.Ap, G + e->poff[P_PE_W], w.M, e->D, e->K));
+    if (progress != nullptr) progress(-1, user);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
@@ -326,6 +488,8 @@ svit_engine* svit_create(const svit_config* cfg) {
     e->Kp = static_cast<int>(align_up(e->K, 64));
     e->Kd = static_cast<int>(align_up(e->K, 8));
     e->num_sms = 148;
+    e->check = 0;
+    e->wdec_f32 = nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int sms = 0;
@@ -389,8 +553,20 @@ long long svit_param_numel(const svit_engine* e, int i) { return (i >= 0 && i < 
 long long svit_flat_numel(const svit_engine* e) { return e->flat_numel; }
 size_t svit_shadow_bytes(const svit_engine* e) { return e->sh_total; }
 size_t svit_mpp_shadow_bytes(const svit_engine* e) { return e->msh_total; }
+int svit_set_check_mode(svit_engine* e, int on) {
+    if (e == nullptr) return -1;
+    e->check = on ? 1 : 0;
+    return 0;
+}
+int svit_get_check_mode(const svit_engine* e) { return e != nullptr ? e->check : 0; }
+
 size_t svit_workspace_bytes(const svit_engine* e, int batch, int training, int mpp) {
     if (batch <= 0) return 0;
+    if (e->check) {
+        CkWs cw;
+        ck_carve(e, batch, mpp, nullptr, &cw);
+        return cw.total;
+    }
     Ws w;
     carve(e, batch, training, mpp, 1, nullptr, &w);
     return w.total;
@@ -418,6 +594,7 @@ int svit_prepare_weights(svit_engine* e, const float* P, void* shadow, void* str
 int svit_mpp_prepare_weights(svit_engine* e, const float* Wdec, void* mpp_shadow, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* sh = reinterpret_cast<uint8_t*>(mpp_shadow);
+    e->wdec_f32 = Wdec;  // the fp32 check mode reads the master weight itself
     // Wdec (K, D): direct [K, D] pitch D; transposed [D, K] pitch Kd
     return launch_cast_transpose(Wdec, sh + e->msh_wdec, sh + e->msh_wdecT, e->K, e->D, e->D, e->Kd, 1, 0, 0, 0, st);
 }
@@ -426,6 +603,10 @@ int svit_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, s
                  const int32_t* table, int n_mesh, const float* ch_mean, const float* ch_std, float* out, int training,
                  void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (e->check) {
+        PackDesc cpd{input, nullptr, B, e->C, e->N, e->V, e->K, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
+        return ck_forward(e, P, ws_ptr, ws_bytes, cpd, B, out, st);
+    }
     Ws w;
     RET_IF(check_ws(e, B, training, 0, 1, ws_ptr, ws_bytes, &w));
     PackDesc pd{input, w.Apatch, B, e->C, e->N, e->V, e->Kp, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
@@ -439,6 +620,7 @@ int svit_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, s
 int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, int B, const float* dout, float* G,
                   svit_progress_fn progress, void* user, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (e->check) return ck_backward(e, P, ws_ptr, B, dout, G, progress, user, st);
     Ws w;
     RET_IF(check_ws(e, B, 1, 0, 1, ws_ptr, 0, &w));
     const float* xf = w.L[e->depth - 1].xout;
@@ -456,6 +638,17 @@ int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, 
 int svit_encoder_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, size_t ws_bytes, const float* x, int B,
                          float* y, int training, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (e->check) {
+        CkWs cw;
+        RET_IF(ck_check_ws(e, B, 0, ws_ptr, ws_bytes, &cw));
+        const float* cxf = nullptr;
+        RET_IF(ck_encoder_fwd(e, P, cw, x, st, &cxf));
+        if (cudaMemcpyAsync(y, cxf, static_cast<size_t>(cw.M) * e->D * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            set_error("encoder_forward (check mode): copy failed");
+            return -12;
+        }
+        return 0;
+    }
     Ws w;
     RET_IF(check_ws(e, B, training, 0, 1, ws_ptr, ws_bytes, &w));
     const float* xf = nullptr;
@@ -471,6 +664,16 @@ int svit_encoder_forward(svit_engine* e, const float* P, const void* sh, void* w
 int svit_encoder_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, int B, const float* x,
                             const float* dy, float* dx, float* G, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (e->check) {
+        CkWs cw;
+        RET_IF(ck_check_ws(e, B, 0, ws_ptr, 0, &cw));
+        const size_t cn = static_cast<size_t>(cw.M) * e->D;
+        cudaMemcpyAsync(cw.g, dy, cn * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        RET_IF(ck::colsum(cw.g, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], cw.M, e->D, st));
+        RET_IF(ck_encoder_bwd(e, P, cw, x, G, st));
+        if (dx != nullptr) cudaMemcpyAsync(dx, cw.g, cn * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        return 0;
+    }
     Ws w;
     RET_IF(check_ws(e, B, 1, 0, 1, ws_ptr, 0, &w));
     const size_t n = static_cast<size_t>(w.M) * e->D;
@@ -487,6 +690,22 @@ int svit_mpp_forward(svit_engine* e, const float* P, const void* sh, const void*
                      const uint8_t* swap_sel, const int64_t* swap_src, const uint8_t* replace_sel, float* loss_sum,
                      float* batch_out, int training, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (e->check) {
+        if (e->wdec_f32 == nullptr) {
+            set_error("svit_mpp_forward (check mode): call svit_mpp_prepare_weights first");
+            return -20;
+        }
+        CkWs cw;
+        RET_IF(ck_check_ws(e, B, 1, ws_ptr, ws_bytes, &cw));
+        PackDesc cpd{input, nullptr, B, e->C, e->N, e->V, e->K, swap_sel, swap_src, replace_sel, mask_token, nullptr, 0, nullptr, nullptr};
+        RET_IF(ck::patches(cpd, cw.Ap, st));
+        RET_IF(ck_linear(st, cw.Ap, P + e->poff[P_PE_W], cw.x0, cw.M, e->D, e->K));
+        RET_IF(ck::embed_finish(cw.x0, P + e->poff[P_POS], P + e->poff[P_CLS], P + e->poff[P_PE_B], B, e->T, e->D, st));
+        const float* cxf = nullptr;
+        RET_IF(ck_encoder_fwd(e, P, cw, cw.x0, st, &cxf));
+        RET_IF(ck_linear(st, cxf, e->wdec_f32, batch_out, cw.M, e->K, e->D, bdec));
+        return launch_mpp_loss_fwd(batch_out, e->K, input, mask, loss_sum, B, e->C, e->N, e->V, st);
+    }
     Ws w;
     RET_IF(check_ws(e, B, training, 1, 1, ws_ptr, ws_bytes, &w));
     PackDesc pd{input, w.Apatch, B, e->C, e->N, e->V, e->Kp, swap_sel, swap_src, replace_sel, mask_token, nullptr, 0, nullptr, nullptr};
@@ -503,6 +722,27 @@ int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void
                         const float* input, const float* batch_out, const uint8_t* mask, const uint8_t* replace_sel,
                         const float* coef, float* G, float* MG, svit_progress_fn progress, void* user, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (e->check) {
+        CkWs cw;
+        RET_IF(ck_check_ws(e, B, 1, ws_ptr, 0, &cw));
+        const int cM = cw.M, cD = e->D, cK = e->K;
+        float* cgW = MG;
+        float* cgb = MG + static_cast<size_t>(cK) * cD;
+        float* cgmt = cgb + cK;
+        const float* cxf = cw.L[e->depth - 1].xout;
+        RET_IF(ck::mpp_loss_bwd(batch_out, input, mask, coef, cw.dy, B, e->C, e->N, e->V, st));
+        RET_IF(ck_wgrad(st, cw.dy, cxf, cgW, cM, cK, cD));
+        RET_IF(ck::colsum(cw.dy, cgb, cM, cK, st));
+        RET_IF(ck_dgrad(st, cw.dy, e->wdec_f32, cw.g, cM, cK, cD));
+        RET_IF(ck::colsum(cw.g, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], cM, cD, st));
+        RET_IF(ck_encoder_bwd(e, P, cw, cw.x0, G, st, progress, user));
+        RET_IF(launch_embed_bwd(cw.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], B, e->T, cD, st));
+        RET_IF(ck_wgrad(st, cw.g, cw.Ap, G + e->poff[P_PE_W], cM, cD, cK));
+        if (progress != nullptr) progress(-1, user);
+        if (replace_sel != nullptr)
+            RET_IF(launch_mask_token_grad(cw.g, replace_sel, P + e->poff[P_PE_W], cw.rvec, cgmt, B, e->T, cD, cK, st));
+        return 0;
+    }
     Ws w;
     RET_IF(check_ws(e, B, 1, 1, 1, ws_ptr, 0, &w));
     const int M = w.M, D = e->D, K = e->K, Kd = e->Kd;

@@ -367,7 +367,6 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         float* wbias = sBias + ew * 64;
         const int sw = lane & 7;       // swizzle key of this thread's row inside a 32-row box
         constexpr int CPH = 32 * (int)sizeof(OutT) / 16;  // 16-byte chunks per 32-column half of a unit (4 bf16, 8 fp32)
-        constexpr int EPC = 16 / (int)sizeof(OutT);       // elements per chunk
         int it = 0, k = 0;             // k = jobs done by this warp
         for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
             const int m0 = (tile / tiles_n) * TM + row_off + q * 32;  // first row of this warp's slice

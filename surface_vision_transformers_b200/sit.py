@@ -232,6 +232,16 @@ class SiT(nn.Module):
     def _weights_version(self):
         return (self._flat.data_ptr(), self._flat._version, sum(p._version for p in self._plist))
 
+    def set_check_mode(self, on=True):
+        """fp32 check mode (include/svit_b200.h): the same forward / backward with every operand in fp32 on the CUDA
+        cores instead of bf16 on the tensor cores -- for verification at a 1e-4 tolerance, not for speed."""
+        check(_lib.load().svit_set_check_mode(self._engine, 1 if on else 0), "svit_set_check_mode")
+        return self
+
+    @property
+    def check_mode(self):
+        return bool(_lib.load().svit_get_check_mode(self._engine))
+
     def mark_weights_dirty(self):
         """Called by optimizers that update the flat buffer through the C ABI (no autograd version bump)."""
         self._shadow_key = None
