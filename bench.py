@@ -326,7 +326,7 @@ def main():
         bias = torch.zeros(H4, device=dev)
         o1 = torch.empty(M, H4, device=dev, dtype=torch.bfloat16)
         o2 = torch.empty(M, H4, device=dev, dtype=torch.bfloat16)
-        mode = 4 if kind == "infer" else 1
+        mode = 4 if kind == "infer" else 5   # training stores gelu'(u) and gelu(u) (EPI_GELU_GRAD), inference gelu(u) only
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         st = _lib.vp(torch.cuda.current_stream().cuda_stream)
 
@@ -356,11 +356,11 @@ def main():
                 traffic = prof["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
-        roof = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,EPI_GELU,192> (fc1 + bias + exact GELU, M=%d N=%d K=%d)" % (M, H4, D),
+        roof = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,%s,192,cta_group::2> (fc1 + bias + exact GELU%s, M=%d N=%d K=%d)" % ("EPI_GELU_ONLY" if mode == 4 else "EPI_GELU_GRAD", "" if mode == 4 else " and its derivative", M, H4, D),
                     achieved=ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=ach / peaks["tflops_burst"],
                     traffic=traffic, traffic_source="profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + "
                     "dram__bytes_write.sum, one ncu --set full launch)" if traffic else None,
-                    algorithmic_bytes=2.0 * M * D + 2.0 * H4 * D + (2 if mode == 1 else 1) * 2.0 * M * H4,
+                    algorithmic_bytes=2.0 * M * D + 2.0 * H4 * D + (2 if mode == 5 else 1) * 2.0 * M * H4,
                     peak_source=peaks["source"] + " (burst: kernel timed alone)",
                     us_per_launch=k_ms * 1e3, flops_per_launch=flops,
                     step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
