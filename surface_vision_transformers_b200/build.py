@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
     "--use_fast_math" if False else "-DSVIT_NO_FAST_MATH",
-]
+] + (["-DSVIT_SPIN_SLEEP_NS=" + os.environ["SVIT_SPIN_SLEEP_NS"]] if os.environ.get("SVIT_SPIN_SLEEP_NS") else [])
 
 
 def sources():

@@ -81,6 +81,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef SVIT_SPIN_SLEEP_NS
+        __nanosleep(SVIT_SPIN_SLEEP_NS);
+#endif
         if ((++spins & 63) == 0 && clock64() - t0 > SVIT_SPIN_LIMIT) {
             printf("svit: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, smem_u32(bar), parity);
