@@ -26,9 +26,41 @@ __device__ __forceinline__ float warp_sum(float v) {
 // =================================================================================================
 // a1: patch gather (bit-exact)
 // =================================================================================================
+// One block per (sample, channel) plane: the whole ico-6 plane (40,962 floats = 160 KB) is staged in shared memory
+// with coalesced loads; then, JT patches at a time, the table entries are read coalesced along the patch index, the
+// vertices are gathered from the staged plane into a [JT][V] tile, and the tile -- one contiguous run of the output --
+// is written out fully coalesced.
+constexpr int GATHER_THREADS = 1024;
+constexpr int GATHER_TILE_FLOATS = 12 * 1024;  // 48 KB next to the 160 KB plane
+__global__ void __launch_bounds__(GATHER_THREADS) gather_patches_smem_kernel(const float* __restrict__ mesh,
+                                                                             const int32_t* __restrict__ table,
+                                                                             float* __restrict__ out, int n_mesh, int N, int V,
+                                                                             int JT) {
+    extern __shared__ float gather_smem[];
+    float* plane_s = gather_smem;                       // [n_mesh]
+    float* tile = gather_smem + ((n_mesh + 31) & ~31);  // [JT][V]
+    const int sc = blockIdx.x;
+    const float* plane = mesh + static_cast<size_t>(sc) * n_mesh;
+    for (int i = threadIdx.x; i < n_mesh; i += GATHER_THREADS) plane_s[i] = __ldcs(plane + i);
+    __syncthreads();
+    float* dst = out + static_cast<size_t>(sc) * N * V;
+    for (int j0 = 0; j0 < N; j0 += JT) {
+        const int nj = min(JT, N - j0);
+        // lane -> patch, warp -> vertex slot: table reads coalesced along the patch index, no integer division
+        const int jj = threadIdx.x & 31;
+        if (jj < nj) {
+            for (int v = threadIdx.x >> 5; v < V; v += GATHER_THREADS / 32)
+                tile[jj * V + v] = plane_s[__ldg(table + static_cast<size_t>(v) * N + j0 + jj)];
+        }
+        __syncthreads();
+        float* d0 = dst + static_cast<size_t>(j0) * V;
+        for (int e = threadIdx.x; e < nj * V; e += GATHER_THREADS) d0[e] = tile[e];
+        __syncthreads();
+    }
+}
+// fallback for meshes that do not fit in shared memory: one block per (patch, plane)
 __global__ void gather_patches_kernel(const float* __restrict__ mesh, const int32_t* __restrict__ table,
                                       float* __restrict__ out, int SC, int n_mesh, int N, int V) {
-    // grid: (N, SC); each block copies one patch of one (sample, channel) plane
     const int j = blockIdx.x;
     const int sc = blockIdx.y;
     const float* plane = mesh + static_cast<size_t>(sc) * n_mesh;
@@ -39,6 +71,19 @@ __global__ void gather_patches_kernel(const float* __restrict__ mesh, const int3
 int launch_gather_patches(const float* mesh, const int32_t* table, float* out, int S, int C, int n_mesh, int N, int V,
                           cudaStream_t st) {
     if (S <= 0) return 0;
+    int JT = GATHER_TILE_FLOATS / (V > 0 ? V : 1);
+    if (JT > 32) JT = 32;
+    const size_t smem = (static_cast<size_t>((n_mesh + 31) & ~31) + static_cast<size_t>(JT > 0 ? JT : 1) * V) * sizeof(float);
+    if (JT >= 1 && smem <= 227 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(gather_patches_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            configured = true;
+        }
+        gather_patches_smem_kernel<<<S * C, GATHER_THREADS, smem, st>>>(mesh, table, out, n_mesh, N, V, JT);
+        SVIT_CHECK_LAUNCH("gather_patches");
+        return 0;
+    }
     dim3 grid(N, S * C);
     gather_patches_kernel<<<grid, 128, 0, st>>>(mesh, table, out, S * C, n_mesh, N, V);
     SVIT_CHECK_LAUNCH("gather_patches");

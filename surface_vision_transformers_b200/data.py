@@ -1,0 +1,74 @@
+"""Data formats on either side of the hot path.
+
+* ``preprocess_meshes`` -- the on-device equivalent of tools/preprocessing.py:62-84: per-channel z-score of the raw
+  ico-6 hemisphere meshes, patch gather with the reference's index table, left hemispheres first then right.  The
+  z-score runs in float64 like the reference's numpy code and is cast to float32 before the (bit-exact) gather, so
+  the result equals ``np.load('{split}_data.npy').astype(np.float32)`` of the reference bit for bit.
+* ``PatchedNpyDataset`` -- reader of the reference's ``{split}_data.npy`` (float64, (2S, C, N, V)) /
+  ``{split}_labels.npy`` files (tools/train.py:97-113): casts to float32 once (``torch.from_numpy(..).float()``,
+  train.py:107), keeps the arrays in PINNED host memory and hands out mini-batches as pinned tuples for
+  ``DevicePrefetcher`` -- no DataLoader workers, no per-iteration pageable copies.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .gather import gather_patches, preprocessing_layout
+
+__all__ = ["preprocess_meshes", "PatchedNpyDataset"]
+
+
+def preprocess_meshes(hemis, means, stds, table):
+    """hemis: (2S, C, 40962) CUDA tensor ordered L0, R0, L1, R1, ... (preprocessing.py:62-67), any float dtype;
+    means / stds: (C,) ; table: (V, N) int32 -> (2S, C, N, V) float32, rows [0, S) left, [S, 2S) right."""
+    if not hemis.is_cuda:
+        raise RuntimeError("preprocess_meshes needs CUDA tensors (no CPU fallback)")
+    C = hemis.shape[1]
+    m = torch.as_tensor(means, dtype=torch.float64, device=hemis.device).reshape(1, C, 1)
+    s = torch.as_tensor(stds, dtype=torch.float64, device=hemis.device).reshape(1, C, 1)
+    normalised = ((hemis.double() - m) / s).float()          # preprocessing.py:72 in float64, train.py:107 cast
+    return preprocessing_layout(gather_patches(normalised, table))
+
+
+class PatchedNpyDataset:
+    """``{split}_data.npy`` + ``{split}_labels.npy`` of the reference, pinned in host memory as float32."""
+
+    def __init__(self, data_path, split, pin=True):
+        data = np.load(os.path.join(data_path, f"{split}_data.npy"))
+        labels = np.load(os.path.join(data_path, f"{split}_labels.npy"))
+        if data.ndim != 4 or labels.shape[0] != data.shape[0]:
+            raise ValueError(f"unexpected shapes {data.shape} / {labels.shape} (want (2S, C, N, V) and (2S,))")
+        self.data = torch.from_numpy(data).float()
+        self.labels = torch.from_numpy(labels).float()
+        if pin and torch.cuda.is_available():
+            self.data = self.data.pin_memory()
+            self.labels = self.labels.pin_memory()
+        self._stage = None
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def batches(self, batch_size, shuffle=False, generator=None, drop_last=False, rank=0, world=1):
+        """Yields (x, y) host batches.  With shuffle, a permutation drawn from ``generator`` (same on every rank) is
+        split into per-rank strided slices, so the ranks of a data-parallel job see disjoint samples."""
+        n = len(self)
+        order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+        order = order[rank::world]
+        pinned = self.data.is_pinned()
+        for i in range(0, order.numel(), batch_size):
+            idx = order[i:i + batch_size]
+            if drop_last and idx.numel() < batch_size:
+                return
+            if not shuffle and world == 1:
+                yield self.data[i:i + idx.numel()], self.labels[i:i + idx.numel()]   # contiguous views stay pinned
+                continue
+            x = torch.empty((idx.numel(),) + self.data.shape[1:], dtype=torch.float32, pin_memory=pinned)
+            y = torch.empty((idx.numel(),), dtype=torch.float32, pin_memory=pinned)
+            torch.index_select(self.data, 0, idx, out=x)
+            torch.index_select(self.labels, 0, idx, out=y)
+            yield x, y

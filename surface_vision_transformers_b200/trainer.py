@@ -1,0 +1,125 @@
+"""Training loop for the scan-age / birth-age regression with the semantics of tools/train.py:271-363 (SURVEY 8(f)
+rank 2), arranged so that the device never waits for the host:
+
+* batches come from ``PatchedNpyDataset.batches`` through ``DevicePrefetcher`` (copy of batch i+1 under step i);
+* the per-iteration ``loss.item()`` / ``.cpu()`` calls of the reference (train.py:293-296) are replaced by device-side
+  accumulators -- sum of losses, sum of |target - prediction| -- that are read ONCE per epoch;
+* under ``torchrun`` the model is wrapped in ``DataParallel`` (flat-gradient all-reduce overlapped with backward), every
+  rank iterates a disjoint slice of the same permutation, and the epoch statistics are all-reduced.
+
+What is kept from the reference: MSE (or L1) criterion on ``outputs.squeeze()``, train MAE per epoch, validation every
+``val_epoch`` epochs in ``eval()`` + ``no_grad``, best-validation-MAE bookkeeping with an optional ``checkpoint.pth``
+holding ``model.state_dict()`` (train.py:355-363), the same scalar names for an optional TensorBoard-like writer.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from .ddp import DataParallel
+from .loader import DevicePrefetcher
+
+__all__ = ["fit", "evaluate"]
+
+
+def _dist_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _all_reduce_(t):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+def evaluate(model, dataset, batch_size, device, l1loss=False):
+    """Validation pass of tools/train.py:311-337: returns (sum of batch losses, MAE, predictions, targets) with the
+    statistics of all ranks combined; predictions / targets are those of this rank (host tensors)."""
+    rank, world = _dist_info()
+    criterion = torch.nn.L1Loss() if l1loss else torch.nn.MSELoss(reduction="mean")
+    net = model.module if isinstance(model, DataParallel) else model
+    was_training = net.training
+    net.eval()
+    stats = torch.zeros(3, dtype=torch.float64, device=device)   # sum of batch losses, sum |err|, count
+    preds, targets = [], []
+    with torch.no_grad():
+        for x, y in DevicePrefetcher(dataset.batches(batch_size, rank=rank, world=world), device):
+            out = net(x)
+            stats[0] += criterion(out.squeeze(-1) if out.dim() > 1 else out, y).double()
+            stats[1] += (out.reshape(-1) - y).abs().sum().double()
+            stats[2] += y.numel()
+            preds.append(out.reshape(-1).clone())
+            targets.append(y.clone())
+    _all_reduce_(stats)
+    s = stats.cpu()
+    net.train(was_training)
+    return float(s[0]), float(s[1] / s[2].clamp(min=1)), torch.cat(preds).cpu(), torch.cat(targets).cpu()
+
+
+def fit(model, optimizer, train_set, val_set=None, *, epochs, batch_size, val_batch_size=None, val_epoch=1, device=None,
+        l1loss=False, save_dir=None, save_ckpt=False, writer=None, seed=0, scheduler=None, log=None):
+    """Returns a dict with the per-epoch history and the best validation MAE / epoch.
+
+    ``model``: a ``SiT`` (wrapped in ``DataParallel`` here when torch.distributed is initialised with > 1 rank).
+    ``train_set`` / ``val_set``: ``PatchedNpyDataset``-like objects (``batches(batch_size, shuffle, generator, rank,
+    world)``).  ``writer``: optional object with ``add_scalar(tag, value, step)`` (TensorBoard SummaryWriter)."""
+    rank, world = _dist_info()
+    device = torch.device(device) if device is not None else next(model.parameters()).device
+    if device.type != "cuda":
+        raise RuntimeError("fit() drives the CUDA hot path (no CPU fallback)")
+    net = model
+    if world > 1 and not isinstance(model, DataParallel):
+        net = DataParallel(model)
+    core = net.module if isinstance(net, DataParallel) else net
+    criterion = torch.nn.L1Loss() if l1loss else torch.nn.MSELoss(reduction="mean")
+    gen = torch.Generator()
+    history = dict(train_loss=[], train_mae=[], val_loss=[], val_mae=[], lr=[])
+    best_mae, best_epoch = float("inf"), None
+    for epoch in range(epochs):
+        core.train()
+        gen.manual_seed(seed + epoch)                       # the same permutation on every rank
+        stats = torch.zeros(4, dtype=torch.float64, device=device)   # sum loss, batches, sum |err|, samples
+        batches = train_set.batches(batch_size, shuffle=True, generator=gen, rank=rank, world=world)
+        for x, y in DevicePrefetcher(batches, device):
+            optimizer.zero_grad(set_to_none=True)
+            out = net(x)
+            loss = criterion(out.squeeze(-1) if out.dim() > 1 else out, y)
+            loss.backward()
+            optimizer.step()
+            with torch.no_grad():                           # device-side bookkeeping: no host sync inside the epoch
+                stats[0] += loss.detach().double()
+                stats[1] += 1
+                stats[2] += (out.detach().reshape(-1) - y).abs().sum().double()
+                stats[3] += y.numel()
+        if scheduler is not None:
+            scheduler.step()
+        _all_reduce_(stats)
+        s = stats.cpu()                                     # the one host read per epoch
+        train_loss, train_mae = float(s[0] / s[1].clamp(min=1)), float(s[2] / s[3].clamp(min=1))
+        history["train_loss"].append(train_loss)
+        history["train_mae"].append(train_mae)
+        history["lr"].append(optimizer.param_groups[0]["lr"])
+        if writer is not None and rank == 0:
+            writer.add_scalar("loss/train", train_loss, epoch + 1)
+            writer.add_scalar("mae/train", train_mae, epoch + 1)
+        if log is not None and rank == 0:
+            log(f"| Epoch - {epoch + 1} | Loss - {train_loss:.4f} | MAE - {train_mae:.4f} | LR - {history['lr'][-1]}")
+        if val_set is not None and (epoch + 1) % val_epoch == 0:
+            val_loss, val_mae, preds, targets = evaluate(net, val_set, val_batch_size or batch_size, device, l1loss)
+            history["val_loss"].append((epoch + 1, val_loss))
+            history["val_mae"].append((epoch + 1, val_mae))
+            if writer is not None and rank == 0:
+                writer.add_scalar("loss/val", val_loss, epoch + 1)
+                writer.add_scalar("mae/val", val_mae, epoch + 1)
+            if log is not None and rank == 0:
+                log(f"| Validation | Epoch - {epoch + 1} | Loss - {val_loss:.4f} | MAE - {val_mae:.4f} |")
+            if val_mae < best_mae:
+                best_mae, best_epoch = val_mae, epoch + 1
+                if save_dir is not None and rank == 0:
+                    os.makedirs(save_dir, exist_ok=True)
+                    torch.save(dict(preds=preds, targets=targets), os.path.join(save_dir, "preds_test.pt"))
+                    if save_ckpt:
+                        torch.save(core.state_dict(), os.path.join(save_dir, "checkpoint.pth"))   # train.py:361-363
+    return dict(history=history, best_mae=best_mae, best_epoch=best_epoch)

@@ -320,3 +320,79 @@ def test_fp32_check_mode_mpp_matches_oracle_to_1e4():
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
         else:
             assert rel_l2(p.grad, ref[n].grad) < CHECK_TOL, n
+
+
+# ------------------------------------------------------------------------------------------- SURVEY 8(f) rows
+@pytest.mark.parametrize("sub_ico", [1, 2])
+def test_preprocess_meshes_bit_exact_vs_reference_loop(sub_ico):
+    """8(f)-1: on-device z-score + gather + L/R re-ordering == the numpy restatement of tools/preprocessing.py:72-84
+    (float64 z-score like the reference, cast to float32 like tools/train.py:107), bit for bit."""
+    import numpy as np
+    from oracle import gather_oracle
+    rs = np.random.RandomState(7 + sub_ico)
+    hemis = (rs.standard_normal((6, 4, 40962)) * 2 + 1).astype(np.float32).astype(np.float64)   # L0,R0,L1,R1,L2,R2
+    means = np.array([1.15, 0.037, 1.0, 0.07]).reshape(1, 4, 1)
+    stds = np.array([0.41, 0.19, 0.39, 4.05]).reshape(1, 4, 1)
+    table = svit.load_index_table(sub_ico)
+    ref = gather_oracle.preprocessing_layout(gather_oracle.zscore(hemis, means, stds), table.numpy()).astype(np.float32)
+    got = svit.preprocess_meshes(torch.from_numpy(hemis).to(DEV), means.reshape(-1), stds.reshape(-1), table.to(DEV))
+    assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
+    assert torch.equal(got.cpu(), torch.from_numpy(ref))
+
+
+def test_fit_tracks_reference_style_loop(tmp_path):
+    """8(f)-2: fit() (prefetched batches, device-side epoch statistics, best-MAE checkpoint) against a plain
+    tools/train.py-style loop on the fp32 oracle with the same data order: same per-epoch loss / MAE within the bf16
+    tolerance, validation bookkeeping and the checkpoint file as in train.py:339-363."""
+    import numpy as np
+    cfg = dict(dim=128, depth=2, heads=2, mlp_dim=256, num_patches=12, num_vertices=10)
+    rng = np.random.default_rng(0)
+    for split, n in (("train", 24), ("validation", 10)):
+        np.save(tmp_path / f"{split}_data.npy", rng.standard_normal((n, 4, 12, 10)))
+        np.save(tmp_path / f"{split}_labels.npy", rng.uniform(26, 45, size=n))
+    train = svit.PatchedNpyDataset(str(tmp_path), "train")
+    val = svit.PatchedNpyDataset(str(tmp_path), "validation")
+    torch.manual_seed(0)
+    oracle = OracleSiT(**cfg).to(DEV)
+    model = svit.SiT(**cfg)
+    model.load_state_dict(oracle.state_dict())
+    model.to(DEV)
+    lines = []
+    res = svit.fit(model, svit.FusedAdamW(model.parameters(), lr=3e-4, weight_decay=0.0), train, val, epochs=3, batch_size=8,
+                   val_epoch=1, device=DEV, save_dir=str(tmp_path / "out"), save_ckpt=True, seed=11, log=lines.append)
+    # reference-style loop on the oracle with the same permutations
+    opt = torch.optim.AdamW(oracle.parameters(), lr=3e-4, weight_decay=0.0)
+    gen = torch.Generator()
+    ref_loss, ref_mae, ref_vmae = [], [], []
+    for epoch in range(3):
+        gen.manual_seed(11 + epoch)
+        oracle.train()
+        run, preds, targs = 0.0, [], []
+        batches = list(train.batches(8, shuffle=True, generator=gen))
+        for x, y in batches:
+            x, y = x.to(DEV), y.to(DEV)
+            opt.zero_grad()
+            out = oracle(x)
+            loss = torch.nn.functional.mse_loss(out.squeeze(), y)
+            loss.backward()
+            opt.step()
+            run += loss.item()
+            preds.append(out.reshape(-1).detach().cpu()); targs.append(y.cpu())
+        ref_loss.append(run / len(batches))
+        ref_mae.append((torch.cat(targs) - torch.cat(preds)).abs().mean().item())
+        oracle.eval()
+        with torch.no_grad():
+            vp_ = torch.cat([oracle(x.to(DEV)).reshape(-1).cpu() for x, _ in val.batches(8)])
+        ref_vmae.append((val.labels - vp_).abs().mean().item())
+    h = res["history"]
+    for e in range(3):
+        assert abs(h["train_loss"][e] - ref_loss[e]) / ref_loss[e] < 3 * TOL, (e, h["train_loss"][e], ref_loss[e])
+        assert abs(h["train_mae"][e] - ref_mae[e]) / ref_mae[e] < 3 * TOL
+        assert h["val_mae"][e][0] == e + 1 and abs(h["val_mae"][e][1] - ref_vmae[e]) / ref_vmae[e] < 3 * TOL
+    assert res["best_epoch"] == int(np.argmin(ref_vmae)) + 1
+    assert abs(res["best_mae"] - min(ref_vmae)) / min(ref_vmae) < 3 * TOL
+    assert len(lines) == 6 and lines[1].startswith("| Validation | Epoch - 1 |")
+    ckpt = torch.load(tmp_path / "out" / "checkpoint.pth")
+    assert set(ckpt) == set(oracle.state_dict())
+    saved = torch.load(tmp_path / "out" / "preds_test.pt")
+    assert saved["preds"].shape == (10,) and torch.equal(saved["targets"], val.labels)

@@ -225,3 +225,104 @@ def test_flat_grad_reducer_two_gloo_ranks(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+# ------------------------------------------------------------------------------------------- formats
+def test_patched_npy_dataset_reads_reference_format(tmp_path):
+    """{split}_data.npy is float64 (2S, C, N, V) (tools/preprocessing.py:99); the reader casts to float32 exactly like
+    train.py:107 and hands out batches in file order (no shuffle) or as a rank-disjoint permutation (shuffle)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((10, 4, 20, 15))              # float64
+    labels = rng.uniform(26, 45, size=10)
+    np.save(tmp_path / "train_data.npy", data)
+    np.save(tmp_path / "train_labels.npy", labels)
+    ds = svit.PatchedNpyDataset(str(tmp_path), "train", pin=False)
+    assert len(ds) == 10 and ds.shape == (10, 4, 20, 15) and ds.data.dtype == torch.float32
+    assert torch.equal(ds.data, torch.from_numpy(data).float()) and torch.equal(ds.labels, torch.from_numpy(labels).float())
+    got = list(ds.batches(4))
+    assert [b[0].shape[0] for b in got] == [4, 4, 2]
+    assert torch.equal(torch.cat([b[0] for b in got]), ds.data) and torch.equal(torch.cat([b[1] for b in got]), ds.labels)
+    assert [b[0].shape[0] for b in ds.batches(4, drop_last=True)] == [4, 4]
+    g = torch.Generator().manual_seed(5)
+    r0 = list(ds.batches(3, shuffle=True, generator=g, rank=0, world=2))
+    g = torch.Generator().manual_seed(5)
+    r1 = list(ds.batches(3, shuffle=True, generator=g, rank=1, world=2))
+    seen = torch.cat([b[1] for b in r0] + [b[1] for b in r1])
+    assert sorted(seen.tolist()) == sorted(ds.labels.tolist())          # disjoint cover of the epoch
+    perm = torch.randperm(10, generator=torch.Generator().manual_seed(5))
+    assert torch.equal(torch.cat([b[0] for b in r0]), ds.data[perm[0::2]])
+
+
+def _timm_like_state_dict(dim, depth, mlp, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    sd = {"norm.weight": torch.randn(dim, generator=g), "norm.bias": torch.randn(dim, generator=g),
+          "cls_token": torch.randn(1, 1, dim, generator=g), "pos_embed": torch.randn(1, 197, dim, generator=g)}
+    for i in range(depth):
+        for k, shape in [("norm1.weight", (dim,)), ("norm1.bias", (dim,)), ("norm2.weight", (dim,)), ("norm2.bias", (dim,)),
+                         ("attn.qkv.weight", (3 * dim, dim)), ("attn.qkv.bias", (3 * dim,)),
+                         ("attn.proj.weight", (dim, dim)), ("attn.proj.bias", (dim,)),
+                         ("mlp.fc1.weight", (mlp, dim)), ("mlp.fc1.bias", (mlp,)),
+                         ("mlp.fc2.weight", (dim, mlp)), ("mlp.fc2.bias", (dim,))]:
+            sd[f"blocks.{i}.{k}"] = torch.randn(*shape, generator=g)
+    return sd
+
+
+def test_load_weights_imagenet_remap():
+    """timm ViT -> SiT remap (utils/utils.py:11-35): every encoder tensor and mlp_head.0 replaced, patch embedding /
+    cls / pos / mlp_head.1 untouched, result loads strictly into the B200 SiT."""
+    cfg = dict(dim=192, depth=3, heads=3, mlp_dim=768, num_patches=20, num_vertices=15)
+    model = svit.SiT(**cfg)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    timm = _timm_like_state_dict(192, 3, 768)
+    sd = svit.load_weights_imagenet(model.state_dict(), timm, 3)
+    model.load_state_dict(sd, strict=True)
+    after = model.state_dict()
+    assert torch.equal(after["mlp_head.0.weight"], timm["norm.weight"])
+    assert torch.equal(after["transformer.layers.2.0.fn.to_qkv.weight"], timm["blocks.2.attn.qkv.weight"])
+    assert torch.equal(after["transformer.layers.1.1.fn.net.3.bias"], timm["blocks.1.mlp.fc2.bias"])
+    for k in ("pos_embedding", "cls_token", "to_patch_embedding.1.weight", "to_patch_embedding.1.bias", "mlp_head.1.weight"):
+        assert torch.equal(after[k], before[k]), k
+    changed = [k for k in after if not torch.equal(after[k], before[k])]
+    assert len(changed) == 2 + 11 * 3
+
+
+@needs_reference
+def test_load_weights_imagenet_equals_reference_function():
+    """Pinned against the reference's own utils/utils.py::load_weights_imagenet (its nibabel import is stubbed: the
+    package is absent offline and unrelated to this function)."""
+    import importlib.util
+    import types
+    sys.modules.setdefault("nibabel", types.ModuleType("nibabel"))
+    spec = importlib.util.spec_from_file_location("_svit_reference_utils",
+                                                  os.path.join(reference_loader.REFERENCE_ROOT, "utils", "utils.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cfg = dict(dim=192, depth=2, heads=3, mlp_dim=768, num_patches=20, num_vertices=15)
+    timm = _timm_like_state_dict(192, 2, 768, seed=3)
+    base = OracleSiT(**cfg).state_dict()
+    a = ref.load_weights_imagenet({k: v.clone() for k, v in base.items()}, timm, 2)
+    b = svit.load_weights_imagenet({k: v.clone() for k, v in base.items()}, timm, 2)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_load_ssl_checkpoint_unwraps_pretrain_format(tmp_path):
+    """tools/pretrain.py:378-389 saves {'model_state_dict': ...}; train.py:216 passes the wrapper to load_state_dict
+    (a silent no-op).  load_ssl_checkpoint unwraps it, also from the masked_patch_pretraining key space."""
+    cfg = dict(dim=128, depth=2, heads=2, mlp_dim=256, num_patches=20, num_vertices=15)
+    src = svit.SiT(**cfg)
+    dst = svit.SiT(**cfg)
+    path = tmp_path / "encoder-best.pt"
+    torch.save({"epoch": 3, "model_state_dict": src.state_dict(), "loss": 0.1}, path)
+    missing, unexpected = svit.load_ssl_checkpoint(dst, str(path))
+    assert not missing and not unexpected
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    wrapped = {"transformer." + k: v for k, v in src.state_dict().items()}
+    wrapped.update({"to_original.weight": torch.zeros(60, 128), "to_original.bias": torch.zeros(60), "mask_token": torch.zeros(1, 1, 60)})
+    dst2 = svit.SiT(**cfg)
+    missing, unexpected = svit.load_ssl_checkpoint(dst2, {"model_state_dict": wrapped})
+    assert not missing and not unexpected
+    assert torch.equal(dst2.state_dict()["cls_token"], src.state_dict()["cls_token"])
