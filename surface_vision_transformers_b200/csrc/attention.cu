@@ -23,12 +23,14 @@ constexpr int TILE_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 // shift is the row's score against key 0 (any shift is exact for softmax; the log-sum-exp is reported with the same
 // shift), and a guard on the row sum falls back to the classic max-shift pass in the (never observed) overflow case.
 // 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the key columns.
-// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sP 96K | sO 16K | row sums / maxima | barriers
+// P never touches shared memory: the bf16 probabilities are written back into TMEM over the consumed scores
+// (tcgen05.st, two per 32-bit column) and feed the PV product as the A operand FROM TMEM -- no STS / proxy fence in the
+// softmax (LSU shared-memory traffic crawls while the tensor core streams operands) and no A fetch for the PV MMAs.
+// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sO 16K | row sums / maxima | barriers   (~130 KB)
 constexpr int FWD_SQ = 0;
 constexpr int FWD_SK = FWD_SQ + TILE_BYTES;
 constexpr int FWD_SV = FWD_SK + 3 * TILE_BYTES;
-constexpr int FWD_SP = FWD_SV + 3 * TILE_BYTES;
-constexpr int FWD_SO = FWD_SP + 6 * TILE_BYTES;
+constexpr int FWD_SO = FWD_SV + 3 * TILE_BYTES;
 constexpr int FWD_RED = FWD_SO + TILE_BYTES;      // float [2][128]
 constexpr int FWD_BAR = FWD_RED + 2 * 128 * 4;
 constexpr int FWD_SMEM = 1024 + FWD_BAR + 128;
@@ -41,7 +43,12 @@ struct AttnFwdArgs {
     float* lse;
     int B, H, T;
     float scale, scale_log2e;
+    int debug;  // SVIT_ATTN_DEBUG: 8 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
 };
+
+// clock64 timeline of one CTA for scripts/prof_attn_*.py; costs nothing unless enabled
+__device__ long long g_attn_prof[256];
+#define PROFF(slot) do { if ((args.debug & 8) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ float fwd_ex2(float x) {
     float r;
@@ -55,7 +62,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     uint8_t* sQ = smem + FWD_SQ;
     uint8_t* sK = smem + FWD_SK;
     uint8_t* sV = smem + FWD_SV;
-    uint8_t* sP = smem + FWD_SP;
     uint8_t* sO = smem + FWD_SO;
     float* sRed = reinterpret_cast<float*>(smem + FWD_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
@@ -112,11 +118,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             const uint32_t idesc_s1 = umma_idesc_bf16(128, n1, 0, 0);
             const uint32_t idesc_s2 = umma_idesc_bf16(128, n2 > 0 ? n2 : 16, 0, 0);
             const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            PROFF(0);
             mbar_wait(bar_kv, 0);
+            PROFF(1);
             for (int i = 0; i < nqb; ++i) {
                 const uint32_t ph = i & 1;
                 mbar_wait(bar_q, ph);
+                PROFF(10 + i * 10);
                 tc_fence_after();
                 // S = Q K^T  (K-major A and B)
 #pragma unroll
@@ -128,21 +137,22 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 }
                 umma_commit(bar_s);
                 mbar_wait(bar_s, ph);  // S done -> sQ reusable
+                PROFF(11 + i * 10);
                 if (i + 1 < nqb) {
                     mbar_expect_tx(bar_q, TILE_BYTES);
                     tma_load_3d(sQ, &args.tmQKV, bar_q, h * 64, (i + 1) * 128, b);
                 }
-                mbar_wait(bar_p, ph);  // P written to smem, S columns free
+                mbar_wait(bar_p, ph);  // P (bf16, in TMEM over the scores) complete
+                PROFF(12 + i * 10);
                 if (i > 0) mbar_wait(bar_of, (i - 1) & 1);  // previous O drained from TMEM
                 tc_fence_after();
-                // O = P V  (A = P K-major from smem, B = V MN-major)
+                // O = P V  (A = P from TMEM: lanes = query rows, 8 columns of packed bf16 pairs per 16-key step; B = V MN-major)
                 const int ksteps = tk / 16;
-                for (int s = 0; s < ksteps; ++s) {
-                    const uint64_t ad = umma_smem_desc(p_addr + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024);
-                    const uint64_t bd = umma_smem_desc(v_addr + s * 2048, 8192, 1024);
-                    umma_ss(tmem_base + FWD_TMEM_O, ad, bd, idesc_pv, s != 0);
-                }
+                for (int s = 0; s < ksteps; ++s)
+                    umma_ts(tmem_base + FWD_TMEM_O, tmem_base + s * 8, umma_smem_desc(v_addr + s * 2048, 8192, 1024), idesc_pv,
+                            s != 0);
                 umma_commit(bar_o);
+                PROFF(13 + i * 10);
             }
         }
     } else {
@@ -157,38 +167,54 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
         const int col_lo = hf == 0 ? 0 : split;
         const int col_hi = hf == 0 ? split : tk;
 
-        // exp2((s - shift) * c) of this thread's columns -> bf16 P tile in smem; returns the partial row sum
+        // exp2((s - shift) * c) of this thread's columns -> packed bf16 pairs in registers (up to 6 groups of 32
+        // columns per half); returns the partial row sum
+        uint32_t pk[96];
         auto softmax_pass = [&](float shift_c) {
-            float sum = 0.0f;
-            for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c0, r);
-                tmem_ld_wait();
-                uint8_t* prow = sP + (c0 >> 6) * TILE_BYTES + row * 128;
-                const int cb = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group (0 or 4)
+            float sm0 = 0.0f, sm1 = 0.0f;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float pv[8];
+            for (int g6 = 0; g6 < 6; ++g6) {
+                const int c0 = col_lo + g6 * 32;
+                if (c0 < col_hi) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + c0, r);
+                    tmem_ld_wait();
+                    if (c0 + 32 <= T) {
+                        // all 32 keys real: no masking.  The row sum adds the fp32 probabilities (their bf16 rounding
+                        // in the PV product is unbiased; the difference is ~1e-4 relative, far below bf16 resolution)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = c0 + g * 8 + e;
-                        const float ex = fwd_ex2(fmaf(__uint_as_float(r[g * 8 + e]), c, -shift_c));
-                        pv[e] = (col < T && col < col_hi) ? ex : 0.0f;
+                        for (int e = 0; e < 32; e += 2) {
+                            const float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
+                            const float p1 = fwd_ex2(fmaf(__uint_as_float(r[e + 1]), c, -shift_c));
+                            pk[g6 * 16 + e / 2] = pack_bf16(p0, p1);
+                            sm0 += p0;
+                            sm1 += p1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
+                            float p1 = fwd_ex2(fmaf(__uint_as_float(r[e + 1]), c, -shift_c));
+                            if (c0 + e >= T) p0 = 0.0f;
+                            if (c0 + e + 1 >= T) p1 = 0.0f;
+                            pk[g6 * 16 + e / 2] = pack_bf16(p0, p1);
+                            sm0 += p0;
+                            sm1 += p1;
+                        }
                     }
-                    uint4 o;
-                    o.x = pack_bf16(pv[0], pv[1]);
-                    o.y = pack_bf16(pv[2], pv[3]);
-                    o.z = pack_bf16(pv[4], pv[5]);
-                    o.w = pack_bf16(pv[6], pv[7]);
-                    // the row sum uses the bf16-rounded probabilities that the PV product will see
-                    sum += bf16_lo(o.x) + bf16_hi(o.x) + bf16_lo(o.y) + bf16_hi(o.y) + bf16_lo(o.z) + bf16_hi(o.z) +
-                           bf16_lo(o.w) + bf16_hi(o.w);
-                    // a 32-column group that straddles col_hi belongs to this half only up to col_hi; the other
-                    // half never writes these chunks (its range starts at a multiple of 32)
-                    *reinterpret_cast<uint4*>(prow + (((cb + g) ^ (row & 7)) << 4)) = o;
                 }
             }
-            return sum;
+            return sm0 + sm1;
+        };
+        // packed P -> TMEM, in place over the scores: the pair (2k, 2k+1) of S columns lands in column k.  Called only
+        // after every warp of the CTA has finished reading S (the row-sum barriers below).
+        auto store_p = [&]() {
+#pragma unroll
+            for (int g6 = 0; g6 < 6; ++g6) {
+                const int c0 = col_lo + g6 * 32;
+                if (c0 < col_hi) tmem_st_32x16(t_row + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(&pk[g6 * 16]));
+            }
+            tmem_st_wait();
         };
 
         for (int i = 0; i < nqb; ++i) {
@@ -199,6 +225,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             float shift = __uint_as_float(tmem_ld_32x1(t_row));
             tmem_ld_wait();
             float part = softmax_pass(shift * c);
+            if (threadIdx.x == 0) PROFF(14 + i * 10);
             sRed[hf * 128 + row] = part;
             bool bad = named_bar_or(1, 256, false);  // (barrier only: make both halves' partial sums visible)
             float total = sRed[row] + sRed[128 + row];
@@ -224,11 +251,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 total = sRed[row] + sRed[128 + row];
                 named_bar_sync(2, 256);
             }
-            fence_proxy_async_smem();
+            if (threadIdx.x == 0) PROFF(15 + i * 10);
+            store_p();
             tc_fence_before();
             mbar_arrive_warp(bar_p);
+            if (threadIdx.x == 0) PROFF(16 + i * 10);
             // ---- epilogue: O / sum -> bf16 -> staging -> TMA store (each half converts 32 of the 64 columns) ----
             mbar_wait(bar_o, ph);
+            if (threadIdx.x == 0) PROFF(17 + i * 10);
             tc_fence_after();
             const float inv = 1.0f / total;
             uint32_t o0[32];
@@ -321,7 +351,6 @@ struct AttnBwdArgs {
     int debug;  // SVIT_ATTN_DEBUG: 4 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
 };
 
-__device__ long long g_attn_prof[256];
 #define PROF(slot) do { if ((args.debug & 4) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -827,6 +856,10 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     a.T = d.T;
     a.scale = d.scale;
     a.scale_log2e = d.scale * 1.4426950408889634f;
+    {
+        static const char* dbg = getenv("SVIT_ATTN_DEBUG");
+        a.debug = dbg ? atoi(dbg) : 0;
+    }
     attn_fwd_kernel<<<d.B * d.H, FWD_THREADS, FWD_SMEM, stream>>>(a);
     count_launch();
     cudaError_t e = cudaGetLastError();
