@@ -63,6 +63,23 @@ unsigned long long svit_launch_count(void);
 int svit_set_check_mode(svit_engine* e, int on);
 int svit_get_check_mode(const svit_engine* e);
 
+/* ---- dropout > 0 ----
+ * Replaces the reference's four nn.Dropout sites: emb_dropout after the position add (models/sit.py:55,74) and, in
+ * every encoder block, the Dropout after to_out, after the GELU and after the second FeedForward Linear (the
+ * vit-pytorch layout pinned by utils/utils.py:18-33).  svit_set_dropout() fixes the state used by the NEXT forward
+ * and by the backward that belongs to it (call it again with the same values before that backward if another forward
+ * ran in between); p = emb_p = 0 (the default, and what nn.Module.eval() means) disables the extra passes.
+ * Keep decisions are a pure function of (seed, offset, site, element index) -- element i of a site's row-major tensor
+ * is kept iff word (i & 3) of Philox4x32-10(counter = {i >> 2, site, offset_lo, offset_hi}, key = {seed_lo, seed_hi})
+ * is >= floor(p * 2^32); kept values are scaled by 1 / (1 - p).  Sites: 4 * layer + {0: to_out, 1: after GELU,
+ * 2: after the second Linear}; 0xFFFF0000: emb_dropout.  The host advances `offset` once per training step.
+ * The stream differs from torch's nn.Dropout stream (as any two dropout implementations do); the distribution
+ * (independent Bernoulli(1 - p) keeps, 1 / (1 - p) scaling) is the reference's.
+ * svit_dropout_mask() writes the keep decisions as bytes (test hook; oracle/dropout.py restates the generator). */
+int svit_set_dropout(svit_engine* e, float p, float emb_p, unsigned long long seed, unsigned long long offset);
+int svit_dropout_mask(uint8_t* keep, size_t n, float p, unsigned long long seed, unsigned long long offset, unsigned site,
+                      void* stream);
+
 /* ---- engine life cycle (host-side object; owns no device memory) ---- */
 svit_engine* svit_create(const svit_config* cfg);
 void svit_destroy(svit_engine* e);

@@ -42,6 +42,8 @@ SIGNATURES = {
     "svit_workspace_bytes": (csz, [vp, ci, ci, ci]),
     "svit_set_check_mode": (ci, [vp, ci]),
     "svit_get_check_mode": (ci, [vp]),
+    "svit_set_dropout": (ci, [vp, cf, cf, ctypes.c_ulonglong, ctypes.c_ulonglong]),
+    "svit_dropout_mask": (ci, [vp, csz, cf, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_uint, vp]),
     "svit_prepare_weights": (ci, [vp, vp, vp, vp]),
     "svit_mpp_prepare_weights": (ci, [vp, vp, vp, vp]),
     "svit_forward": (ci, [vp, vp, vp, vp, csz, vp, ci, vp, ci, vp, vp, vp, ci, vp]),

@@ -9,6 +9,7 @@
 
 #include "attention.cuh"
 #include "check.cuh"
+#include "dropout.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "svit_b200.h"
@@ -34,6 +35,9 @@ struct svit_engine {
     size_t msh_wdec, msh_wdecT, msh_total;
     int check;  // fp32 check mode (svit_set_check_mode)
     const float* wdec_f32;  // fp32 master of the MPP decoder weight (recorded by svit_mpp_prepare_weights, check mode)
+    // dropout state of the next forward / backward (svit_set_dropout); p = 0 disables a site
+    float drop_p, drop_emb_p;
+    unsigned long long drop_seed, drop_offset;
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -167,6 +171,13 @@ static int wgrad(const svit_engine* e, cudaStream_t st, const void* dY, int ldy,
     return launch_gemm_wgrad(d, e->num_sms, st);
 }
 
+static inline DropoutSite drop_layer(const svit_engine* e, int l, int which) {
+    return DropoutSite{e->drop_seed, e->drop_offset, dropout_site_layer(l, which), e->drop_p};
+}
+static inline DropoutSite drop_emb(const svit_engine* e) {
+    return DropoutSite{e->drop_seed, e->drop_offset, DROP_SITE_EMB, e->drop_emb_p};
+}
+
 static inline const bf16* shp(const void* shadow, size_t off) {
     return reinterpret_cast<const bf16*>(reinterpret_cast<const uint8_t*>(shadow) + off);
 }
@@ -196,6 +207,8 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
                        const float** x_final) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
     const float scale = 0.125f;  // dim_head ** -0.5 with dim_head = 64
+    const bool drop = e->drop_p > 0.0f;  // extra passes (dropout.cuh); the p = 0 launch sequence is unchanged
+    const size_t nD = static_cast<size_t>(M) * D, nmlp = static_cast<size_t>(M) * mlp;
     const float* xin = x_in;
     for (int l = 0; l < e->depth; ++l) {
         LayerWs& L = w.L[l];
@@ -208,6 +221,7 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
         RET_IF(launch_attn_fwd(ad, st));
         RET_IF(gemm(e, st, L.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, L.xmid, D, M, D, I, EPI_RESID, 1,
                     pp(OUT_B), xin));
+        if (drop) RET_IF(launch_dropout_residual(L.xmid, xin, nD, drop_layer(e, l, DROP_SITE_TO_OUT), st));
         RET_IF(launch_ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
         if (w.training) {
             // training keeps gelu'(u) (in L.u) instead of u: the backward epilogue is then a single multiply
@@ -217,8 +231,11 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
             RET_IF(gemm(e, st, L.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, L.h, mlp, M, mlp, D,
                         EPI_GELU_ONLY, 0, pp(FC1_B)));
         }
+        // the same mask on gelu(u) and on the stored gelu'(u): d/du [gelu(u) m / (1-p)] = gelu'(u) m / (1-p)
+        if (drop) RET_IF(launch_dropout_scale(L.h, w.training ? L.u : nullptr, nmlp, 1, drop_layer(e, l, DROP_SITE_FF_ACT), st));
         RET_IF(gemm(e, st, L.h, mlp, shp(sh, e->sh_w2) + static_cast<size_t>(l) * D * mlp, mlp, L.xout, D, M, D, mlp,
                     EPI_RESID, 1, pp(FC2_B), L.xmid));
+        if (drop) RET_IF(launch_dropout_residual(L.xout, L.xmid, nD, drop_layer(e, l, DROP_SITE_FF_OUT), st));
         xin = L.xout;
     }
     *x_final = xin;
@@ -227,10 +244,15 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
 
 // On entry w.g / w.g16 hold dL/dx_final (fp32 + bf16) and grads[fc2_b of last layer] already holds colsum(g).
 // On exit w.g / w.g16 hold dL/dx_in.
+// With dropout the gradient that enters a dropped branch is g * m / (1-p) (a bf16 copy in w.da, which is free at
+// both points); the bias gradients of to_out / fc2 are then column sums of that masked copy, so they come from the
+// wgrad kernel's bias column instead of the LayerNorm-backward / head column sums (callers skip those too).
 static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws& w, const float* x_in, float* G,
                        cudaStream_t st, svit_progress_fn progress = nullptr, void* user = nullptr) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
     const float scale = 0.125f;
+    const bool drop = e->drop_p > 0.0f;
+    const size_t nD = static_cast<size_t>(M) * D;
     for (int l = e->depth - 1; l >= 0; --l) {
         LayerWs& L = w.L[l];
         const float* xin = (l == 0) ? x_in : w.L[l - 1].xout;
@@ -238,26 +260,36 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         auto gp = [&](int which) { return G + e->poff[pidx_layer(l, which)]; };
         // ---- FeedForward ----
         // du = (g W2) * gelu'(u)      (L.u holds gelu'(u), stored by the forward epilogue)
-        RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_MUL,
+        const bf16* gb = w.g16;
+        if (drop) {
+            RET_IF(launch_dropout_grad(w.g, w.da, nD, 1, drop_layer(e, l, DROP_SITE_FF_OUT), st));
+            gb = w.da;
+        }
+        RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_MUL,
                     0, nullptr, L.u));
-        RET_IF(wgrad(e, st, w.g16, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp));
+        RET_IF(wgrad(e, st, gb, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp, drop ? gp(FC2_B) : nullptr));
         // da2 = du W1
         RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, M, D, mlp,
                     EPI_STORE, 0));
         RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D, gp(FC1_B)));  // + d fc1_b = colsum(du)
         // g_mid = g + LN2'(da2) ; colsum(g_mid) = d out_b
-        RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, w.g16, gp(LN2_W), gp(LN2_B), gp(OUT_B), M, D,
-                             st));
+        RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, w.g16, gp(LN2_W), gp(LN2_B),
+                             drop ? nullptr : gp(OUT_B), M, D, st));
         // ---- Attention ----
-        RET_IF(gemm(e, st, w.g16, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
-        RET_IF(wgrad(e, st, w.g16, D, L.O, I, gp(OUT_W), I, M, D, I));
+        gb = w.g16;
+        if (drop) {
+            RET_IF(launch_dropout_grad(w.g, w.da, nD, 1, drop_layer(e, l, DROP_SITE_TO_OUT), st));
+            gb = w.da;
+        }
+        RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
+        RET_IF(wgrad(e, st, gb, D, L.O, I, gp(OUT_W), I, M, D, I, drop ? gp(OUT_B) : nullptr));
         AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, nullptr, w.dqkv, w.B, e->H, e->T, scale, nullptr};
         RET_IF(launch_attn_bwd(bd, st));
         RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
                     EPI_STORE, 0));
         RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
         // g_in = g_mid + LN1'(da1) ; colsum(g_in) = d fc2_b of the previous layer
-        float* cs = (l > 0) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
+        float* cs = (l > 0 && !drop) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
         RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs, M, D, st));
         // every gradient of layer l is final now (d fc2_b[l] was added by the layer above / the head)
         if (progress != nullptr) progress(l, user);
@@ -267,13 +299,21 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
 
 static int embed_fwd(const svit_engine* e, const void* sh, Ws& w, const PackDesc& pd, cudaStream_t st) {
     RET_IF(launch_pack_patches(pd, st));
-    return gemm(e, st, w.Apatch, e->Kp, shp(sh, e->sh_wpe), e->Kp, w.x0, e->D, w.M, e->D, e->Kp, EPI_STORE, 1, nullptr,
+    RET_IF(gemm(e, st, w.Apatch, e->Kp, shp(sh, e->sh_wpe), e->Kp, w.x0, e->D, w.M, e->D, e->Kp, EPI_STORE, 1, nullptr,
                 nullptr, nullptr, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(sh) + e->sh_rowtab),
-                e->T);
+                e->T));
+    // emb_dropout over all T rows, after the position add (models/sit.py:73-74)
+    if (e->drop_emb_p > 0.0f) RET_IF(launch_dropout_scale(w.x0, nullptr, static_cast<size_t>(w.M) * e->D, 0, drop_emb(e), st));
+    return 0;
 }
 
 // g / g16 hold dL/dx0
 static int embed_bwd(const svit_engine* e, Ws& w, float* G, cudaStream_t st) {
+    if (e->drop_emb_p > 0.0f) {
+        const size_t n = static_cast<size_t>(w.M) * e->D;
+        RET_IF(launch_dropout_scale(w.g, nullptr, n, 0, drop_emb(e), st));
+        RET_IF(launch_cast_bf16(w.g, w.g16, n, st));
+    }
     RET_IF(launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], w.B, e->T, e->D, st));
     cudaMemsetAsync(w.dWp, 0, static_cast<size_t>(e->D) * e->Kp * sizeof(float), st);
     RET_IF(wgrad(e, st, w.g16, e->D, w.Apatch, e->Kp, w.dWp, e->Kp, w.M, e->D, e->Kp));
@@ -366,6 +406,8 @@ static int ck_wgrad(cudaStream_t st, const float* dY, const float* X, float* dW,
 static int ck_encoder_fwd(const svit_engine* e, const float* P, CkWs& w, const float* x_in, cudaStream_t st,
                           const float** x_final) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
+    const bool drop = e->drop_p > 0.0f;
+    const size_t nD = static_cast<size_t>(M) * D, nmlp = static_cast<size_t>(M) * mlp;
     const float* xin = x_in;
     for (int l = 0; l < e->depth; ++l) {
         CkLayer& L = w.L[l];
@@ -374,9 +416,12 @@ static int ck_encoder_fwd(const svit_engine* e, const float* P, CkWs& w, const f
         RET_IF(ck_linear(st, L.a1, pp(QKV_W), L.qkv, M, 3 * I, D));
         RET_IF(ck::attn_fwd(L.qkv, L.O, L.lse, w.B, e->H, e->T, 0.125f, st));
         RET_IF(ck_linear(st, L.O, pp(OUT_W), L.xmid, M, D, I, pp(OUT_B), xin));
+        if (drop) RET_IF(launch_dropout_residual(L.xmid, xin, nD, drop_layer(e, l, DROP_SITE_TO_OUT), st));
         RET_IF(ck::ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
         RET_IF(ck_linear(st, L.a2, pp(FC1_W), L.u, M, mlp, D, pp(FC1_B), nullptr, L.h));
+        if (drop) RET_IF(launch_dropout_scale(L.h, nullptr, nmlp, 0, drop_layer(e, l, DROP_SITE_FF_ACT), st));
         RET_IF(ck_linear(st, L.h, pp(FC2_W), L.xout, M, D, mlp, pp(FC2_B), L.xmid));
+        if (drop) RET_IF(launch_dropout_residual(L.xout, L.xmid, nD, drop_layer(e, l, DROP_SITE_FF_OUT), st));
         xin = L.xout;
     }
     *x_final = xin;
@@ -386,26 +431,40 @@ static int ck_encoder_fwd(const svit_engine* e, const float* P, CkWs& w, const f
 static int ck_encoder_bwd(const svit_engine* e, const float* P, CkWs& w, const float* x_in, float* G, cudaStream_t st,
                           svit_progress_fn progress = nullptr, void* user = nullptr) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
+    const bool drop = e->drop_p > 0.0f;
+    const size_t nD = static_cast<size_t>(M) * D, nmlp = static_cast<size_t>(M) * mlp;
     for (int l = e->depth - 1; l >= 0; --l) {
         CkLayer& L = w.L[l];
         const float* xin = (l == 0) ? x_in : w.L[l - 1].xout;
         auto pp = [&](int which) { return P + e->poff[pidx_layer(l, which)]; };
         auto gp = [&](int which) { return G + e->poff[pidx_layer(l, which)]; };
-        RET_IF(ck_dgrad(st, w.g, pp(FC2_W), w.du, M, D, mlp));           // dh = g W2
-        RET_IF(ck::mul_dgelu(w.du, L.u, static_cast<size_t>(M) * mlp, st));  // du = dh * gelu'(u)
-        RET_IF(ck_wgrad(st, w.g, L.h, gp(FC2_W), M, D, mlp));
+        const float* gs = w.g;  // gradient entering the (possibly dropped) branch; w.da is free here
+        if (drop) {
+            RET_IF(launch_dropout_grad(w.g, w.da, nD, 0, drop_layer(e, l, DROP_SITE_FF_OUT), st));
+            gs = w.da;
+        }
+        RET_IF(ck_dgrad(st, gs, pp(FC2_W), w.du, M, D, mlp));           // dh = g W2
+        if (drop) RET_IF(launch_dropout_scale(w.du, nullptr, nmlp, 0, drop_layer(e, l, DROP_SITE_FF_ACT), st));
+        RET_IF(ck::mul_dgelu(w.du, L.u, nmlp, st));  // du = dh * gelu'(u)
+        RET_IF(ck_wgrad(st, gs, L.h, gp(FC2_W), M, D, mlp));
+        if (drop) RET_IF(ck::colsum(gs, gp(FC2_B), M, D, st));
         RET_IF(ck::colsum(w.du, gp(FC1_B), M, mlp, st));
         RET_IF(ck_dgrad(st, w.du, pp(FC1_W), w.da, M, mlp, D));
         RET_IF(ck_wgrad(st, w.du, L.a2, gp(FC1_W), M, mlp, D));
         RET_IF(ck::ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, gp(LN2_W), gp(LN2_B), M, D, st));
-        RET_IF(ck::colsum(w.g, gp(OUT_B), M, D, st));
-        RET_IF(ck_dgrad(st, w.g, pp(OUT_W), w.dO, M, D, I));
-        RET_IF(ck_wgrad(st, w.g, L.O, gp(OUT_W), M, D, I));
+        gs = w.g;
+        if (drop) {
+            RET_IF(launch_dropout_grad(w.g, w.da, nD, 0, drop_layer(e, l, DROP_SITE_TO_OUT), st));
+            gs = w.da;
+        }
+        RET_IF(ck::colsum(gs, gp(OUT_B), M, D, st));
+        RET_IF(ck_dgrad(st, gs, pp(OUT_W), w.dO, M, D, I));
+        RET_IF(ck_wgrad(st, gs, L.O, gp(OUT_W), M, D, I));
         RET_IF(ck::attn_bwd(L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, 0.125f, st));
         RET_IF(ck_dgrad(st, w.dqkv, pp(QKV_W), w.da, M, 3 * I, D));
         RET_IF(ck_wgrad(st, w.dqkv, L.a1, gp(QKV_W), M, 3 * I, D));
         RET_IF(ck::ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, gp(LN1_W), gp(LN1_B), M, D, st));
-        if (l > 0) RET_IF(ck::colsum(w.g, G + e->poff[pidx_layer(l - 1, FC2_B)], M, D, st));
+        if (l > 0 && !drop) RET_IF(ck::colsum(w.g, G + e->poff[pidx_layer(l - 1, FC2_B)], M, D, st));
         if (progress != nullptr) progress(l, user);
     }
     return 0;
@@ -417,6 +476,7 @@ static int ck_forward(svit_engine* e, const float* P, void* ws_ptr, size_t ws_by
     RET_IF(ck::patches(pd, w.Ap, st));
     RET_IF(ck_linear(st, w.Ap, P + e->poff[P_PE_W], w.x0, w.M, e->D, e->K));
     RET_IF(ck::embed_finish(w.x0, P + e->poff[P_POS], P + e->poff[P_CLS], P + e->poff[P_PE_B], B, e->T, e->D, st));
+    if (e->drop_emb_p > 0.0f) RET_IF(launch_dropout_scale(w.x0, nullptr, static_cast<size_t>(w.M) * e->D, 0, drop_emb(e), st));
     const float* xf = nullptr;
     RET_IF(ck_encoder_fwd(e, P, w, w.x0, st, &xf));
     return launch_head_fwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)],
@@ -430,9 +490,11 @@ static int ck_backward(svit_engine* e, const float* P, void* ws_ptr, int B, cons
     RET_IF(launch_head_bwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)], dout,
                            w.g, w.g16, G + e->poff[pidx_head(e, 0)], G + e->poff[pidx_head(e, 1)],
                            G + e->poff[pidx_head(e, 2)], G + e->poff[pidx_head(e, 3)],
-                           G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st));
+                           e->drop_p > 0.0f ? nullptr : G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC,
+                           e->cfg.pool_mean, 1e-5f, st));
     if (progress != nullptr) progress(e->depth, user);
     RET_IF(ck_encoder_bwd(e, P, w, w.x0, G, st, progress, user));
+    if (e->drop_emb_p > 0.0f) RET_IF(launch_dropout_scale(w.g, nullptr, static_cast<size_t>(w.M) * e->D, 0, drop_emb(e), st));
     RET_IF(launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], B, e->T, e->D, st));
     RET_IF(ck_wgrad(st, w.g, w.Ap, G + e->poff[P_PE_W], w.M, e->D, e->K));
     if (progress != nullptr) progress(-1, user);
@@ -490,6 +552,8 @@ svit_engine* svit_create(const svit_config* cfg) {
     e->num_sms = 148;
     e->check = 0;
     e->wdec_f32 = nullptr;
+    e->drop_p = e->drop_emb_p = 0.0f;
+    e->drop_seed = e->drop_offset = 0;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int sms = 0;
@@ -559,6 +623,22 @@ int svit_set_check_mode(svit_engine* e, int on) {
     return 0;
 }
 int svit_get_check_mode(const svit_engine* e) { return e != nullptr ? e->check : 0; }
+int svit_set_dropout(svit_engine* e, float p, float emb_p, unsigned long long seed, unsigned long long offset) {
+    if (e == nullptr) return -1;
+    if (!(p >= 0.0f) || p >= 1.0f || !(emb_p >= 0.0f) || emb_p >= 1.0f) {
+        set_error("svit_set_dropout: probabilities must be in [0, 1) (got %f, %f)", p, emb_p);
+        return -1;
+    }
+    e->drop_p = p;
+    e->drop_emb_p = emb_p;
+    e->drop_seed = seed;
+    e->drop_offset = offset;
+    return 0;
+}
+int svit_dropout_mask(uint8_t* keep, size_t n, float p, unsigned long long seed, unsigned long long offset, unsigned site,
+                      void* stream) {
+    return launch_dropout_mask(keep, n, DropoutSite{seed, offset, site, p}, reinterpret_cast<cudaStream_t>(stream));
+}
 
 size_t svit_workspace_bytes(const svit_engine* e, int batch, int training, int mpp) {
     if (batch <= 0) return 0;
@@ -627,7 +707,8 @@ int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, 
     RET_IF(launch_head_bwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)], dout,
                            w.g, w.g16, G + e->poff[pidx_head(e, 0)], G + e->poff[pidx_head(e, 1)],
                            G + e->poff[pidx_head(e, 2)], G + e->poff[pidx_head(e, 3)],
-                           G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st));
+                           e->drop_p > 0.0f ? nullptr : G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC,
+                           e->cfg.pool_mean, 1e-5f, st));
     if (progress != nullptr) progress(e->depth, user);
     RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user));
     RET_IF(embed_bwd(e, w, G, st));
@@ -669,7 +750,7 @@ int svit_encoder_backward(svit_engine* e, const float* P, const void* sh, void* 
         RET_IF(ck_check_ws(e, B, 0, ws_ptr, 0, &cw));
         const size_t cn = static_cast<size_t>(cw.M) * e->D;
         cudaMemcpyAsync(cw.g, dy, cn * sizeof(float), cudaMemcpyDeviceToDevice, st);
-        RET_IF(ck::colsum(cw.g, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], cw.M, e->D, st));
+        if (!(e->drop_p > 0.0f)) RET_IF(ck::colsum(cw.g, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], cw.M, e->D, st));
         RET_IF(ck_encoder_bwd(e, P, cw, x, G, st));
         if (dx != nullptr) cudaMemcpyAsync(dx, cw.g, cn * sizeof(float), cudaMemcpyDeviceToDevice, st);
         return 0;
@@ -679,7 +760,7 @@ int svit_encoder_backward(svit_engine* e, const float* P, const void* sh, void* 
     const size_t n = static_cast<size_t>(w.M) * e->D;
     cudaMemcpyAsync(w.g, dy, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     RET_IF(launch_cast_bf16(dy, w.g16, n, st));
-    RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], w.M, e->D, e->D, st));
+    if (!(e->drop_p > 0.0f)) RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], w.M, e->D, e->D, st));
     RET_IF(encoder_bwd(e, P, sh, w, x, G, st));
     if (dx != nullptr) cudaMemcpyAsync(dx, w.g, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     return 0;
@@ -701,6 +782,8 @@ int svit_mpp_forward(svit_engine* e, const float* P, const void* sh, const void*
         RET_IF(ck::patches(cpd, cw.Ap, st));
         RET_IF(ck_linear(st, cw.Ap, P + e->poff[P_PE_W], cw.x0, cw.M, e->D, e->K));
         RET_IF(ck::embed_finish(cw.x0, P + e->poff[P_POS], P + e->poff[P_CLS], P + e->poff[P_PE_B], B, e->T, e->D, st));
+        if (e->drop_emb_p > 0.0f)
+            RET_IF(launch_dropout_scale(cw.x0, nullptr, static_cast<size_t>(cw.M) * e->D, 0, drop_emb(e), st));
         const float* cxf = nullptr;
         RET_IF(ck_encoder_fwd(e, P, cw, cw.x0, st, &cxf));
         RET_IF(ck_linear(st, cxf, e->wdec_f32, batch_out, cw.M, e->K, e->D, bdec));
@@ -734,8 +817,10 @@ int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void
         RET_IF(ck_wgrad(st, cw.dy, cxf, cgW, cM, cK, cD));
         RET_IF(ck::colsum(cw.dy, cgb, cM, cK, st));
         RET_IF(ck_dgrad(st, cw.dy, e->wdec_f32, cw.g, cM, cK, cD));
-        RET_IF(ck::colsum(cw.g, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], cM, cD, st));
+        if (!(e->drop_p > 0.0f)) RET_IF(ck::colsum(cw.g, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], cM, cD, st));
         RET_IF(ck_encoder_bwd(e, P, cw, cw.x0, G, st, progress, user));
+        if (e->drop_emb_p > 0.0f)
+            RET_IF(launch_dropout_scale(cw.g, nullptr, static_cast<size_t>(cM) * cD, 0, drop_emb(e), st));
         RET_IF(launch_embed_bwd(cw.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], B, e->T, cD, st));
         RET_IF(ck_wgrad(st, cw.g, cw.Ap, G + e->poff[P_PE_W], cM, cD, cK));
         if (progress != nullptr) progress(-1, user);
@@ -755,7 +840,7 @@ int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void
     // g = dy Wdec   (A = dy [M, K] pitch Kd, B = WdecT [D, K] pitch Kd)
     RET_IF(gemm(e, st, w.dy, Kd, shp(msh, e->msh_wdecT), Kd, w.g, D, M, D, K, EPI_STORE, 1));
     RET_IF(launch_cast_bf16(w.g, w.g16, static_cast<size_t>(M) * D, st));
-    RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], M, D, D, st));
+    if (!(e->drop_p > 0.0f)) RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], M, D, D, st));
     RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user));
     RET_IF(embed_bwd(e, w, G, st));
     if (progress != nullptr) progress(-1, user);

@@ -77,6 +77,8 @@ class _MPPFunction(torch.autograd.Function):
         T, K = model.num_patches + 1, model.num_channels * model.num_vertices
         out_full = torch.empty(B, T, K, dtype=torch.float32, device=dev)
         loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+        ctx.drop = model._next_dropout_state()   # emb_dropout (mpp.py:125) and the encoder's dropouts (mpp.py:128)
+        model._apply_dropout_state(ctx.drop)
         check(lib.svit_mpp_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(module._shadow),
                                    ptr(to_b), ptr(mask_token), ptr(ws), nbytes, ptr(batch), B, ptr(mask8), ptr(swap8),
                                    ptr(src64), ptr(repl8), ptr(loss_sum), ptr(out_full), 1 if training else 0,
@@ -105,6 +107,7 @@ class _MPPFunction(torch.autograd.Function):
         MG = torch.zeros_like(module._flat)
         with torch.cuda.device(ctx.dev):
             hook = model._make_progress_hook(G)
+            model._apply_dropout_state(ctx.drop)
             check(lib.svit_mpp_backward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(module._shadow),
                                         ptr(ctx.ws), ctx.B, ptr(batch), ptr(out_full), ptr(mask8),
                                         ptr(repl8) if ctx.has_replace else vp(0), ptr(coef), ptr(G), ptr(MG), hook, vp(0),

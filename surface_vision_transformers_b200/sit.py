@@ -93,6 +93,8 @@ class _SiTFunction(torch.autograd.Function):
         nbytes = lib.svit_workspace_bytes(model._engine, B, 1, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(B, model.num_classes, dtype=torch.float32, device=dev)
+        ctx.drop = model._next_dropout_state()
+        model._apply_dropout_state(ctx.drop)
         check(lib.svit_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(img), B,
                                vp(0), 0, vp(0), vp(0), ptr(out), 1, _stream(dev)), "svit_forward")
         ctx.model = model
@@ -109,6 +111,7 @@ class _SiTFunction(torch.autograd.Function):
         G = torch.zeros_like(model._flat)
         with torch.cuda.device(ctx.dev):
             hook = model._make_progress_hook(G)
+            model._apply_dropout_state(ctx.drop)
             check(lib.svit_backward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ctx.ws), ctx.B, ptr(dout),
                                     ptr(G), hook, vp(0), _stream(ctx.dev)), "svit_backward")
             model._finish_progress_hook(G)
@@ -127,6 +130,8 @@ class _EncoderFunction(torch.autograd.Function):
         nbytes = lib.svit_workspace_bytes(model._engine, B, training, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         y = torch.empty_like(x)
+        ctx.drop = model._next_dropout_state(emb=False)
+        model._apply_dropout_state(ctx.drop)
         check(lib.svit_encoder_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(x), B,
                                        ptr(y), training, _stream(dev)), "svit_encoder_forward")
         ctx.model = model
@@ -145,6 +150,7 @@ class _EncoderFunction(torch.autograd.Function):
         G = torch.zeros_like(model._flat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(ctx.dev):
+            model._apply_dropout_state(ctx.drop)
             check(lib.svit_encoder_backward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ctx.ws), ctx.B,
                                             ptr(x), ptr(dy), ptr(dx), ptr(G), _stream(ctx.dev)), "svit_encoder_backward")
         ctx.ws = None
@@ -157,9 +163,8 @@ class SiT(nn.Module):
                  num_vertices=2145, dim_head=64, dropout=0., emb_dropout=0.):
         super().__init__()
         assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
-        if dropout != 0. or emb_dropout != 0.:
-            raise NotImplementedError("the fused sm_100a path supports dropout=0 / emb_dropout=0 only "
-                                      "(all shipped reference configs use 0.0)")
+        if not (0. <= dropout < 1.) or not (0. <= emb_dropout < 1.):
+            raise ValueError(f"dropout probabilities must be in [0, 1) (got {dropout}, {emb_dropout})")
         if dim_head != 64:
             raise NotImplementedError("the fused attention kernel requires dim_head == 64")
         patch_dim = num_channels * num_vertices
@@ -176,6 +181,10 @@ class SiT(nn.Module):
         self.num_patches, self.num_classes = num_patches, num_classes
         self.num_channels, self.num_vertices = num_channels, num_vertices
         self.transformer._owner = weakref.ref(self)
+        # dropout > 0: counter-based masks generated inside the engine (include/svit_b200.h)
+        self._drop_p, self._emb_drop_p = float(dropout), float(emb_dropout)
+        self._drop_seed = None     # drawn from torch's seed at first use; see set_dropout_seed
+        self._drop_step = 0
 
         cfg = SvitConfig(dim, depth, heads, dim_head, mlp_dim, num_patches, num_vertices, num_channels, num_classes,
                          1 if pool == 'mean' else 0)
@@ -237,6 +246,26 @@ class SiT(nn.Module):
         cores instead of bf16 on the tensor cores -- for verification at a 1e-4 tolerance, not for speed."""
         check(_lib.load().svit_set_check_mode(self._engine, 1 if on else 0), "svit_set_check_mode")
         return self
+
+    def set_dropout_seed(self, seed, step=0):
+        """Fixes the (seed, step) of the dropout masks: forward number k after this call uses offset step + k."""
+        self._drop_seed, self._drop_step = int(seed) & 0xFFFFFFFFFFFFFFFF, int(step)
+        return self
+
+    def _next_dropout_state(self, emb=True):
+        """(p, emb_p, seed, offset) of the forward about to run; like nn.Dropout, active only in .train() mode."""
+        p, emb_p = (self._drop_p, self._emb_drop_p if emb else 0.) if self.training else (0., 0.)
+        if p == 0. and emb_p == 0.:
+            return (0., 0., 0, 0)
+        if self._drop_seed is None:
+            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            self._drop_seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
+        state = (p, emb_p, self._drop_seed, self._drop_step)
+        self._drop_step += 1
+        return state
+
+    def _apply_dropout_state(self, state):
+        check(_lib.load().svit_set_dropout(self._engine, state[0], state[1], state[2], state[3]), "svit_set_dropout")
 
     @property
     def check_mode(self):
@@ -319,6 +348,7 @@ class SiT(nn.Module):
         nbytes = lib.svit_workspace_bytes(self._engine, B, 0, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(B, self.num_classes, dtype=torch.float32, device=dev)
+        self._apply_dropout_state(self._next_dropout_state())   # .train() under no_grad still drops, as nn.Dropout does
         check(lib.svit_forward(self._engine, ptr(self._flat), ptr(self._shadow), ptr(ws), nbytes, ptr(img), B,
                                ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std), ptr(out), 0, _stream(dev)), "svit_forward")
         return out
@@ -342,6 +372,7 @@ class SiT(nn.Module):
             nbytes = lib.svit_workspace_bytes(self._engine, B, 0, 0)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             y = torch.empty_like(x)
+            self._apply_dropout_state(self._next_dropout_state(emb=False))
             check(lib.svit_encoder_forward(self._engine, ptr(self._flat), ptr(self._shadow), ptr(ws), nbytes, ptr(x), B,
                                            ptr(y), 0, _stream(dev)), "svit_encoder_forward")
             return y

@@ -396,3 +396,150 @@ def test_fit_tracks_reference_style_loop(tmp_path):
     assert set(ckpt) == set(oracle.state_dict())
     saved = torch.load(tmp_path / "out" / "preds_test.pt")
     assert saved["preds"].shape == (10,) and torch.equal(saved["targets"], val.labels)
+
+
+# ------------------------------------------------------------------------------------------- dropout > 0 (8(f)-4)
+def _dropout_pair(cfg, p, emb_p, seed, step, check_mode):
+    """B200 SiT with dropout and the oracle with MaskedDropout modules applying the very same keep decisions."""
+    from oracle.dropout import install
+    oracle = OracleSiT(**cfg).to(DEV)
+    model = svit.SiT(**cfg, dropout=p, emb_dropout=emb_p)
+    model.load_state_dict(oracle.state_dict())
+    model.to(DEV).set_check_mode(check_mode).set_dropout_seed(seed, step)
+    install(oracle, p, emb_p, seed, step)
+    return model, oracle
+
+
+@pytest.mark.parametrize("n,p,seed,offset,site", [(4096, 0.1, 1, 0, 0), (1001, 0.5, 0xDEADBEEFCAFEF00D, 2 ** 40 + 3, 46),
+                                                  (3, 0.25, 7, 1, 0xFFFF0000), (82176 * 96 + 1, 0.1, 123, 456, 5),
+                                                  (257, 0.0, 9, 9, 9)])
+def test_dropout_mask_generator_bit_exact(n, p, seed, offset, site):
+    """svit_dropout_mask (the Philox4x32-10 keep decisions every dropout kernel uses) == the numpy restatement."""
+    from oracle.dropout import keep_mask
+    from surface_vision_transformers_b200 import _lib
+    keep = torch.zeros(n, dtype=torch.uint8, device=DEV)
+    _lib.check(_lib.load().svit_dropout_mask(_lib.ptr(keep), n, p, seed, offset, site,
+                                            _lib.vp(torch.cuda.current_stream().cuda_stream)), "svit_dropout_mask")
+    want = keep_mask(n, p, seed, offset, site)
+    assert torch.equal(keep.cpu().bool(), torch.from_numpy(want))
+
+
+@pytest.mark.parametrize("pool", ["cls", "mean"])
+def test_dropout_fp32_check_mode_matches_oracle_with_same_masks(pool):
+    """dropout 0.1 / emb_dropout 0.2 (the reference's four nn.Dropout sites) in fp32 check mode: output, encoder output
+    and every parameter gradient within 1e-4 of the oracle applying the same masks."""
+    cfg = dict(dim=192, depth=3, heads=3, mlp_dim=768, num_patches=80, num_vertices=45, pool=pool)
+    B = 5
+    torch.manual_seed(11)
+    model, oracle = _dropout_pair(cfg, 0.1, 0.2, seed=2024, step=3, check_mode=True)
+    x = torch.randn(B, 4, cfg["num_patches"], cfg["num_vertices"], device=DEV)
+    y = torch.rand(B, device=DEV) * 19 + 26
+    out_o = oracle(x)
+    torch.nn.functional.mse_loss(out_o.squeeze(), y).backward()
+    out_m = model(x)
+    torch.nn.functional.mse_loss(out_m.squeeze(), y).backward()
+    assert rel_l2(out_m, out_o) < CHECK_TOL
+    ref = dict(oracle.named_parameters())
+    worst = max((rel_l2(p.grad, ref[n].grad), n) for n, p in model.named_parameters())
+    assert worst[0] < CHECK_TOL, worst
+    # the masks matter: the no-dropout forward is far away
+    model.eval()
+    with torch.no_grad():
+        assert rel_l2(model(x), out_o) > 10 * CHECK_TOL
+
+
+@pytest.mark.parametrize("name", ["C1_tiny_ico2", "C2_small_ico2"])
+def test_dropout_bf16_matches_oracle_with_same_masks(name):
+    """The tensor-core path with dropout > 0 against the fp32 oracle on the same masks, bf16 tolerance; the encoder
+    alone (model.transformer(x), no emb_dropout) too."""
+    cfg, B = CONFIGS[name]
+    cfg = dict(cfg, depth=6)
+    torch.manual_seed(12)
+    model, oracle = _dropout_pair(cfg, 0.1, 0.1, seed=77, step=0, check_mode=False)
+    x = torch.randn(B, 4, cfg["num_patches"], cfg["num_vertices"], device=DEV)
+    y = torch.rand(B, device=DEV) * 19 + 26
+    out_o = oracle(x)
+    torch.nn.functional.mse_loss(out_o.squeeze(), y).backward()
+    out_m = model(x)                                       # offset 0
+    torch.nn.functional.mse_loss(out_m.squeeze(), y).backward()
+    assert rel_l2(out_m, out_o) < 3 * TOL
+    check_grads(model, oracle)
+    from oracle.dropout import install
+    install(oracle, 0.1, 0.1, 77, 1)                       # the next forward of `model` uses offset 1
+    xe = torch.randn(B, cfg["num_patches"] + 1, cfg["dim"], device=DEV, requires_grad=True)
+    xo = xe.detach().clone().requires_grad_(True)
+    model.zero_grad(), oracle.zero_grad()
+    ye = model.transformer(xe)
+    yo = oracle.transformer(xo)
+    assert rel_l2(ye, yo) < TOL
+    w = torch.randn_like(yo)
+    (ye * w).sum().backward()
+    (yo * w).sum().backward()
+    assert rel_l2(xe.grad, xo.grad) < 2 * TOL
+    enc = [(n, p) for n, p in model.named_parameters() if n.startswith("transformer.")]
+    assert global_grad_rel(enc, oracle.named_parameters()) < TOL
+
+
+def test_dropout_train_eval_semantics_and_statistics():
+    """eval() == the dropout-free model bit for bit; train() differs, changes from step to step, is reproducible from
+    (seed, step), and drops under no_grad as nn.Dropout does; the mean over many masks approaches the eval output of
+    the first dropout site (unbiased 1/(1-p) scaling)."""
+    cfg = dict(dim=192, depth=2, heads=3, mlp_dim=768, num_patches=80, num_vertices=45)
+    torch.manual_seed(13)
+    plain = svit.SiT(**cfg).to(DEV)
+    model = svit.SiT(**cfg, dropout=0.2, emb_dropout=0.1)
+    model.load_state_dict(plain.state_dict())
+    model.to(DEV)
+    x = torch.randn(4, 4, 80, 45, device=DEV)
+    with torch.no_grad():
+        model.eval()
+        assert torch.equal(model(x), plain(x))
+        model.train().set_dropout_seed(5, 0)
+        a, b = model(x), model(x)
+        assert not torch.equal(a, b) and not torch.equal(a, plain(x))
+        model.set_dropout_seed(5, 0)
+        assert torch.equal(model(x), a) and torch.equal(model(x), b)
+    # unbiasedness at one site: encoder of depth 1 with only emb_dropout = linear in the mask up to the first LayerNorm
+    one = svit.SiT(**dict(cfg, depth=1), emb_dropout=0.3).to(DEV)
+    from surface_vision_transformers_b200 import _lib
+    n = 1 << 20
+    keep = torch.zeros(n, dtype=torch.uint8, device=DEV)
+    acc = torch.zeros(n, device=DEV)
+    for step in range(64):
+        _lib.check(_lib.load().svit_dropout_mask(_lib.ptr(keep), n, 0.3, 1, step, 0xFFFF0000,
+                                                _lib.vp(torch.cuda.current_stream().cuda_stream)), "mask")
+        acc += keep.float() / 0.7
+    assert abs(acc.mean().item() / 64 - 1.0) < 2e-3 and one._emb_drop_p == pytest.approx(0.3)
+
+
+def test_dropout_mpp_matches_oracle_with_same_masks():
+    """MPP forward / backward with dropout: emb_dropout at mpp.py:125, the encoder's dropouts through mpp.py:128."""
+    from oracle.dropout import install
+    from surface_vision_transformers_b200.mpp import draw_masks
+    cfg = dict(dim=192, depth=3, heads=3, mlp_dim=768, num_patches=80, num_vertices=45)
+    B, K = 4, 4 * 45
+    torch.manual_seed(14)
+    kw = dict(mask_prob=0.5, replace_prob=0.8, swap_prob=0.1, channels=4, num_vertices=cfg["num_vertices"])
+    oracle = OracleMPP(OracleSiT(**cfg), cfg["dim"], K, DEV, **kw).to(DEV)
+    for check_mode, tol in ((True, CHECK_TOL), (False, TOL)):
+        ssl = svit.masked_patch_pretraining(transformer=svit.SiT(**cfg, dropout=0.1, emb_dropout=0.1), dim_in=cfg["dim"],
+                                            dim_out=K, device=DEV, **kw)
+        ssl.load_state_dict(oracle.state_dict())
+        ssl.to(DEV)
+        ssl.transformer.set_check_mode(check_mode).set_dropout_seed(31, 4)
+        install(oracle.transformer, 0.1, 0.1, 31, 4)
+        oracle.zero_grad()
+        x = torch.randn(B, 4, cfg["num_patches"], cfg["num_vertices"], device=DEV)
+        masks = draw_masks(B, cfg["num_patches"], K, DEV, 0.5, 0.8, 0.1)
+        lo, oo = oracle(x, masks=masks)
+        lo.backward()
+        lm, om = ssl(x, masks=masks)
+        lm.backward()
+        assert abs(lm.item() - lo.item()) / lo.item() < tol
+        assert rel_l2(om, oo) < tol
+        ref = dict(oracle.named_parameters())
+        for n, p in ssl.named_parameters():
+            if ref[n].grad is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            else:
+                assert rel_l2(p.grad, ref[n].grad) < (tol if check_mode else 2 * tol), n

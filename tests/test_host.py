@@ -7,6 +7,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -56,8 +57,10 @@ def test_engine_rejects_unsupported_configs():
     bad = _lib.SvitConfig(384, 12, 6, 64, 1536, 1280, 45, 4, 1, 0)      # T = 1281 > 384
     assert not lib.svit_create(ctypes.byref(bad))
     assert b"sequence length" in lib.svit_last_error()
-    with pytest.raises(NotImplementedError):
-        svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, dropout=0.1)
+    with pytest.raises(ValueError):
+        svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, dropout=1.0)
+    with pytest.raises(ValueError):
+        svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, emb_dropout=-0.1)
     with pytest.raises(AssertionError):
         svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, pool="max")
 
@@ -326,3 +329,59 @@ def test_load_ssl_checkpoint_unwraps_pretrain_format(tmp_path):
     missing, unexpected = svit.load_ssl_checkpoint(dst2, {"model_state_dict": wrapped})
     assert not missing and not unexpected
     assert torch.equal(dst2.state_dict()["cls_token"], src.state_dict()["cls_token"])
+
+
+# ------------------------------------------------------------------------------------------- dropout (8(f)-4)
+def test_philox_restatement_matches_random123_known_answers():
+    """oracle/dropout.py's Philox4x32-10 against the Random123 known-answer vectors (kat_vectors: zeros, ones, pi)."""
+    from oracle.dropout import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(w) for w in philox4x32_10(*ctr, *key)) == want
+
+
+def test_dropout_oracle_masks_and_module_semantics():
+    from oracle.dropout import MaskedDropout, SITE_EMB, install, keep_mask
+    from oracle.sit_oracle import OracleSiT
+    n = 1_000_003
+    for p in (0.1, 0.5):
+        m = keep_mask(n, p, seed=1234, offset=5, site=7)
+        assert m.shape == (n,) and abs(m.mean() - (1 - p)) < 4 * (p * (1 - p) / n) ** 0.5
+        assert np.array_equal(m, keep_mask(n, p, 1234, 5, 7))                   # pure function of its arguments
+        assert not np.array_equal(m, keep_mask(n, p, 1234, 6, 7))               # another step
+        assert not np.array_equal(m, keep_mask(n, p, 1234, 5, 8))               # another site
+        assert np.array_equal(m[:1001], keep_mask(1001, p, 1234, 5, 7))         # prefix-stable, ragged tail
+    assert keep_mask(4097, 0.0, 1, 2, 3).all()
+    # independent across elements: lag-1 agreement of a Bernoulli(0.5) stream is 0.5
+    m = keep_mask(n, 0.5, 99, 0, SITE_EMB)
+    assert abs((m[1:] == m[:-1]).mean() - 0.5) < 3e-3
+    d = MaskedDropout(0.25, 1, 0, 3)
+    x = torch.randn(7, 33)
+    y = d(x)
+    kept = y != 0
+    assert torch.allclose(y[kept], x[kept] / 0.75) and 0.5 < kept.float().mean() < 0.95
+    d.eval()
+    assert d(x) is x
+    model = install(OracleSiT(dim=64, depth=2, heads=2, mlp_dim=64, num_patches=4, num_vertices=3), 0.1, 0.2, 5, 0)
+    sites = [mod.site for mod in model.modules() if isinstance(mod, MaskedDropout)]
+    assert sorted(sites) == [0, 1, 2, 4, 5, 6, SITE_EMB]
+    assert not any(isinstance(mod, torch.nn.Dropout) for mod in model.modules())
+
+
+def test_dropout_state_follows_module_mode():
+    """Like nn.Dropout: active only in .train(); every training forward advances the offset; eval draws nothing."""
+    m = svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, num_patches=4, num_vertices=3, dropout=0.1, emb_dropout=0.2)
+    m.set_dropout_seed(42, step=10)
+    assert m._next_dropout_state() == (0.1, 0.2, 42, 10)
+    assert m._next_dropout_state(emb=False) == (0.1, 0.0, 42, 11)
+    m.eval()
+    assert m._next_dropout_state() == (0.0, 0.0, 0, 0)
+    m.train()
+    assert m._next_dropout_state() == (0.1, 0.2, 42, 12)
+    plain = svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, num_patches=4, num_vertices=3)
+    assert plain._next_dropout_state() == (0.0, 0.0, 0, 0) and plain._drop_step == 0
+    lib = _lib.load()
+    assert lib.svit_set_dropout(m._engine, 1.0, 0.0, 0, 0) != 0 and b"[0, 1)" in lib.svit_last_error()
