@@ -18,11 +18,11 @@ buf = (ctypes.c_longlong * 256)()
 lib.svit_debug_attn_prof(buf, 256)
 v = list(buf); t0 = v[0]
 def rel(i): return v[i] - t0 if v[i] else None
-print("MMA thread: start 0, first operands landed", rel(1), " last MMA issued", rel(2), " dQ stored", rel(3))
+print("MMA thread X: start 0, first operands landed", rel(1), " last MMA issued", rel(2), " dQ stored", rel(3))
+print("compute warp: start", rel(90), "delta loaded", rel(91), "after barrier", rel(92), "S(0) ready", rel(93), "P(0) stored", rel(94))
 for p in range(8):
-    print(f" pair {p}: MMA wait p_full {rel(10+p*4)}->{rel(11+p*4)} wait ds_full {rel(12+p*4)}->{rel(13+p*4)} |"
-          f" P warp: wait s_full {rel(100+p*4)}->{rel(101+p*4)} P written {rel(102+p*4)} |"
-          f" dS warp: wait dp_full {rel(150+p*4)}->{rel(151+p*4)} dS written {rel(152+p*4)}")
-print("per-warp completion times: P written (warps 2..5) | dS written (warps 6..9)")
-for p in range(6):
-    print(f" pair {p}:", [rel(190 + p * 4 + k) for k in range(4)], "|", [rel(220 + p * 4 + k) for k in range(4)])
+    print(f" step {p}: X wait p_full {rel(10+p*4)}->{rel(11+p*4)}  Y wait ds_full {rel(12+p*4)}->{rel(13+p*4)} |"
+          f" compute: top {rel(100+p*4)} waits done {rel(101+p*4)} dS stored {rel(102+p*4)} P stored {rel(103+p*4)}")
+for j in range(1, 4):
+    print(f" copy-out of key block {j-1}: {rel(80+2*j)} -> {rel(81+2*j)}")
+print("tail: last copy-out", rel(95), "->", rel(96), " dq_full", rel(97))

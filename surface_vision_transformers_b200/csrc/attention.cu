@@ -333,8 +333,11 @@ constexpr int BK_SKV = BK_SDO + 3 * TILE_BYTES;  // stage s: K at + s * 2 * BK_K
 constexpr int BK_SP = BK_SKV + 4 * BK_KV_TILE;
 constexpr int BK_SDS = BK_SP + 2 * TILE_BYTES;   // buffer b: keys 0..63 in tile b, keys 64..95 in tile 2 at byte 64 * b of each row
 constexpr int BK_BAR = BK_SDS + 3 * TILE_BYTES;
-constexpr int BK_SMEM = 1024 + BK_BAR + 256;
-constexpr int BK_THREADS = 448;  // MMA warps X and Y, 4 P warps, 8 dS warps (14 warps: 4 per sub-partition -> 128 registers)
+constexpr int BK_DELTA = BK_BAR + 256;          // [3][128] fp32: delta * scale of every query row
+constexpr int BK_SMEM = 1024 + BK_DELTA + 3 * 128 * 4;
+static_assert(BK_SMEM <= 232448, "attn_bwd shared memory");
+constexpr int BK_THREADS = 512;  // warp group 0: MMA warps X and Y (+ 2 idle warps), warp groups 1..3: 12 compute warps
+constexpr int BK_REGS_MMA = 56, BK_REGS_COMPUTE = 152;  // setmaxnreg: 4 * 56 + 12 * 152 = 16 * 128
 constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
@@ -342,9 +345,8 @@ struct AttnBwdArgs {
     CUtensorMap tmDO;   // dout (inner, T, B)   bf16 box 64 x 128
     CUtensorMap tmKV;   // qkv                  bf16 box 64 x 96 : K_j, V_j loads
     CUtensorMap tmDQ;   // dqkv (3*inner, T, B) bf16 box 64 x 128: dQ_i stores
-    __nv_bfloat16* dqkv;  // dK_j / dV_j rows are stored directly
-    const __nv_bfloat16* out;
-    const __nv_bfloat16* dout;
+    CUtensorMap tmO;    // out  (inner, T, B)   bf16 box 64 x 128: O_i loads (delta only)
+    CUtensorMap tmDKV;  // dqkv                 bf16 box 64 x 96 : dK_j, dV_j stores
     const float* lse;
     int B, H, T;
     float scale, scale_log2e;
@@ -361,41 +363,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
     return bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
            bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
-}
-
-// Key block j is complete: one of its accumulators (dK_j or dV_j) -> bf16 -> 64 bytes per thread straight to global
-// memory.  TMEM lane = key index inside the block; each (quadrant, half) warp converts 32 of the 64 head dimensions.
-// Called where few registers are live (top of a P-warp iteration, end of a dS-warp iteration): spills inside the
-// hot loops are fatal (local-memory traffic crawls while the tensor core streams operands from shared memory).
-template <int PARTS>  // PARTS x 16 accumulator columns per thread
-__device__ __forceinline__ void bwd_store_acc(uint32_t t_acc, __nv_bfloat16* dst_row, bool key_warp, bool row_ok, uint64_t* full_bar,
-                                           uint32_t full_parity, uint64_t* free_bar) {
-    mbar_wait(full_bar, full_parity);
-    tc_fence_after();
-#pragma unroll 1
-    for (int part = 0; part < PARTS; ++part) {
-        uint32_t o[16];
-        if (key_warp) {
-            tmem_ld_32x16(t_acc + part * 16, o);
-            tmem_ld_wait();
-        }
-        if (part == PARTS - 1) {
-            tc_fence_before();
-            mbar_arrive_warp(free_bar);
-        }
-        if (key_warp && row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(dst_row + part * 16);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                uint4 v;
-                v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
-                v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
-                v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
-                v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
-                dst[g] = v;
-            }
-        }
-    }
 }
 
 __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs args) {
@@ -438,20 +405,22 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         tma_prefetch_desc(&args.tmDO);
         tma_prefetch_desc(&args.tmKV);
         tma_prefetch_desc(&args.tmDQ);
+        tma_prefetch_desc(&args.tmO);
+        tma_prefetch_desc(&args.tmDKV);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&kv_full[s], 1);
-            mbar_init(&ds_full[s], 8);
+            mbar_init(&ds_full[s], 12);
             mbar_init(&ds_free[s], 1);
         }
         for (int i = 0; i < 3; ++i) mbar_init(&q_full[i], 1);
         mbar_init(s_full, 1);
-        mbar_init(s_free, 4);
+        mbar_init(s_free, 12);
         mbar_init(dp_full, 1);
-        mbar_init(dp_free, 8);
-        mbar_init(p_full, 4);
-        mbar_init(p_free, 9);
+        mbar_init(dp_free, 12);
+        mbar_init(p_full, 12);
+        mbar_init(p_free, 1);
         mbar_init(dv_full, 1);
-        mbar_init(dv_free, 4);
+        mbar_init(dv_free, 8);
         mbar_init(dk_full, 1);
         mbar_init(dk_free, 8);
         mbar_init(dq_full, 1);
@@ -465,6 +434,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the issuing warps need few registers, the compute warps many: move them (per warp group of 4 warps)
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BK_REGS_MMA));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK_REGS_COMPUTE));
 
     auto load_kv = [&](int j) {  // K_j, V_j -> stage j & 1 (called by one thread)
         const int s = j & 1;
@@ -478,9 +450,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
         if (elect_one()) {
             auto load_q = [&](int i) {
-                mbar_expect_tx(&q_full[i], 2 * TILE_BYTES);
+                mbar_expect_tx(&q_full[i], 3 * TILE_BYTES);
                 tma_load_3d(sQ + i * TILE_BYTES, &args.tmQ, &q_full[i], h * 64, i * 128, b);
                 tma_load_3d(sdO + i * TILE_BYTES, &args.tmDO, &q_full[i], h * 64, i * 128, b);
+                tma_load_3d(sdS + i * TILE_BYTES, &args.tmO, &q_full[i], h * 64, i * 128, b);  // O_i: only for delta, before any dS
             };
             load_q(0);
             load_kv(0);
@@ -573,99 +546,226 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             if (!X) umma_commit(dq_full);
             if (X) PROF(2);
         }
-    } else if (warp < 6) {
-        // ================================ P warps ================================
-        // 4 warps: warp q owns TMEM lane quadrant q, one query row x 96 key columns per thread
+    } else if (warp >= 4) {
+        // ================================ compute warps ================================
+        // 12 warps: warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and the 32 key columns
+        // [32 slab, 32 slab + 32) of every 96-key block -- for the probabilities AND for dS, so P stays in registers
+        // between the two phases of a pair.
         const int q = warp & 3;
+        const int slab = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int c0 = slab * 32;
         const float c = args.scale_log2e;
         const int sw = row & 7;
-        const bool prof_thread = threadIdx.x == 64;
-        float lse2[3];
+        const bool prof_thread = threadIdx.x == 128;
+        // ---- prologue: delta * scale = rowsum(dO * O) * scale of query block `slab` -> smem, then everybody reads its rows.
+        // O_i arrives by TMA in the (still unused) dS tiles next to dO_i: per-thread global loads of these rows took
+        // 11,000 clocks here, the TMA tiles land in about 1,500.
+        float* sdl = reinterpret_cast<float*>(smem + BK_DELTA);
+        if (prof_thread) PROF(90);
+        if (slab < nqb) {
+            mbar_wait(&q_full[slab], 0);
+            const uint8_t* orow = sdS + slab * TILE_BYTES + row * 128;
+            const uint8_t* drow = sdO + slab * TILE_BYTES + row * 128;
+            float acc = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                acc += dot8_bf16(*reinterpret_cast<const uint4*>(orow + ((g ^ sw) << 4)), *reinterpret_cast<const uint4*>(drow + ((g ^ sw) << 4)));
+            sdl[slab * 128 + row] = acc * args.scale;  // rows past T were zero-filled by the TMA
+        }
+        float lse2[3], sdelta[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int t = i * 128 + row;
             lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : 0.0f;
         }
-        auto store_dv = [&](int j) {  // dV_j: TMEM lane = key row, 64 head dimensions per thread
-            const int kvp = min(BK_KEYS, T - j * BK_KEYS);
-            bwd_store_acc<4>(t_row + BK_T_DV,
-                             args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner + 2 * inner + h * 64,
-                             q * 32 < kvp, row < kvp, dv_full, j & 1, dv_free);
-        };
-        int p = 0;
-        for (int j = 0; j < nkb; ++j) {
-            const int kvalid = min(BK_KEYS, T - j * BK_KEYS);
+        if (prof_thread) PROF(91);
+        named_bar_sync(1, 384);
+        if (prof_thread) PROF(92);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sdelta[i] = sdl[i * 128 + row];
+
+        // Key block jb is complete: dK | dV (TMEM columns [192, 320), lane = key, eight 16-column parts; three / three / two
+        // per slab) -> bf16 -> the block's own K / V stage (every MMA that read it has retired) -> two TMA stores; then
+        // the stage is refilled with block jb+2.  Per-thread global stores from here crawl (32 rows per request, and the
+        // LSU starves while the tensor core streams operands from shared memory).  A small rolled loop on purpose:
+        // unrolled, its register bursts made ptxas spill inside the software-pipelined loop below.
+        auto store_kv = [&](int jb) {
+            const bool key_warp = q * 32 < min(BK_KEYS, T - jb * BK_KEYS);
+            uint8_t* stage = sKV + (jb & 1) * 2 * BK_KV_TILE;
+            if (slab < 2) mbar_wait(dk_full, jb & 1);
+            if (slab > 0) mbar_wait(dv_full, jb & 1);
+            tc_fence_after();
+            if (key_warp) {
 #pragma unroll 1
-            for (int i = 0; i < nqb; ++i, ++p) {
-                const bool qvalid = i * 128 + row < T;
-                const bool warp_any = i * 128 + q * 32 < T;  // at least one real query row in this warp
-                const float l2 = i == 0 ? lse2[0] : (i == 1 ? lse2[1] : lse2[2]);
-                // dV_{j-1} became final when c(j-1, last) retired: copy it out first so that c(j, 0) can start at once
-                if (i == 0 && j > 0) store_dv(j - 1);
-                uint32_t pk[48];  // P of this thread's 96 columns, packed bf16
-                if (prof_thread && p < 8) PROF(100 + p * 4);
-                mbar_wait(s_full, p & 1);
-                if (prof_thread && p < 8) PROF(101 + p * 4);
-                tc_fence_after();
-                {
-                    // 16-column chunks; the TMEM load of chunk ch+1 is in flight while chunk ch is exponentiated
-                    const int nch = warp_any ? (kvalid + 15) >> 4 : 0;  // warp-uniform
-                    const bool full = qvalid && kvalid == BK_KEYS;
-                    uint32_t ca[16], cb[16];
-                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_S, ca);
+                for (int a = slab * 3; a < min(8, slab * 3 + 3); ++a) {
+                    uint32_t o[16];
+                    tmem_ld_32x16(t_row + BK_T_DK + a * 16, o);
+                    tmem_ld_wait();
+                    uint8_t* trow = stage + (a >> 2) * BK_KV_TILE + row * 128;
 #pragma unroll
-                    for (int ch = 0; ch < 6; ++ch) {
-                        uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
-                        uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
-                        if (ch < nch) {
-                            tmem_ld_wait();
-                            if (ch + 1 < nch) {
-                                tmem_ld_32x16(t_row + BK_T_S + (ch + 1) * 16, nxt);
-                            } else {
-                                tc_fence_before();
-                                mbar_arrive_warp(s_free);
-                            }
-#pragma unroll
-                            for (int e = 0; e < 16; e += 2) {
-                                float a0 = ex2_approx(fmaf(__uint_as_float(cur[e]), c, -l2));
-                                float a1 = ex2_approx(fmaf(__uint_as_float(cur[e + 1]), c, -l2));
-                                if (!full) {
-                                    if (!qvalid || ch * 16 + e >= kvalid) a0 = 0.0f;
-                                    if (!qvalid || ch * 16 + e + 1 >= kvalid) a1 = 0.0f;
-                                }
-                                pk[ch * 8 + e / 2] = pack_bf16(a0, a1);
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) pk[ch * 8 + e] = 0u;
-                        }
-                    }
-                    if (nch == 0) {
-                        tc_fence_before();
-                        mbar_arrive_warp(s_free);
+                    for (int g = 0; g < 2; ++g) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+                        v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                        v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                        v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                        *reinterpret_cast<uint4*>(trow + ((((a & 3) * 2 + g) ^ sw) << 4)) = v;
                     }
                 }
-                if (p > 0) mbar_wait(p_free, (p - 1) & 1);  // c(p-1) retired and the dS warps re-read P(p-1)
-                uint8_t* prow = sP + row * 128;
-#pragma unroll
-                for (int g = 0; g < 12; ++g) {
-                    const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(prow + (g >> 3) * TILE_BYTES + (((g & 7) ^ sw) << 4)) = o;
-                }
-                fence_proxy_async_smem();
-                mbar_arrive_warp(p_full);
-                if (prof_thread && p < 8) PROF(102 + p * 4);
             }
+            tc_fence_before();
+            if (slab < 2) mbar_arrive_warp(dk_free);
+            if (slab > 0) mbar_arrive_warp(dv_free);
+            fence_proxy_async_smem();
+            named_bar_sync(2, 384);
+            if (warp == 4 && lane == 0) {
+                tma_store_3d(&args.tmDKV, stage, inner + h * 64, jb * BK_KEYS, b);
+                tma_store_3d(&args.tmDKV, stage + BK_KV_TILE, 2 * inner + h * 64, jb * BK_KEYS, b);
+                tma_store_commit();
+                if (jb + 2 < nkb) {
+                    tma_store_wait_read<0>();
+                    load_kv(jb + 2);
+                }
+            }
+        };
+
+        // Software pipeline: step p computes dS(p) and P(p+1).  S(p+1) and dP(p) were both issued at the beginning of
+        // step p-1 (when their TMEM buffers were read out), so neither wait below ever sees the tensor pipe's latency,
+        // and the S load is in flight while dS is computed and written.
+        // Both phases compute all 32 columns unconditionally; slabs that contain rows past T or keys past the block's
+        // end (a few warps of the last query / key block) then clear those entries with integer masks, which also
+        // kills whatever stale TMEM contents (columns beyond the MMA's N extent) may have produced.
+        uint32_t pk[16];  // P(p), then dS(p), of this thread's 32 columns, packed bf16 (exact zeros where masked)
+        auto clear_unreal = [&](int jj, int ii) {
+            const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns (may be <= 0 or >= 32)
+            const bool qv = ii * 128 + row < T;
+            if (nv >= 32 && ii * 128 + q * 32 + 31 < T) return;   // warp-uniform: nothing to mask
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t m = !qv ? 0u : (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
+                pk[k] &= m;
+            }
+        };
+        auto p_math = [&](const uint32_t (&sv)[32], int ii) {
+            const float l2 = ii == 0 ? lse2[0] : (ii == 1 ? lse2[1] : lse2[2]);
+#pragma unroll
+            for (int e = 0; e < 32; e += 2)
+                pk[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
+                                      ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
+        };
+        auto p_store = [&]() {
+            uint8_t* prow = sP + row * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int gc = slab * 4 + g;
+                *reinterpret_cast<uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4)) =
+                    make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive_warp(p_full);
+        };
+        auto ds_math = [&](const uint32_t (&dv)[32], int ii) {
+            const float sd = ii == 0 ? sdelta[0] : (ii == 1 ? sdelta[1] : sdelta[2]);
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                const uint32_t pa = pk[e / 2];
+                pk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(dv[e]), args.scale, -sd),
+                                      bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
+            }
+        };
+        auto ds_store = [&](int p) {
+            const uint32_t pp = p & 1;
+            if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired: this dS buffer is free
+            uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;  // keys 0..63
+            uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;   // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int gc = slab * 4 + g;
+                const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                if (gc < 8) *reinterpret_cast<uint4*>(dsrow0 + ((gc ^ sw) << 4)) = o;
+                else *reinterpret_cast<uint4*>(dsrow1 + ((((gc - 8) + 4 * pp) ^ sw) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive_warp(&ds_full[pp]);
+        };
+
+        // ---- step -1: P(0)
+        {
+            uint32_t sv[32];
+            mbar_wait(s_full, 0);
+            if (prof_thread) PROF(93);
+            tc_fence_after();
+            tmem_ld_32x32(t_row + BK_T_S + c0, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_warp(s_free);
+            p_math(sv, 0);
+            clear_unreal(0, 0);
+            p_store();
+            if (prof_thread) PROF(94);
         }
-        store_dv(nkb - 1);
-        // ---- epilogue: dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store ----
-        mbar_wait(dq_full, 0);
-        tc_fence_after();
+        // ---- steps 0 .. total-2: dS(p) and P(p+1);  pair p = (j, i), pair p+1 = (jn, in)
+        int j = 0, i = 0, jn = nqb > 1 ? 0 : 1, in = nqb > 1 ? 1 : 0;
 #pragma unroll 1
-        for (int i = 0; i < nqb; ++i) {
-            if (i * 128 + q * 32 >= T) continue;  // rows past T are clipped by the store anyway
+        for (int p = 0; p + 1 < total; ++p) {
+            // key block j-1 is final (both accumulators retired during the previous step): copy dK / dV out, refill its stage
+            if (i == 0 && j > 0) {
+                if (prof_thread) PROF(80 + j * 2);
+                store_kv(j - 1);
+                if (prof_thread) PROF(81 + j * 2);
+            }
+            uint32_t dv[32], sv[32];
+            if (prof_thread && p < 8) PROF(100 + p * 4);
+            mbar_wait(dp_full, p & 1);
+            mbar_wait(s_full, (p + 1) & 1);
+            if (prof_thread && p < 8) PROF(101 + p * 4);
+            tc_fence_after();
+            tmem_ld_32x32(t_row + BK_T_DP + c0, dv);
+            tmem_ld_wait();
+            tmem_ld_32x32(t_row + BK_T_S + c0, sv);   // lands while dS is computed and written
+            tc_fence_before();
+            mbar_arrive_warp(dp_free);
+            ds_math(dv, i);
+            clear_unreal(j, i);
+            ds_store(p);
+            if (prof_thread && p < 8) PROF(102 + p * 4);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_warp(s_free);
+            p_math(sv, in);
+            clear_unreal(jn, in);
+            mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
+            p_store();
+            if (prof_thread && p < 8) PROF(103 + p * 4);
+            j = jn, i = in;
+            if (++in == nqb) in = 0, ++jn;
+        }
+        // ---- last step: dS(total-1)
+        {
+            const int p = total - 1;
+            if (i == 0 && j > 0) store_kv(j - 1);
+            uint32_t dv[32];
+            mbar_wait(dp_full, p & 1);
+            tc_fence_after();
+            tmem_ld_32x32(t_row + BK_T_DP + c0, dv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_warp(dp_free);
+            ds_math(dv, i);
+            clear_unreal(j, i);
+            ds_store(p);
+        }
+        if (prof_thread) PROF(95);
+        store_kv(nkb - 1);
+        if (prof_thread) PROF(96);
+        // ---- epilogue: slab i converts dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store ----
+        mbar_wait(dq_full, 0);
+        if (prof_thread) PROF(97);
+        tc_fence_after();
+        if (slab < nqb && slab * 128 + q * 32 < T) {  // rows past T are clipped by the store anyway
+            const int i = slab;
             uint8_t* orow = (i < 2 ? sP + i * TILE_BYTES : sdS) + row * 128;
 #pragma unroll 1
             for (int part = 0; part < 2; ++part) {
@@ -685,128 +785,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (warp == 2 && lane == 0) {
+        named_bar_sync(1, 384);
+        if (warp == 4 && lane == 0) {
             for (int i = 0; i < nqb; ++i)
                 tma_store_3d(&args.tmDQ, i < 2 ? sP + i * TILE_BYTES : sdS, h * 64, i * 128, b);
             tma_store_commit();
             tma_store_wait_all<0>();
             PROF(3);
         }
-    } else {
-        // ================================ dS warps ================================
-        // 8 warps with the same (q, half) split as the P warps
-        const int q = warp & 3;
-        const int half = (warp - 6) >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int sw = row & 7;
-        const bool prof_thread = threadIdx.x == 192;
-        // delta * scale of this thread's query rows: rowsum(dO * O) over the 64 head dimensions
-        float sdelta[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int t = i * 128 + row;
-            float acc = 0.0f;
-            if (i < nqb && t < T) {
-                const size_t off = (static_cast<size_t>(b) * T + t) * inner + h * 64;
-                const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
-                const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) acc += dot8_bf16(po[g], pd[g]);
-            }
-            sdelta[i] = acc * args.scale;
-        }
-        auto store_dk = [&](int j) {
-            const int kvp = min(BK_KEYS, T - j * BK_KEYS);
-            bwd_store_acc<2>(t_row + BK_T_DK + half * 32,
-                             args.dqkv + (static_cast<size_t>(b) * T + j * BK_KEYS + row) * 3 * inner + inner + h * 64 + half * 32,
-                             q * 32 < kvp, row < kvp, dk_full, j & 1, dk_free);
-        };
-        int p = 0;
-        for (int j = 0; j < nkb; ++j) {
-            const int kvalid = min(BK_KEYS, T - j * BK_KEYS) - half * 48;
-#pragma unroll 1
-            for (int i = 0; i < nqb; ++i, ++p) {
-                const bool warp_any = i * 128 + q * 32 < T;
-                const float sd = i == 0 ? sdelta[0] : (i == 1 ? sdelta[1] : sdelta[2]);
-                const uint32_t pp = p & 1;
-                // ---- P(p): smem -> registers right away, so the P warps get their tile back early ----
-                uint32_t pk[24];  // packed bf16 P, overwritten in place by dS
-                if (prof_thread && p < 8) PROF(150 + p * 4);
-                mbar_wait(p_full, pp);
-                {
-                    const uint8_t* prow = sP + row * 128;  // (rows of all-invalid warps hold the zeros the P warps wrote)
-#pragma unroll
-                    for (int g = 0; g < 6; ++g) {
-                        const int gc = half * 6 + g;
-                        const uint4 v = *reinterpret_cast<const uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4));
-                        pk[g * 4] = v.x;
-                        pk[g * 4 + 1] = v.y;
-                        pk[g * 4 + 2] = v.z;
-                        pk[g * 4 + 3] = v.w;
-                    }
-                }
-                mbar_arrive_warp(p_free);
-                // ---- dS = P * (dP * scale - delta * scale), masked entries of P are exact zeros ----
-                mbar_wait(dp_full, pp);
-                if (prof_thread && p < 8) PROF(151 + p * 4);
-                tc_fence_after();
-                if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired long ago: this dS buffer is free
-                uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;       // keys 0..63
-                uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;        // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
-                {
-                    // chunks past nch hold P = 0 -> the packed zeros already are the right dS
-                    const int nch = (warp_any && kvalid > 0) ? min(3, (kvalid + 15) >> 4) : 0;
-                    uint32_t ca[16], cb[16];
-                    if (nch > 0) tmem_ld_32x16(t_row + BK_T_DP + half * 48, ca);
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        uint32_t (&cur)[16] = (ch & 1) ? cb : ca;
-                        uint32_t (&nxt)[16] = (ch & 1) ? ca : cb;
-                        uint32_t ds[8];
-                        if (ch < nch) {
-                            tmem_ld_wait();
-                            if (ch + 1 < nch) {
-                                tmem_ld_32x16(t_row + BK_T_DP + half * 48 + (ch + 1) * 16, nxt);
-                            } else {
-                                tc_fence_before();
-                                mbar_arrive_warp(dp_free);
-                            }
-#pragma unroll
-                            for (int e = 0; e < 16; e += 2) {
-                                const uint32_t pa = pk[ch * 8 + e / 2];
-                                ds[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(cur[e]), args.scale, -sd),
-                                                      bf16_hi(pa) * fmaf(__uint_as_float(cur[e + 1]), args.scale, -sd));
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) ds[e] = 0u;
-                        }
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int gc = half * 6 + ch * 2 + g;
-                            const uint4 o = make_uint4(ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]);
-                            if (gc < 8) *reinterpret_cast<uint4*>(dsrow0 + ((gc ^ sw) << 4)) = o;
-                            else *reinterpret_cast<uint4*>(dsrow1 + ((((gc - 8) + 4 * pp) ^ sw) << 4)) = o;
-                        }
-                    }
-                    if (nch == 0) {
-                        tc_fence_before();
-                        mbar_arrive_warp(dp_free);
-                    }
-                }
-                fence_proxy_async_smem();
-                mbar_arrive_warp(&ds_full[pp]);
-                if (prof_thread && p < 8) PROF(152 + p * 4);
-                if (i == 0 && j > 0) {
-                    store_dk(j - 1);  // by now d(j-1, last) has long retired
-                    // every MMA of block j-1 has retired (dk_full; X's are causally earlier): refill its K/V stage
-                    if (warp == 6 && lane == 0 && j + 1 < nkb) load_kv(j + 1);
-                }
-            }
-        }
-        store_dk(nkb - 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -890,13 +876,12 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     rc |= make_tmap_3d(&a.tmDO, d.dout, TmapDtype::BF16, inner, d.T, d.B, p_o, (uint64_t)d.T * p_o, 64, 128);
     rc |= make_tmap_3d(&a.tmKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_qkv, (uint64_t)d.T * p_qkv, 64, BK_KEYS);
     rc |= make_tmap_3d(&a.tmDQ, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_qkv, (uint64_t)d.T * p_qkv, 64, 128);
+    rc |= make_tmap_3d(&a.tmO, d.out, TmapDtype::BF16, inner, d.T, d.B, p_o, (uint64_t)d.T * p_o, 64, 128);
+    rc |= make_tmap_3d(&a.tmDKV, d.dqkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_qkv, (uint64_t)d.T * p_qkv, 64, BK_KEYS);
     if (rc) {
         set_error("attn_bwd: tensor map creation failed: %s", tmap_last_error());
         return -3;
     }
-    a.out = reinterpret_cast<const __nv_bfloat16*>(d.out);
-    a.dout = reinterpret_cast<const __nv_bfloat16*>(d.dout);
-    a.dqkv = reinterpret_cast<__nv_bfloat16*>(d.dqkv);
     a.lse = d.lse;
     a.B = d.B;
     a.H = d.H;

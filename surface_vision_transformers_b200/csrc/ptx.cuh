@@ -85,9 +85,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         __nanosleep(SVIT_SPIN_SLEEP_NS);
 #endif
         if ((++spins & 63) == 0 && clock64() - t0 > SVIT_SPIN_LIMIT) {
+            // a printf here costs every inlined wait a call site (argument set-up, caller-saved registers): the kernels
+            // that poll from register-heavy loops spilled because of it.  Build with -DSVIT_SPIN_DEBUG to get the message.
+#ifdef SVIT_SPIN_DEBUG
             printf("svit: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, smem_u32(bar), parity);
-            __trap();
+#endif
+            __trap();  // the host sees a failed launch instead of a hang
         }
     }
 }
