@@ -624,10 +624,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 tma_store_3d(&args.tmDKV, stage, inner + h * 64, jb * BK_KEYS, b);
                 tma_store_3d(&args.tmDKV, stage + BK_KV_TILE, 2 * inner + h * 64, jb * BK_KEYS, b);
                 tma_store_commit();
-                if (jb + 2 < nkb) {
-                    tma_store_wait_read<0>();
-                    load_kv(jb + 2);
-                }
+            }
+        };
+        // one step later the stores have long read the stage: refill it with block jb+2 (waiting right away would stall
+        // this warp, and with it every hand-off of the step, for the ~1,500 clocks the TMA needs to drain 24 KB)
+        auto reload_kv = [&](int jb) {
+            if (warp == 4 && lane == 0 && jb + 2 < nkb) {
+                tma_store_wait_read<0>();
+                load_kv(jb + 2);
             }
         };
 
@@ -638,7 +642,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         // end (a few warps of the last query / key block) then clear those entries with integer masks, which also
         // kills whatever stale TMEM contents (columns beyond the MMA's N extent) may have produced.
         uint32_t pk[16];  // P(p), then dS(p), of this thread's 32 columns, packed bf16 (exact zeros where masked)
-        auto clear_unreal = [&](int jj, int ii) {
+        uint32_t pn[16];  // P(p+1) while dS(p) is still in pk
+        auto clear_unreal = [&](uint32_t (&pk)[16], int jj, int ii) {
             const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns (may be <= 0 or >= 32)
             const bool qv = ii * 128 + row < T;
             if (nv >= 32 && ii * 128 + q * 32 + 31 < T) return;   // warp-uniform: nothing to mask
@@ -655,7 +660,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 pk[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
                                       ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
         };
-        auto p_store = [&]() {
+        auto p_store = [&](const uint32_t (&pk)[16]) {
             uint8_t* prow = sP + row * 128;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -702,8 +707,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_warp(s_free);
             p_math(sv, 0);
-            clear_unreal(0, 0);
-            p_store();
+            clear_unreal(pk, 0, 0);
+            p_store(pk);
             if (prof_thread) PROF(94);
         }
         // ---- steps 0 .. total-2: dS(p) and P(p+1);  pair p = (j, i), pair p+1 = (jn, in)
@@ -723,22 +728,34 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             if (prof_thread && p < 8) PROF(101 + p * 4);
             tc_fence_after();
             tmem_ld_32x32(t_row + BK_T_DP + c0, dv);
+            tmem_ld_32x32(t_row + BK_T_S + c0, sv);
             tmem_ld_wait();
-            tmem_ld_32x32(t_row + BK_T_S + c0, sv);   // lands while dS is computed and written
             tc_fence_before();
             mbar_arrive_warp(dp_free);
-            ds_math(dv, i);
-            clear_unreal(j, i);
+            mbar_arrive_warp(s_free);
+            // dS(p) (FMA pipe) and P(p+1) (MUFU) element by element in one instruction stream, so that the two pipes overlap
+            {
+                const float sd = i == 0 ? sdelta[0] : (i == 1 ? sdelta[1] : sdelta[2]);
+                const float l2 = in == 0 ? lse2[0] : (in == 1 ? lse2[1] : lse2[2]);
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const uint32_t pa = pk[e / 2];
+                    pn[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
+                                          ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
+                    pk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(dv[e]), args.scale, -sd),
+                                          bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
+                }
+            }
+            clear_unreal(pk, j, i);
             ds_store(p);
             if (prof_thread && p < 8) PROF(102 + p * 4);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive_warp(s_free);
-            p_math(sv, in);
-            clear_unreal(jn, in);
+            clear_unreal(pn, jn, in);
             mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
-            p_store();
+            p_store(pn);
             if (prof_thread && p < 8) PROF(103 + p * 4);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pk[k] = pn[k];
+            if (i == 0 && j > 0) reload_kv(j - 1);
             j = jn, i = in;
             if (++in == nqb) in = 0, ++jn;
         }
@@ -754,7 +771,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_warp(dp_free);
             ds_math(dv, i);
-            clear_unreal(j, i);
+            clear_unreal(pk, j, i);
             ds_store(p);
         }
         if (prof_thread) PROF(95);
