@@ -25,4 +25,7 @@ for p in range(8):
           f" compute: top {rel(100+p*4)} waits done {rel(101+p*4)} dS stored {rel(102+p*4)} P stored {rel(103+p*4)}")
 for j in range(1, 4):
     print(f" copy-out of key block {j-1}: {rel(80+2*j)} -> {rel(81+2*j)}")
+print(" inside copy-out 0: accumulators final", rel(70), "staged", rel(71), "after barrier", rel(72))
 print("tail: last copy-out", rel(95), "->", rel(96), " dq_full", rel(97))
+for p in (1, 2):
+    print(f"step {p}: dS stored per compute warp (warps 4..15):", [rel(200 + (p - 1) * 16 + w) for w in range(4, 16)])

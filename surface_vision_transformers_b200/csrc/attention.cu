@@ -306,25 +306,30 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 // Keys are processed in blocks of 96 (j, outer loop, K_j / V_j double-buffered by TMA), queries in blocks of 128
 // (i, inner loop, all Q_i / dO_i resident in shared memory).  With 96-column score tiles everything fits in TMEM:
 //   S [0,96)  dP [96,192)  dK_j [192,256)  dV_j [256,320)  dQ_0..2 [320,512)
-// so dQ accumulates on chip across the key blocks (the former kernel red.add-ed fp32 partials into a global
-// scratch buffer and converted them afterwards).  delta = rowsum(dO * O) is computed in the prologue.
+// so dQ accumulates on chip across the key blocks (no atomics, no fp32 scratch, no separate delta / convert kernels).
 //
-//   tensor core (two issuing warps)       P warps (4, one row x 96 keys per thread)   dS warps (8, one row x 48 keys per thread)
-//   a(p): S  = Q_i K_j^T                  P  = exp2(S*scale*log2e - lse*log2e)     dS = P * (dP*scale - delta*scale)
-//   b(p): dP = dO_i V_j^T                    -> bf16 smem tile sP                     -> bf16 smem tile sdS
-//   c(p): dV_j += P^T dO_i                                                         after the last i of block j:
-//   d(p): dK_j += dS^T Q_i ; dQ_i += dS K_j                                           dK_j, dV_j -> bf16 -> TMA store
-// The two warp groups work on different pairs at the same time (the exponentials of pair p+1 overlap the dS
-// arithmetic of pair p), and the MMAs of both neighbours run underneath.  Two MMA-issuing warps keep the two
-// chains independent: warp X issues a(p+1) | c(p), warp Y issues b(p+1) | d(p).  dK_j / dV_j leave through the dS
-// warps at the start of the next key block (plain 128-byte row stores, nothing to wait for); the same point in
-// time is when block j-1's K/V stage is provably free, so a dS-warp thread also issues the TMA load of block j+1
-// (there is no separate producer warp: X issues the initial loads).
-// The dS tile is double-buffered and the dS warps pull P into registers as soon as it is written, so neither the
-// "d(p) retired -> next dS" nor the "P consumed -> next P" hand-back sits on the critical path.
+//   tensor core (two issuing warps X, Y)     12 compute warps: warp (q, slab) = TMEM lane quadrant q (one query row per
+//   a(p): S  = Q_i K_j^T          (X)         thread) x key columns [32 slab, 32 slab + 32) of the 96-key block
+//   b(p): dP = dO_i V_j^T         (Y)           P  = exp2(S*scale*log2e - lse*log2e)    -> bf16 smem tile sP
+//   c(p): dV_j += P^T dO_i        (X)           dS = P * (dP*scale - delta*scale)       -> bf16 smem tile sdS
+//   d(p): dK_j += dS^T Q_i ; dQ_i += dS K_j (Y)
+// The compute warps are software-pipelined: step p computes dS(p) AND P(p+1) in one merged instruction stream (the
+// exponentials run on the MUFU while the dS arithmetic runs on the FMA pipe; P(p+1) stays in registers for dS(p+1), it
+// is never read back from shared memory).  S(p+1) and dP(p) were issued at the start of step p-1, as soon as their TMEM
+// buffers had been read out, so a step never waits for the tensor pipe; c and d of a step run underneath the next one.
+// Row masking costs nothing (lse = +inf for rows past T), column masking only touches the one slab that straddles T.
+// What the profile (SVIT_ATTN_DEBUG=4, scripts/prof_attn_bwd.py) taught, in clocks per CTA at T = 321 (63 k before):
+//   * delta = rowsum(dO * O): per-thread global loads of the O / dO rows took 11 k; O_i now arrives by TMA in the not yet
+//     used dS tiles and delta is read from shared memory (1.5 k);
+//   * dK_j / dV_j leave through the block's own K / V stage and two TMA stores (the stage is refilled one step later):
+//     per-thread row stores took 3 k per key block, and the LSU starves while the tensor core streams smem operands;
+//   * 4 P warps + 8 dS warps were unbalanced (the P warps needed 3.1 k per pair) and re-read P from shared memory;
+//   * registers: the two issuing warps give theirs up (setmaxnreg 56 / 152), the timeout printf of mbar_wait is gone
+//     (every inlined wait paid for a call site), the copy-out is a small rolled loop -- spills inside the pipelined
+//     loop are fatal (local-memory traffic crawls under the tensor core's shared-memory streaming).
 // A [128 x 96] bf16 tile occupies one full 64-column swizzled tile plus half of a second one; the two dS buffers
 // share that second tile (buffer 1 lives in its columns 32..63, i.e. 64 bytes into every row).
-// smem: sQ[3] sdO[3] (16K each) | sK,sV x2 stages (12K each) | sP 32K | sdS 16K + 16K + 16K shared | barriers (~225 KB)
+// smem: sQ[3] sdO[3] (16K each) | sK,sV x2 stages (12K each) | sP 32K | sdS 16K + 16K + 16K shared | barriers, delta (~227 KB)
 constexpr int BK_KEYS = 96;
 constexpr int BK_KV_TILE = BK_KEYS * 128;  // [96 keys x 64 bf16] swizzled tile
 constexpr int BK_SQ = 0;
@@ -376,19 +381,19 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BK_BAR);
     uint64_t* q_full = bars + 0;     // [3] Q_i and dO_i landed (once per CTA)
     uint64_t* kv_full = bars + 4;    // [2]
-    uint64_t* s_full = bars + 8;     // S in TMEM                      (MMA -> P warps)
-    uint64_t* s_free = bars + 9;     // S copied to registers          (P warps -> MMA)
-    uint64_t* dp_full = bars + 10;   // dP in TMEM                     (MMA -> dS warps)
-    uint64_t* dp_free = bars + 11;   // dP copied to registers         (dS warps -> MMA)
-    uint64_t* p_full = bars + 12;    // P tile written                 (P warps -> MMA, dS warps)
-    uint64_t* p_free = bars + 13;    // c(p) retired and P re-read     (MMA + dS warps -> P warps)
-    uint64_t* ds_full = bars + 14;   // [2] dS tile p & 1 written      (dS warps -> MMA)
-    uint64_t* ds_free = bars + 16;   // [2] d(p) retired               (MMA -> dS warps)
-    uint64_t* dv_full = bars + 18;   // dV_j final (c(j, last) retired)  (MMA X -> P warps)
-    uint64_t* dv_free = bars + 19;   // dV_j copied to registers         (P warps -> MMA X)
-    uint64_t* dk_full = bars + 20;   // dK_j final (d(j, last) retired)  (MMA Y -> dS warps)
-    uint64_t* dk_free = bars + 21;   // dK_j copied to registers         (dS warps -> MMA Y)
-    uint64_t* dq_full = bars + 22;   // every MMA of the CTA retired     (MMA -> P warps)
+    uint64_t* s_full = bars + 8;     // S in TMEM                      (MMA -> compute warps)
+    uint64_t* s_free = bars + 9;     // S copied to registers          (compute warps -> MMA)
+    uint64_t* dp_full = bars + 10;   // dP in TMEM                     (MMA -> compute warps)
+    uint64_t* dp_free = bars + 11;   // dP copied to registers         (compute warps -> MMA)
+    uint64_t* p_full = bars + 12;    // P tile written                 (compute warps -> MMA)
+    uint64_t* p_free = bars + 13;    // c(p) retired                   (MMA X -> compute warps)
+    uint64_t* ds_full = bars + 14;   // [2] dS tile p & 1 written      (compute warps -> MMA)
+    uint64_t* ds_free = bars + 16;   // [2] d(p) retired               (MMA -> compute warps)
+    uint64_t* dv_full = bars + 18;   // dV_j final (c(j, last) retired)  (MMA X -> compute warps)
+    uint64_t* dv_free = bars + 19;   // dV_j copied to registers         (compute warps -> MMA X)
+    uint64_t* dk_full = bars + 20;   // dK_j final (d(j, last) retired)  (MMA Y -> compute warps)
+    uint64_t* dk_free = bars + 21;   // dK_j copied to registers         (compute warps -> MMA Y)
+    uint64_t* dq_full = bars + 22;   // every MMA of the CTA retired     (MMA -> compute warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
     const int warp = threadIdx.x >> 5;
@@ -574,11 +579,13 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 acc += dot8_bf16(*reinterpret_cast<const uint4*>(orow + ((g ^ sw) << 4)), *reinterpret_cast<const uint4*>(drow + ((g ^ sw) << 4)));
             sdl[slab * 128 + row] = acc * args.scale;  // rows past T were zero-filled by the TMA
         }
+        // Query rows past T: lse = +inf makes their probabilities exact zeros (S = 0 there: the TMA zero-fills Q), and with
+        // P = 0, dP = 0 (dO zero-filled) and delta = 0 their dS is an exact zero too -- no masking needed for rows.
         float lse2[3], sdelta[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int t = i * 128 + row;
-            lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : 0.0f;
+            lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : __int_as_float(0x7f800000);
         }
         if (prof_thread) PROF(91);
         named_bar_sync(1, 384);
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             uint8_t* stage = sKV + (jb & 1) * 2 * BK_KV_TILE;
             if (slab < 2) mbar_wait(dk_full, jb & 1);
             if (slab > 0) mbar_wait(dv_full, jb & 1);
+            if (prof_thread && jb == 0) PROF(70);
             tc_fence_after();
             if (key_warp) {
 #pragma unroll 1
@@ -618,8 +626,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             if (slab < 2) mbar_arrive_warp(dk_free);
             if (slab > 0) mbar_arrive_warp(dv_free);
+            if (prof_thread && jb == 0) PROF(71);
             fence_proxy_async_smem();
             named_bar_sync(2, 384);
+            if (prof_thread && jb == 0) PROF(72);
             if (warp == 4 && lane == 0) {
                 tma_store_3d(&args.tmDKV, stage, inner + h * 64, jb * BK_KEYS, b);
                 tma_store_3d(&args.tmDKV, stage + BK_KV_TILE, 2 * inner + h * 64, jb * BK_KEYS, b);
@@ -643,15 +653,19 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         // kills whatever stale TMEM contents (columns beyond the MMA's N extent) may have produced.
         uint32_t pk[16];  // P(p), then dS(p), of this thread's 32 columns, packed bf16 (exact zeros where masked)
         uint32_t pn[16];  // P(p+1) while dS(p) is still in pk
-        auto clear_unreal = [&](uint32_t (&pk)[16], int jj, int ii) {
-            const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns (may be <= 0 or >= 32)
-            const bool qv = ii * 128 + row < T;
-            if (nv >= 32 && ii * 128 + q * 32 + 31 < T) return;   // warp-uniform: nothing to mask
+        // Keys past T exist only in the last key block: slabs entirely beyond them hold zeros, the one slab that straddles
+        // the end clears its invalid columns with integer masks (which also kills whatever the stale TMEM columns beyond
+        // the MMA's N extent produced).
+        auto clear_unreal = [&](uint32_t (&pk)[16], int jj) {
+            const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns
+            if (nv >= 32) return;                                 // warp-uniform
+            if (nv <= 0) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t m = !qv ? 0u : (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
-                pk[k] &= m;
+                for (int k = 0; k < 16; ++k) pk[k] = 0u;
+                return;
             }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pk[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
         };
         auto p_math = [&](const uint32_t (&sv)[32], int ii) {
             const float l2 = ii == 0 ? lse2[0] : (ii == 1 ? lse2[1] : lse2[2]);
@@ -707,7 +721,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_warp(s_free);
             p_math(sv, 0);
-            clear_unreal(pk, 0, 0);
+            clear_unreal(pk, 0);
             p_store(pk);
             if (prof_thread) PROF(94);
         }
@@ -746,10 +760,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                                           bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
                 }
             }
-            clear_unreal(pk, j, i);
+            clear_unreal(pk, j);
             ds_store(p);
             if (prof_thread && p < 8) PROF(102 + p * 4);
-            clear_unreal(pn, jn, in);
+            clear_unreal(pn, jn);
             mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
             p_store(pn);
             if (prof_thread && p < 8) PROF(103 + p * 4);
@@ -771,7 +785,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_warp(dp_free);
             ds_math(dv, i);
-            clear_unreal(pk, j, i);
+            clear_unreal(pk, j);
             ds_store(p);
         }
         if (prof_thread) PROF(95);
