@@ -13,12 +13,14 @@ One JSON line is printed by rank 0:
   e2e          same metric through the public API with HOST (pinned) inputs: H2D copy of every step's batch
                (svit.DevicePrefetcher: copy of batch i+1 under the kernels of batch i) and a D2H read of every step's
                loss inside the timed region
-  roofline     dominant kernel (tcgen05 GEMM of the MLP up-projection, the largest single launch) timed live
-               with CUDA events; whole-step tensor fraction reported next to it
+  roofline     the kernel with the largest share of the step (fused attention backward when training, forward when
+               inferring) timed live with CUDA events, whole-step tensor fraction next to it; roofline_gemm = the same
+               for the largest GEMM launch (MLP up-projection + bias + GELU epilogue)
   cpu_baseline the oracle port of the reference (fp32 PyTorch on the host cores) on a bounded sample
 --impl reference times that CPU path as its own arm (rank 0 only).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -356,13 +358,66 @@ def main():
                 traffic = prof["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
-        roof = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,%s,192,cta_group::2> (fc1 + bias + exact GELU%s, M=%d N=%d K=%d)" % ("EPI_GELU_ONLY" if mode == 4 else "EPI_GELU_GRAD", "" if mode == 4 else " and its derivative", M, H4, D),
+        roof_gemm = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,%s,192,cta_group::2> (fc1 + bias + exact GELU%s, M=%d N=%d K=%d)" % ("EPI_GELU_ONLY" if mode == 4 else "EPI_GELU_GRAD", "" if mode == 4 else " and its derivative", M, H4, D),
                     achieved=ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=ach / peaks["tflops_burst"],
                     traffic=traffic, traffic_source="profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + "
                     "dram__bytes_write.sum, one ncu --set full launch)" if traffic else None,
                     algorithmic_bytes=2.0 * M * D + 2.0 * H4 * D + (2 if mode == 5 else 1) * 2.0 * M * H4,
                     peak_source=peaks["source"] + " (burst: kernel timed alone)",
-                    us_per_launch=k_ms * 1e3, flops_per_launch=flops,
+                    us_per_launch=k_ms * 1e3, flops_per_launch=flops)
+        roof_gemm["hbm_view"] = dict(achieved=roof_gemm["algorithmic_bytes"] / (k_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
+                                     unit="GB/s", frac=roof_gemm["algorithmic_bytes"] / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                     note="arithmetic intensity %.0f flop/B is below the machine balance: by the roofline "
+                                          "model this launch is HBM-bound" % (flops / roof_gemm["algorithmic_bytes"]))
+
+        # ---- the kernel with the largest share of the step: fused attention (backward when training) ----
+        Hh, T = m["heads"], m["num_patches"] + 1
+        inner = Hh * 64
+        qkv = torch.randn(B, T, 3 * inner, device=dev).bfloat16()
+        o = torch.empty(B, T, inner, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, Hh, T, device=dev)
+        scale = ctypes.c_float(0.125)
+        _lib.check(lib.svit_attn_fwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(lse), B, Hh, T, scale, st), "attn_fwd")
+        if kind == "infer":
+            def attn():
+                _lib.check(lib.svit_attn_fwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(lse), B, Hh, T, scale, st), "attn_fwd")
+            a_flops, a_name, a_key = 4.0 * T * T * 64 * B * Hh, "attn_fwd_kernel", "attn_fwd"
+            a_bytes = 2.0 * B * T * (3 * inner + inner) + 4.0 * B * Hh * T
+        else:
+            do = torch.randn(B, T, inner, device=dev).bfloat16()
+            dqkv = torch.empty_like(qkv)
+
+            def attn():
+                _lib.check(lib.svit_attn_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse), _lib.vp(0), _lib.vp(0),
+                                             _lib.ptr(dqkv), B, Hh, T, scale, st), "attn_bwd")
+            a_flops, a_name, a_key = 10.0 * T * T * 64 * B * Hh, "attn_bwd_kernel", "attn_bwd"
+            a_bytes = 2.0 * B * T * (3 * inner + inner + inner + 3 * inner) + 4.0 * B * Hh * T
+        for _ in range(3):
+            attn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n_it):
+            attn()
+        e1.record()
+        torch.cuda.synchronize()
+        a_ms = e0.elapsed_time(e1) / n_it
+        a_ach = a_flops / (a_ms * 1e-3) / 1e12
+        a_traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
+                prof = json.load(f)[a_key]
+            if (B, Hh, T) == (256, 6, 321):
+                a_traffic = prof["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
+        roof = dict(bound="tensor", kernel="%s (one CTA per (sample, head); B=%d H=%d T=%d d=64; %s*T^2*64 flop per head at the "
+                                          "unpadded T)" % (a_name, B, Hh, T, "4" if kind == "infer" else "10"),
+                    achieved=a_ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=a_ach / peaks["tflops_burst"],
+                    traffic=a_traffic, traffic_source="profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + "
+                    "dram__bytes_write.sum, one ncu --set full launch)" if a_traffic else None,
+                    algorithmic_bytes=a_bytes, peak_source=peaks["source"] + " (burst: kernel timed alone)",
+                    us_per_launch=a_ms * 1e3, flops_per_launch=a_flops,
+                    share_of_step=a_ms * m["depth"] / ms_step,
                     step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
                     step_frac_of_nominal_2250=step_tf / 2250.0)
 
@@ -383,7 +438,7 @@ def main():
                                 **m),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                             ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+                    gpu_launches=int(launches), roofline=roof, roofline_gemm=roof_gemm if rank == 0 else None, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

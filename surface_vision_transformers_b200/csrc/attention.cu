@@ -50,6 +50,18 @@ struct AttnFwdArgs {
 __device__ long long g_attn_prof[256];
 #define PROFF(slot) do { if ((args.debug & 8) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial for 2^f on [-0.5, 0.5], max relative error
+// 7.6e-5 -- far below the bf16 rounding of the probabilities): every fourth exponential of the forward pass takes this
+// path and relieves the MUFU (16 ex2 / clk / SM).
+__device__ __forceinline__ float fwd_ex2_poly(float x) {
+    x = fminf(fmaxf(x, -126.0f), 126.0f);
+    const float t = x + 12582912.0f;              // 1.5 * 2^23: round(x) now sits in the low mantissa bits
+    const float f = x - (t - 12582912.0f);        // in [-0.5, 0.5]
+    float p = fmaf(f, 0.05522261559963226f, 0.24261537194252014f);
+    p = fmaf(p, f, 0.6932516098022461f);
+    p = fmaf(p, f, 0.9999275803565979f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // * 2^round(x)
+}
 __device__ __forceinline__ float fwd_ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -185,7 +197,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 #pragma unroll
                         for (int e = 0; e < 32; e += 2) {
                             const float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
-                            const float p1 = fwd_ex2(fmaf(__uint_as_float(r[e + 1]), c, -shift_c));
+                            const float x1 = fmaf(__uint_as_float(r[e + 1]), c, -shift_c);
+                            const float p1 = ((e >> 1) & 1) ? fwd_ex2_poly(x1) : fwd_ex2(x1);  // every 4th on the FMA pipe
                             pk[g6 * 16 + e / 2] = pack_bf16(p0, p1);
                             sm0 += p0;
                             sm1 += p1;
@@ -227,10 +240,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             float part = softmax_pass(shift * c);
             if (threadIdx.x == 0) PROFF(14 + i * 10);
             sRed[hf * 128 + row] = part;
-            bool bad = named_bar_or(1, 256, false);  // (barrier only: make both halves' partial sums visible)
-            float total = sRed[row] + sRed[128 + row];
-            bad = !(total > 0.0f && total < 1e30f);
-            if (named_bar_or(2, 256, bad)) {
+            // One barrier publishes the partial sums and votes on the fallback.  The row sum cannot underflow (key 0
+            // contributes exp2(0) = 1), so "some partial sum is not < 1e30" (overflow, inf or NaN) is the whole test.
+            float total;
+            if (named_bar_or(1, 256, !(part < 1e30f))) {
                 // ---- fallback (uniform for the CTA): classic max-shifted softmax ----
                 float mx = -INFINITY;
                 for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
@@ -250,6 +263,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 named_bar_sync(1, 256);
                 total = sRed[row] + sRed[128 + row];
                 named_bar_sync(2, 256);
+            } else {
+                total = sRed[row] + sRed[128 + row];
             }
             if (threadIdx.x == 0) PROFF(15 + i * 10);
             store_p();
@@ -439,9 +454,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // the issuing warps need few registers, the compute warps many: move them (per warp group of 4 warps)
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BK_REGS_MMA));
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK_REGS_COMPUTE));
+    // The issuing warps need few registers, the compute warps many: move them (per warp group of 4 warps).  Each
+    // setmaxnreg sits at the top of the role branch it governs: ptxas allocates a region by the setmaxnreg that dominates
+    // it (after a common if / else it may fall back to the smaller limit).
 
     auto load_kv = [&](int j) {  // K_j, V_j -> stage j & 1 (called by one thread)
         const int s = j & 1;
@@ -451,7 +466,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         tma_load_3d(dst + BK_KV_TILE, &args.tmKV, &kv_full[s], 2 * inner + h * 64, j * BK_KEYS, b);
     };
 
-    if (warp == 0) {
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BK_REGS_MMA));
+      if (warp == 0) {
         // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
         if (elect_one()) {
             auto load_q = [&](int i) {
@@ -465,8 +482,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             for (int i = 1; i < nqb; ++i) load_q(i);
             if (nkb > 1) load_kv(1);
         }
-    }
-    if (warp < 2) {
+      }
+      if (warp < 2) {
         // ================================ MMA issuers ================================
         // warp 0 (X): a(p+1) = S, c(p) = dV.   warp 1 (Y): b(p+1) = dP, d(p) = dQ, dK.
         // Descriptors are (lo, hi) 32-bit pairs; a K-step adds a constant to lo (see ptx.cuh).
@@ -551,7 +568,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             if (!X) umma_commit(dq_full);
             if (X) PROF(2);
         }
-    } else if (warp >= 4) {
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK_REGS_COMPUTE));
         // ================================ compute warps ================================
         // 12 warps: warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and the 32 key columns
         // [32 slab, 32 slab + 32) of every 96-key block -- for the probabilities AND for dS, so P stays in registers
