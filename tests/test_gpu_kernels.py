@@ -168,6 +168,43 @@ def test_attention_fwd_bwd(env, B, H, T):
             assert rel_l2(got, want) < 2 * TOL
 
 
+@pytest.mark.parametrize("T", [2, 31, 33, 95, 96, 97, 112, 127, 129, 191, 192, 193, 255, 256, 257, 287, 288, 289, 320, 322, 383])
+def test_attention_boundary_lengths(env, T):
+    """Every tile boundary of the fused kernels (96-key blocks x 32-column slabs and 128-query blocks in the backward,
+    32-column groups in the forward): one token short of, exactly at and one past each of them.  NaN-prefilled outputs
+    catch rows or columns that a masked path forgot; a poisoned second pass catches stale TMEM contents."""
+    dev, lib = env["dev"], env["lib"]
+    B, H = 2, 2
+    torch.manual_seed(T)
+    inner, scale = H * 64, 64 ** -0.5
+    qkv = torch.randn(B, T, 3 * inner, device=dev).bfloat16()
+    dout = torch.randn(B, T, inner, device=dev).bfloat16()
+    q, k, v = [t.reshape(B, T, H, 64).permute(0, 2, 1, 3).float().requires_grad_(True) for t in qkv.chunk(3, dim=-1)]
+    dots = q @ k.transpose(-1, -2) * scale
+    ref = (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, T, inner)
+    ref.backward(dout.float())
+    dref = torch.cat([g.permute(0, 2, 1, 3).reshape(B, T, inner) for g in (q.grad, k.grad, v.grad)], dim=-1)
+    # a first launch on a long, huge-valued problem leaves large numbers in every TMEM column / smem tile
+    big = (torch.randn(B, 384, 3 * inner, device=dev) * 30).bfloat16()
+    bo = torch.empty(B, 384, inner, device=dev, dtype=torch.bfloat16)
+    bl = torch.zeros(B, H, 384, device=dev)
+    bd = torch.empty_like(big)
+    for _ in range(2):
+        check(lib.svit_attn_fwd(ptr(big), ptr(bo), ptr(bl), B, H, 384, scale, stream()), "attn_fwd")
+        check(lib.svit_attn_bwd(ptr(big), ptr(bo), ptr(bo), ptr(bl), vp(0), vp(0), ptr(bd), B, H, 384, scale, stream()), "attn_bwd")
+        out = torch.full((B, T, inner), float("nan"), device=dev, dtype=torch.bfloat16)
+        lse = torch.full((B, H, T), float("nan"), device=dev)
+        dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
+        check(lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, scale, stream()), "attn_fwd")
+        check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), vp(0), vp(0), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all() and torch.isfinite(dqkv.float()).all()
+        assert rel_l2(out, ref) < TOL
+        assert rel_l2(lse, torch.logsumexp(dots, -1)) < 1e-3
+        for i in range(3):
+            assert rel_l2(dqkv[..., i * inner:(i + 1) * inner].float(), dref[..., i * inner:(i + 1) * inner]) < 2 * TOL, i
+
+
 @pytest.mark.parametrize("kind", ["large_random", "ascending_keys", "descending_keys"])
 def test_attention_fwd_extreme_logits(env, kind):
     """The online softmax with lazy rescaling stays exact when later key chunks raise the row maximum by far more than
