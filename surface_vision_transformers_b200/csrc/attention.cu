@@ -748,12 +748,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         int j = 0, i = 0, jn = nqb > 1 ? 0 : 1, in = nqb > 1 ? 1 : 0;
 #pragma unroll 1
         for (int p = 0; p + 1 < total; ++p) {
-            // key block j-1 is final (both accumulators retired during the previous step): copy dK / dV out, refill its stage
-            if (i == 0 && j > 0) {
-                if (prof_thread) PROF(80 + j * 2);
-                store_kv(j - 1);
-                if (prof_thread) PROF(81 + j * 2);
-            }
             uint32_t dv[32], sv[32];
             if (prof_thread && p < 8) PROF(100 + p * 4);
             mbar_wait(dp_full, p & 1);
@@ -778,6 +772,13 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                     pk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(dv[e]), args.scale, -sd),
                                           bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
                 }
+            }
+            // Key block j-1 is final: copy dK / dV out.  Here rather than at the top of the step: d(p-1) needs ~1,000 clocks
+            // after the previous step's dS hand-off to retire, and the arithmetic above has just covered them.
+            if (i == 0 && j > 0) {
+                if (prof_thread) PROF(80 + j * 2);
+                store_kv(j - 1);
+                if (prof_thread) PROF(81 + j * 2);
             }
             clear_unreal(pk, j);
             ds_store(p);
