@@ -6,7 +6,7 @@ Public API mirrors the reference (SD3004/surface-vision-transformers):
 plus the pieces the north star adds around them: FusedAdamW / FusedSGD (optim), DataParallel (ddp),
 gather_patches / index tables (gather), DevicePrefetcher (loader: overlapped host -> device batch staging),
 and the formats either side of the path: preprocess_meshes / PatchedNpyDataset (data),
-load_weights_imagenet / load_ssl_checkpoint (interop), fit (trainer).
+load_weights_imagenet / load_ssl_checkpoint (interop), fit / fit_mpp (trainer).
 """
 from .sit import SiT, Transformer  # noqa: F401
 from .mpp import masked_patch_pretraining, get_mask_from_prob, prob_mask_like  # noqa: F401
@@ -16,4 +16,4 @@ from .gather import gather_patches, load_index_table  # noqa: F401
 from .loader import DevicePrefetcher  # noqa: F401
 from .data import preprocess_meshes, PatchedNpyDataset  # noqa: F401
 from .interop import load_weights_imagenet, load_ssl_checkpoint  # noqa: F401
-from .trainer import fit, evaluate  # noqa: F401
+from .trainer import fit, evaluate, fit_mpp  # noqa: F401

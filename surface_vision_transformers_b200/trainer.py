@@ -10,6 +10,8 @@ rank 2), arranged so that the device never waits for the host:
 What is kept from the reference: MSE (or L1) criterion on ``outputs.squeeze()``, train MAE per epoch, validation every
 ``val_epoch`` epochs in ``eval()`` + ``no_grad``, best-validation-MAE bookkeeping with an optional ``checkpoint.pth``
 holding ``model.state_dict()`` (train.py:355-363), the same scalar names for an optional TensorBoard-like writer.
+
+``fit_mpp`` is the same arrangement for the masked-patch pre-training loop of tools/pretrain.py:303-389.
 """
 import os
 
@@ -19,7 +21,7 @@ import torch.distributed as dist
 from .ddp import DataParallel
 from .loader import DevicePrefetcher
 
-__all__ = ["fit", "evaluate"]
+__all__ = ["fit", "evaluate", "fit_mpp"]
 
 
 def _dist_info():
@@ -123,3 +125,78 @@ def fit(model, optimizer, train_set, val_set=None, *, epochs, batch_size, val_ba
                     if save_ckpt:
                         torch.save(core.state_dict(), os.path.join(save_dir, "checkpoint.pth"))   # train.py:361-363
     return dict(history=history, best_mae=best_mae, best_epoch=best_epoch)
+
+
+def _mpp_epoch_loss(ssl, dataset, batch_size, device, rank, world, train, optimizer=None, generator=None):
+    """Mean over iterations of the MPP loss (pretrain.py: running_loss / (i + 1)), all ranks combined."""
+    stats = torch.zeros(2, dtype=torch.float64, device=device)   # sum of batch losses, batches
+    batches = dataset.batches(batch_size, shuffle=train, generator=generator, rank=rank, world=world)
+    for x, _ in DevicePrefetcher(batches, device):
+        if train:
+            optimizer.zero_grad(set_to_none=True)
+            loss, _ = ssl(x)
+            loss.backward()
+            optimizer.step()
+        else:
+            loss, _ = ssl(x)
+        with torch.no_grad():
+            stats[0] += loss.detach().double()
+            stats[1] += 1
+    _all_reduce_(stats)
+    s = stats.cpu()                                         # the one host read per pass
+    return float(s[0] / s[1].clamp(min=1))
+
+
+def fit_mpp(ssl, optimizer, train_set, val_set=None, *, epochs, batch_size, val_batch_size=None, val_epoch=1, device=None,
+            save_dir=None, writer=None, seed=0, scheduler=None, log=None):
+    """Masked-patch pre-training with the semantics of tools/pretrain.py:303-389: ``mpp_loss, _ = ssl(inputs)`` per
+    iteration, epoch loss = mean of the iteration losses, validation every ``val_epoch`` epochs under ``ssl.eval()`` +
+    ``no_grad`` (the masking stays active, as in the reference), and on every improvement of the validation loss the two
+    checkpoints the reference writes -- ``encoder-best.pt`` (the SiT's ``state_dict``) and ``encoder-decoder-best.pt``
+    (the whole module's), each as ``{'epoch', 'model_state_dict', 'optimizer_state_dict', 'loss'}``, which is the file
+    format ``load_ssl_checkpoint`` reads back for fine-tuning (train.py:213-223).
+
+    ``ssl``: a B200 ``masked_patch_pretraining`` (wrapped in ``DataParallel`` here under torchrun).  Returns a dict with
+    the history, the best validation loss and its epoch."""
+    rank, world = _dist_info()
+    device = torch.device(device) if device is not None else next(ssl.parameters()).device
+    if device.type != "cuda":
+        raise RuntimeError("fit_mpp() drives the CUDA hot path (no CPU fallback)")
+    net = ssl
+    if world > 1 and not isinstance(ssl, DataParallel):
+        net = DataParallel(ssl)
+    core = net.module if isinstance(net, DataParallel) else net
+    gen = torch.Generator()
+    history = dict(train_loss=[], val_loss=[], lr=[])
+    best_val, best_epoch = float("inf"), None
+    for epoch in range(epochs):
+        core.train()
+        gen.manual_seed(seed + epoch)
+        train_loss = _mpp_epoch_loss(net, train_set, batch_size, device, rank, world, True, optimizer, gen)
+        if scheduler is not None:
+            scheduler.step()
+        history["train_loss"].append(train_loss)
+        history["lr"].append(optimizer.param_groups[0]["lr"])
+        if writer is not None and rank == 0:
+            writer.add_scalar("loss/train", train_loss, epoch + 1)
+        if log is not None and rank == 0:
+            log(f"| Epoch - {epoch + 1} | Loss - {train_loss:.4f} | LR - {history['lr'][-1]}")
+        if val_set is not None and (epoch + 1) % val_epoch == 0:
+            core.eval()
+            with torch.no_grad():
+                val_loss = _mpp_epoch_loss(net, val_set, val_batch_size or batch_size, device, rank, world, False)
+            core.train()
+            history["val_loss"].append((epoch + 1, val_loss))
+            if writer is not None and rank == 0:
+                writer.add_scalar("loss/val", val_loss, epoch + 1)
+            if log is not None and rank == 0:
+                log(f"| Validation | Epoch - {epoch + 1} | Loss - {val_loss} |")
+            if val_loss < best_val:
+                best_val, best_epoch = val_loss, epoch + 1
+                if save_dir is not None and rank == 0:
+                    os.makedirs(save_dir, exist_ok=True)
+                    for name, module in (("encoder-best.pt", core.transformer), ("encoder-decoder-best.pt", core)):
+                        torch.save({"epoch": epoch + 1, "model_state_dict": module.state_dict(),
+                                    "optimizer_state_dict": optimizer.state_dict(), "loss": train_loss},
+                                   os.path.join(save_dir, name))   # pretrain.py:378-389
+    return dict(history=history, best_val_loss=best_val, best_epoch=best_epoch)

@@ -398,6 +398,69 @@ def test_fit_tracks_reference_style_loop(tmp_path):
     assert saved["preds"].shape == (10,) and torch.equal(saved["targets"], val.labels)
 
 
+def test_fit_mpp_tracks_reference_style_loop(tmp_path):
+    """8(f)-2, pre-training half: fit_mpp() against a plain tools/pretrain.py-style loop (pretrain.py:303-389) on the
+    fp32 oracle.  Both consume torch's RNG in the reference's order, so they draw the same masks; per-epoch train and
+    validation losses agree within the bf16 tolerance, the best epoch is the same, and the two checkpoint files have
+    the reference's format -- load_ssl_checkpoint() reads the encoder back for fine-tuning."""
+    import numpy as np
+    cfg = dict(dim=128, depth=2, heads=2, mlp_dim=256, num_patches=20, num_vertices=15)
+    K = 4 * 15
+    rng = np.random.default_rng(1)
+    for split, n in (("train", 24), ("validation", 8)):
+        np.save(tmp_path / f"{split}_data.npy", rng.standard_normal((n, 4, 20, 15)))
+        np.save(tmp_path / f"{split}_labels.npy", rng.uniform(26, 45, size=n))
+    train = svit.PatchedNpyDataset(str(tmp_path), "train")
+    val = svit.PatchedNpyDataset(str(tmp_path), "validation")
+    kw = dict(mask_prob=0.5, replace_prob=0.8, swap_prob=0.02, channels=4, num_vertices=15)
+    torch.manual_seed(2)
+    oracle = OracleMPP(OracleSiT(**cfg), cfg["dim"], K, DEV, **kw).to(DEV)
+    ssl = svit.masked_patch_pretraining(transformer=svit.SiT(**cfg), dim_in=cfg["dim"], dim_out=K, device=DEV, **kw)
+    ssl.load_state_dict(oracle.state_dict())
+    ssl.to(DEV)
+    epochs, bs = 3, 8
+    # reference-style loop on the oracle
+    opt = torch.optim.AdamW(oracle.parameters(), lr=3e-4, weight_decay=0.0)
+    gen = torch.Generator()
+    torch.manual_seed(99)
+    ref_train, ref_val = [], []
+    for epoch in range(epochs):
+        gen.manual_seed(5 + epoch)
+        oracle.train()
+        run, nb = 0.0, 0
+        for x, _ in train.batches(bs, shuffle=True, generator=gen):
+            opt.zero_grad()
+            loss, _ = oracle(x.to(DEV))
+            loss.backward()
+            opt.step()
+            run += loss.item(); nb += 1
+        ref_train.append(run / nb)
+        oracle.eval()
+        with torch.no_grad():
+            vl = [oracle(x.to(DEV))[0].item() for x, _ in val.batches(bs)]
+        ref_val.append(sum(vl) / len(vl))
+    torch.manual_seed(99)
+    opt2 = svit.FusedAdamW(ssl.parameters(), lr=3e-4, weight_decay=0.0)
+    res = svit.fit_mpp(ssl, opt2, train, val, epochs=epochs, batch_size=bs, val_epoch=1, device=DEV,
+                       save_dir=str(tmp_path / "out"), seed=5)
+    h = res["history"]
+    for a, b in zip(h["train_loss"], ref_train):
+        assert abs(a - b) / b < 3 * TOL, (h["train_loss"], ref_train)
+    for (e, a), b in zip(h["val_loss"], ref_val):
+        assert abs(a - b) / b < 3 * TOL, (h["val_loss"], ref_val)
+    assert h["train_loss"][-1] < h["train_loss"][0]
+    assert res["best_epoch"] == 1 + min(range(epochs), key=lambda i: ref_val[i])
+    ck = torch.load(tmp_path / "out" / "encoder-decoder-best.pt")
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss"} and ck["epoch"] == res["best_epoch"]
+    assert set(ck["model_state_dict"]) == set(oracle.state_dict())
+    enc = torch.load(tmp_path / "out" / "encoder-best.pt")
+    assert set(enc["model_state_dict"]) == set(oracle.transformer.state_dict())
+    fresh = svit.SiT(**cfg)
+    svit.load_ssl_checkpoint(fresh, str(tmp_path / "out" / "encoder-best.pt"))
+    for k, v in enc["model_state_dict"].items():
+        assert torch.equal(fresh.state_dict()[k].cpu(), v.cpu()), k
+
+
 # ------------------------------------------------------------------------------------------- dropout > 0 (8(f)-4)
 def _dropout_pair(cfg, p, emb_p, seed, step, check_mode):
     """B200 SiT with dropout and the oracle with MaskedDropout modules applying the very same keep decisions."""
