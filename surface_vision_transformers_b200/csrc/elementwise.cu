@@ -492,11 +492,22 @@ __global__ void head_bwd_kernel(const float* __restrict__ x, const float* __rest
     float* gb = g + static_cast<size_t>(b) * T * D;
     __nv_bfloat16* gbb = g_bf16 + static_cast<size_t>(b) * T * D;
     const float inv_t = 1.0f / T;
-    for (size_t i = threadIdx.x; i < static_cast<size_t>(T) * D; i += blockDim.x) {
-        const int t = static_cast<int>(i / D), d = static_cast<int>(i - static_cast<size_t>(t) * D);
-        const float v = pool_mean ? dz[d] * inv_t : (t == 0 ? dz[d] : 0.0f);
-        gb[i] = v;
-        gbb[i] = __float2bfloat16(v);
+    // g of this sample: every row (mean pooling) or row 0 only (cls pooling) carries dz, the rest is zero -- 6 bytes per
+    // element of pure store traffic: one warp per row, 16-byte fp32 and 8-byte bf16 stores (D % 4 == 0)
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int t = threadIdx.x >> 5; t < T; t += nw) {
+        const bool live = pool_mean || t == 0;
+        const float sc = pool_mean ? inv_t : 1.0f;
+        for (int d = lane * 4; d < D; d += 128) {
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (live) v = make_float4(dz[d] * sc, dz[d + 1] * sc, dz[d + 2] * sc, dz[d + 3] * sc);
+            *reinterpret_cast<float4*>(gb + static_cast<size_t>(t) * D + d) = v;
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(gbb + static_cast<size_t>(t) * D + d) = o;
+        }
     }
 }
 
@@ -516,7 +527,7 @@ int launch_head_bwd(const float* x, const float* gamma, const float* beta, const
         set_error("head_bwd: num_classes=%d > 256 unsupported", C);
         return -2;
     }
-    head_bwd_kernel<<<B, 256, (2 * D + 32) * sizeof(float), st>>>(x, gamma, beta, W, dout, g,
+    head_bwd_kernel<<<B, 512, (2 * D + 32) * sizeof(float), st>>>(x, gamma, beta, W, dout, g,
                                                                   reinterpret_cast<__nv_bfloat16*>(g_bf16), dgamma, dbeta,
                                                                   dW, dbias, colsum_out, T, D, C, pool_mean, eps);
     SVIT_CHECK_LAUNCH("head_bwd");
@@ -820,18 +831,38 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     const long long c1 = min(sg.numel, c0 + ADAM_BLOCK_ELEMS);
     const float step_size = lr / sg.bias_corr1;
     const float inv_sqrt_bc2 = rsqrtf(sg.bias_corr2);
-    for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const long long j = sg.offset + i;
-        float pj = p[j];
-        float gj = g[j] * grad_scale;
+    auto update = [&](float& pj, float gj, float& mj, float& vj) {
+        gj *= grad_scale;
         if (decoupled) pj *= (1.0f - lr * weight_decay);
         else gj += weight_decay * pj;
-        const float mj = beta1 * m[j] + (1.0f - beta1) * gj;
-        const float vj = beta2 * v[j] + (1.0f - beta2) * gj * gj;
+        mj = beta1 * mj + (1.0f - beta1) * gj;
+        vj = beta2 * vj + (1.0f - beta2) * gj * gj;
+        const float denom = sqrtf(vj) * inv_sqrt_bc2 + eps;
+        pj = pj - step_size * (mj / denom);
+    };
+    // segment offsets and chunk starts are multiples of 64 elements: 16-byte accesses for the body, scalars for a ragged tail
+    const long long c4 = c0 + ((c1 - c0) & ~3LL);
+    for (long long i = c0 + 4 * threadIdx.x; i < c4; i += 4 * blockDim.x) {
+        const long long j = sg.offset + i;
+        float4 p4 = *reinterpret_cast<const float4*>(p + j);
+        const float4 g4 = *reinterpret_cast<const float4*>(g + j);
+        float4 m4 = *reinterpret_cast<const float4*>(m + j);
+        float4 v4 = *reinterpret_cast<const float4*>(v + j);
+        update(p4.x, g4.x, m4.x, v4.x);
+        update(p4.y, g4.y, m4.y, v4.y);
+        update(p4.z, g4.z, m4.z, v4.z);
+        update(p4.w, g4.w, m4.w, v4.w);
+        *reinterpret_cast<float4*>(m + j) = m4;
+        *reinterpret_cast<float4*>(v + j) = v4;
+        *reinterpret_cast<float4*>(p + j) = p4;
+    }
+    for (long long i = c4 + threadIdx.x; i < c1; i += blockDim.x) {
+        const long long j = sg.offset + i;
+        float pj = p[j], mj = m[j], vj = v[j];
+        update(pj, g[j], mj, vj);
         m[j] = mj;
         v[j] = vj;
-        const float denom = sqrtf(vj) * inv_sqrt_bc2 + eps;
-        p[j] = pj - step_size * (mj / denom);
+        p[j] = pj;
     }
 }
 
