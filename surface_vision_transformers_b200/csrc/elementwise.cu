@@ -100,17 +100,19 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 // =================================================================================================
 // One thread per 8 consecutive output elements (one 16-byte store); the operand row is channel-major (k = c * V + v),
 // so the 8 inputs of a thread are consecutive floats of one channel (or straddle one channel boundary).
+// IdxT = uint32_t whenever the vector count fits (always, in practice): the two divisions per thread are 32-bit then.
+template <typename IdxT>
 __global__ void __launch_bounds__(256) pack_patches_kernel(const PackDesc d) {
     const int T = d.N + 1;
     const int nvec = d.Kp >> 3;
-    const size_t total = static_cast<size_t>(d.B) * T * nvec;
+    const IdxT total = static_cast<IdxT>(d.B) * T * nvec;
     const int CV = d.C * d.V;
-    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const size_t row = idx / nvec;  // b*T + t
+    for (IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<IdxT>(gridDim.x) * blockDim.x) {
+        const IdxT row = idx / static_cast<IdxT>(nvec);  // b*T + t
         const int i = static_cast<int>(idx - row * nvec);
-        const int b = static_cast<int>(row / T), t = static_cast<int>(row - static_cast<size_t>(b) * T);
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.A) + row * d.Kp) + i;
+        const int b = static_cast<int>(row / static_cast<IdxT>(T)), t = static_cast<int>(row - static_cast<IdxT>(b) * T);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.A) + static_cast<size_t>(row) * d.Kp) + i;
         if (t == 0) {
             *dst = make_uint4(0u, 0u, 0u, 0u);
             continue;
@@ -122,6 +124,26 @@ __global__ void __launch_bounds__(256) pack_patches_kernel(const PackDesc d) {
         float val[8];
         const int k0 = i * 8;
         int c = k0 / d.V, v = k0 - c * d.V;
+        if (!replace && d.table == nullptr && k0 + 8 <= CV) {
+            // plain pre-patched input, no padding column in this vector: 8 consecutive (c, v) of one patch
+            const float* src = d.x + ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v;
+            const size_t cstep = static_cast<size_t>(d.N - 1) * d.V;  // extra offset once the channel wraps
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                val[e] = __ldg(src + e);
+                if (++v == d.V) {
+                    v = 0;
+                    src += cstep;
+                }
+            }
+            uint4 o;
+            o.x = pack2_bf16(val[0], val[1]);
+            o.y = pack2_bf16(val[2], val[3]);
+            o.z = pack2_bf16(val[4], val[5]);
+            o.w = pack2_bf16(val[6], val[7]);
+            *dst = o;
+            continue;
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float x = 0.0f;
@@ -159,7 +181,10 @@ int launch_pack_patches(const PackDesc& d, cudaStream_t st) {
     const size_t total = static_cast<size_t>(d.B) * (d.N + 1) * (d.Kp / 8);
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    pack_patches_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d);
+    if (total + static_cast<size_t>(148) * 64 * 256 < (static_cast<size_t>(1) << 32))
+        pack_patches_kernel<uint32_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(d);
+    else
+        pack_patches_kernel<size_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(d);
     SVIT_CHECK_LAUNCH("pack_patches");
     return 0;
 }
