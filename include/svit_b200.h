@@ -142,12 +142,19 @@ typedef struct svit_adam_segment {
     float bias_corr1; /* 1 - beta1^step */
     float bias_corr2; /* 1 - beta2^step */
     int active;       /* 0 = parameter had no gradient: skipped like torch.optim does */
+    int step;         /* updates applied so far (torch's state['step']); maintained on the device by svit_adamw_advance */
 } svit_adam_segment;
 #define SVIT_ADAM_BLOCK_ELEMS 4096
 /* block_map: int pairs (segment index, chunk index), one per thread block, chunks of SVIT_ADAM_BLOCK_ELEMS elements */
 int svit_adamw_step(float* p, const float* g, float* m, float* v, const svit_adam_segment* segs_dev, int nsegs,
                     const int* block_map_dev, int nblocks, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int decoupled, float grad_scale, void* stream);
+/* Stream-ordered bookkeeping for the next svit_adamw_step: step += 1 and bias_corr{1,2} = 1 - beta{1,2}^step for every
+ * active segment of the DEVICE table.  The host therefore uploads the table only when offsets or active flags change:
+ * nothing step-dependent crosses the host/device boundary asynchronously any more (a pinned staging buffer rewritten by
+ * a host that runs several steps ahead of the GPU used to), and a captured CUDA graph of the training step replays
+ * correctly. */
+int svit_adamw_advance(svit_adam_segment* segs_dev, int nsegs, float beta1, float beta2, void* stream);
 int svit_sgd_step(float* p, const float* g, float* momentum_buf, long long n, float lr, float momentum, float dampening,
                   float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 

@@ -6,7 +6,8 @@ Public API mirrors the reference (SD3004/surface-vision-transformers):
 plus the pieces the north star adds around them: FusedAdamW / FusedSGD (optim), DataParallel (ddp),
 gather_patches / index tables (gather), DevicePrefetcher (loader: overlapped host -> device batch staging),
 and the formats either side of the path: preprocess_meshes / PatchedNpyDataset (data),
-load_weights_imagenet / load_ssl_checkpoint (interop), fit / fit_mpp (trainer).
+load_weights_imagenet / load_ssl_checkpoint (interop), fit / fit_mpp (trainer), GraphedInference /
+GraphedTrainStep (graphs: CUDA-graph capture of the step).
 """
 from .sit import SiT, Transformer  # noqa: F401
 from .mpp import masked_patch_pretraining, get_mask_from_prob, prob_mask_like  # noqa: F401
@@ -17,3 +18,4 @@ from .loader import DevicePrefetcher  # noqa: F401
 from .data import preprocess_meshes, PatchedNpyDataset  # noqa: F401
 from .interop import load_weights_imagenet, load_ssl_checkpoint  # noqa: F401
 from .trainer import fit, evaluate, fit_mpp  # noqa: F401
+from .graphs import GraphedInference, GraphedTrainStep  # noqa: F401

@@ -20,7 +20,7 @@ class SvitConfig(ctypes.Structure):
 
 
 class AdamSegment(ctypes.Structure):
-    _fields_ = [("offset", cll), ("numel", cll), ("bias_corr1", cf), ("bias_corr2", cf), ("active", ci)]
+    _fields_ = [("offset", cll), ("numel", cll), ("bias_corr1", cf), ("bias_corr2", cf), ("active", ci), ("step", ci)]
 
 
 ADAM_BLOCK_ELEMS = 4096
@@ -54,6 +54,7 @@ SIGNATURES = {
     "svit_mpp_backward": (ci, [vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "svit_gather_patches": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "svit_adamw_step": (ci, [vp, vp, vp, vp, vp, ci, vp, ci, cf, cf, cf, cf, cf, ci, cf, vp]),
+    "svit_adamw_advance": (ci, [vp, ci, cf, cf, vp]),
     "svit_sgd_step": (ci, [vp, vp, vp, cll, cf, cf, cf, cf, ci, ci, cf, vp]),
     "svit_gemm_tn": (ci, [vp] * 7 + [ci] * 10 + [vp]),
     "svit_gemm_wgrad": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),

@@ -891,6 +891,21 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
+__global__ void adamw_advance_kernel(AdamSegment* __restrict__ segs, int nsegs, float beta1, float beta2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsegs || !segs[i].active) return;
+    const int k = segs[i].step + 1;
+    segs[i].step = k;
+    segs[i].bias_corr1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(k)));
+    segs[i].bias_corr2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), static_cast<double>(k)));
+}
+int launch_adamw_advance(AdamSegment* segs_dev, int nsegs, float beta1, float beta2, cudaStream_t st) {
+    if (nsegs <= 0) return 0;
+    adamw_advance_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(segs_dev, nsegs, beta1, beta2);
+    SVIT_CHECK_LAUNCH("adamw_advance");
+    return 0;
+}
+
 int launch_adamw(float* p, const float* g, float* m, float* v, const AdamSegment* segs_dev, int nsegs,
                  const int* block_map_dev, int nblocks, float lr, float beta1, float beta2, float eps, float weight_decay,
                  int decoupled, float grad_scale, cudaStream_t st) {

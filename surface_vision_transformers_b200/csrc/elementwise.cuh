@@ -90,7 +90,10 @@ struct AdamSegment {
     float bias_corr1;   // 1 - beta1^step
     float bias_corr2;   // 1 - beta2^step
     int active;         // 0: skip (no gradient)
+    int step;           // updates applied so far (device-side counter, see launch_adamw_advance)
 };
+// step += 1, bias_corr = 1 - beta^step for every active segment (one tiny stream-ordered kernel before launch_adamw)
+int launch_adamw_advance(AdamSegment* segs_dev, int nsegs, float beta1, float beta2, cudaStream_t st);
 int launch_adamw(float* p, const float* g, float* m, float* v, const AdamSegment* segs_dev, int nsegs,
                  const int* block_map_dev, int nblocks, float lr, float beta1, float beta2, float eps, float weight_decay,
                  int decoupled, float grad_scale, cudaStream_t st);

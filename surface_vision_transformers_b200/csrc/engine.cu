@@ -861,6 +861,10 @@ int svit_adamw_step(float* p, const float* g, float* m, float* v, const svit_ada
     return launch_adamw(p, g, m, v, reinterpret_cast<const AdamSegment*>(segs_dev), nsegs, block_map_dev, nblocks, lr, beta1,
                         beta2, eps, weight_decay, decoupled, grad_scale, reinterpret_cast<cudaStream_t>(stream));
 }
+int svit_adamw_advance(svit_adam_segment* segs_dev, int nsegs, float beta1, float beta2, void* stream) {
+    return launch_adamw_advance(reinterpret_cast<AdamSegment*>(segs_dev), nsegs, beta1, beta2,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
 int svit_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float dampening,
                   float weight_decay, int nesterov, int first_step, float grad_scale, void* stream) {
     return launch_sgd(p, g, mom, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale,

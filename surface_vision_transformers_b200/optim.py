@@ -65,6 +65,7 @@ class _FlatState:
         self.seg_pinned = torch.empty(ctypes.sizeof(self.seg_host), dtype=torch.uint8).pin_memory() \
             if owner._flat.is_cuda else None
         self.seg_dev = torch.empty(ctypes.sizeof(self.seg_host), dtype=torch.uint8, device=owner._flat.device)
+        self.table_key = None      # active pattern the device table was uploaded for (None: upload needed)
 
 
 class FusedAdamW(Optimizer):
@@ -77,11 +78,13 @@ class FusedAdamW(Optimizer):
         self.grad_scale = grad_scale
         self._flat_states = {}
 
-    def _state_for(self, owner):
+    def _state_for(self, owner, rebind=True):
         st = self._flat_states.get(id(owner))
         if st is None or st.flat_ptr != owner._flat.data_ptr():
             st = _FlatState(owner, 2)
             self._flat_states[id(owner)] = st
+            if not rebind:
+                return st
             for p in owner._plist:
                 off, n = owner._offsets[p._svit_index]
                 self.state[p] = {"step": torch.tensor(0.0), "exp_avg": st.bufs[0][off:off + n].view(p.shape),
@@ -113,26 +116,85 @@ class FusedAdamW(Optimizer):
                 if G is None:
                     continue
                 st = self._state_for(owner)
-                for i, (p, a) in enumerate(zip(ps, active)):
-                    off, n = owner._offsets[i]
-                    if a:
-                        st.steps[i] += 1
-                        self.state[p]["step"] = torch.tensor(float(st.steps[i]))
-                    s = st.seg_host[i]
-                    s.offset, s.numel, s.active = off, n, 1 if a else 0
-                    k = max(st.steps[i], 1)
-                    s.bias_corr1, s.bias_corr2 = 1.0 - beta1 ** k, 1.0 - beta2 ** k
-                nbytes = ctypes.sizeof(st.seg_host)
-                ctypes.memmove(st.seg_pinned.data_ptr(), ctypes.addressof(st.seg_host), nbytes)
-                st.seg_dev.copy_(st.seg_pinned, non_blocking=True)
                 dev = owner._flat.device
+                stream = vp(torch.cuda.current_stream(dev).cuda_stream)
+                # The step counters and bias corrections live in the DEVICE table and are advanced by a stream-ordered
+                # kernel; the host uploads the table only when the active pattern changes (first step, a parameter
+                # gaining / losing its gradient, load_state_dict).  Nothing step-dependent is staged through pinned
+                # memory any more -- a host that runs several steps ahead of the GPU would overwrite it before the copy
+                # executes -- and a captured CUDA graph of the step replays correctly (graphs.GraphedTrainStep).
+                key = tuple(active)
+                if st.table_key != key:
+                    if torch.cuda.is_current_stream_capturing():
+                        raise RuntimeError("FusedAdamW: the set of parameters with gradients changed during CUDA graph "
+                                           "capture; run the warm-up steps with the same graph first")
+                    for i, a in enumerate(active):
+                        off, n = owner._offsets[i]
+                        s = st.seg_host[i]
+                        s.offset, s.numel, s.active, s.step = off, n, 1 if a else 0, st.steps[i]
+                        s.bias_corr1 = s.bias_corr2 = 1.0
+                    ctypes.memmove(st.seg_pinned.data_ptr(), ctypes.addressof(st.seg_host), ctypes.sizeof(st.seg_host))
+                    st.seg_dev.copy_(st.seg_pinned)      # synchronous on purpose (rare)
+                    st.table_key = key
+                self._note_step(owner, st, active)
+                check(lib.svit_adamw_advance(ptr(st.seg_dev), len(ps), beta1, beta2, stream), "svit_adamw_advance")
                 check(lib.svit_adamw_step(ptr(owner._flat), ptr(G), ptr(st.bufs[0]), ptr(st.bufs[1]), ptr(st.seg_dev),
                                           len(ps), ptr(st.block_map), st.nblocks, group["lr"], beta1, beta2, group["eps"],
                                           group["weight_decay"], 1 if group["decoupled"] else 0, self.grad_scale,
-                                          vp(torch.cuda.current_stream(dev).cuda_stream)), "svit_adamw_step")
+                                          stream), "svit_adamw_step")
                 owner.mark_weights_dirty()
             self._generic_adam(group, loose)
         return loss
+
+    def _note_step(self, owner, st, active):
+        """Host mirror of the device-side step counters (what ``state_dict()`` reports as ``state[p]['step']``)."""
+        st.last_active = list(active)
+        if torch.cuda.is_current_stream_capturing():
+            return      # a capture records the step without executing it: the device counters do not move either
+        for i, (p, a) in enumerate(zip(owner._plist, active)):
+            if a:
+                st.steps[i] += 1
+                self.state[p]["step"] = torch.tensor(float(st.steps[i]))
+        st.last_active = list(active)
+
+    def note_graph_replay(self):
+        """A captured training step was replayed: the device advanced its counters, mirror that on the host."""
+        for st, owner in ((s_, o_) for s_, o_ in self._owners()):
+            if getattr(st, "last_active", None) is not None:
+                self._note_step(owner, st, st.last_active)
+
+    def _owners(self):
+        seen = {}
+        for group in self.param_groups:
+            for p in group["params"]:
+                o = _owner_of(p)
+                if o is not None and id(o) in self._flat_states:
+                    seen[id(o)] = (self._flat_states[id(o)], o)
+        return list(seen.values())
+
+    def load_state_dict(self, state_dict):
+        """torch's loader replaces the per-parameter state tensors; copy them back into the flat moment buffers (the
+        fused kernel updates those), restore the step counters and force a re-upload of the device table."""
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            owners = {}
+            for p in group["params"]:
+                o = _owner_of(p)
+                if o is not None and hasattr(o, "_offsets") and hasattr(p, "_svit_index"):
+                    owners[id(o)] = o
+            for owner in owners.values():
+                st = self._state_for(owner, rebind=False)
+                for i, p in enumerate(owner._plist):
+                    loaded = self.state.get(p, {})
+                    off, n = owner._offsets[i]
+                    if "exp_avg" in loaded:
+                        st.bufs[0][off:off + n].copy_(loaded["exp_avg"].reshape(-1))
+                        st.bufs[1][off:off + n].copy_(loaded["exp_avg_sq"].reshape(-1))
+                        st.steps[i] = int(float(loaded.get("step", 0)))
+                    self.state[p] = {"step": torch.tensor(float(st.steps[i])),
+                                     "exp_avg": st.bufs[0][off:off + n].view(p.shape),
+                                     "exp_avg_sq": st.bufs[1][off:off + n].view(p.shape)}
+                st.table_key = None
 
     def _generic_adam(self, group, params):
         beta1, beta2 = group["betas"]

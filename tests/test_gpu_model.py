@@ -461,6 +461,101 @@ def test_fit_mpp_tracks_reference_style_loop(tmp_path):
         assert torch.equal(fresh.state_dict()[k].cpu(), v.cpu()), k
 
 
+def _param_rel(a, b):
+    num = sum(((p.detach() - q.detach()).float() ** 2).sum() for p, q in zip(a.parameters(), b.parameters()))
+    den = sum((q.detach().float() ** 2).sum() for q in b.parameters())
+    return (num / den).sqrt().item()
+
+
+def test_adamw_step_bookkeeping_is_stream_ordered_and_restorable():
+    """The AdamW step counters / bias corrections live on the device: (a) a host that enqueues many steps without ever
+    synchronising gets the same parameters as one that synchronises after every step (staging them through a pinned
+    buffer did not guarantee that: the host could rewrite it before the copy ran); (b) optimizer.state_dict() ->
+    load_state_dict() into a fresh optimizer continues the run (moments, step counts, device table)."""
+    cfg = dict(dim=128, depth=2, heads=2, mlp_dim=256, num_patches=20, num_vertices=15)
+    torch.manual_seed(21)
+    base = svit.SiT(**cfg).to(DEV)
+    xs = [torch.randn(8, 4, 20, 15, device=DEV) for _ in range(8)]
+    ys = [torch.rand(8, device=DEV) * 19 + 26 for _ in range(8)]
+
+    def run(model, opt, lo, hi, sync):
+        for k in range(lo, hi):
+            opt.zero_grad(set_to_none=True)
+            torch.nn.functional.mse_loss(model(xs[k]).squeeze(), ys[k]).backward()
+            opt.step()
+            if sync:
+                torch.cuda.synchronize()
+
+    models = []
+    for sync in (False, True):
+        m = svit.SiT(**cfg)
+        m.load_state_dict(base.state_dict())
+        m.to(DEV)
+        o = svit.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
+        run(m, o, 0, 8, sync)
+        models.append((m, o))
+    torch.cuda.synchronize()
+    # (at this learning rate two synchronised runs agree to 4e-9 -- fp32 atomics order; at 1e-2 the run is chaotic enough
+    # to amplify that to 1e-4, which says nothing about the optimizer)
+    assert _param_rel(models[0][0], models[1][0]) < 1e-6
+    assert float(models[0][1].state[models[0][0].cls_token]["step"]) == 8.0
+    # (b) resume from a checkpoint taken after 4 steps
+    m1 = svit.SiT(**cfg); m1.load_state_dict(base.state_dict()); m1.to(DEV)
+    o1 = svit.FusedAdamW(m1.parameters(), lr=1e-3, weight_decay=0.0)
+    run(m1, o1, 0, 4, True)
+    ck_m = {k: v.clone() for k, v in m1.state_dict().items()}
+    ck_o = copy.deepcopy(o1.state_dict())
+    m2 = svit.SiT(**cfg); m2.load_state_dict(ck_m); m2.to(DEV)
+    o2 = svit.FusedAdamW(m2.parameters(), lr=1e-3, weight_decay=0.0)
+    o2.load_state_dict(ck_o)
+    run(m2, o2, 4, 8, True)
+    torch.cuda.synchronize()
+    assert _param_rel(m2, models[1][0]) < 1e-6
+    assert float(o2.state[m2.cls_token]["step"]) == 8.0
+
+
+def test_cuda_graph_capture_of_inference_and_training_step():
+    """8(f)-2: the whole step replays from a CUDA graph.  Inference: bit-identical to the eager call.  Training (zero_grad
+    + forward + MSE + backward + FusedAdamW.step in ONE graph): parameters after warm-up + 5 replays on changing batches
+    equal those of the same eager steps (the bias corrections advance on the device inside the graph)."""
+    cfg = dict(dim=192, depth=3, heads=3, mlp_dim=768, num_patches=80, num_vertices=45)
+    torch.manual_seed(22)
+    base = svit.SiT(**cfg).to(DEV)
+    B = 8
+    xs = [torch.randn(B, 4, 80, 45, device=DEV) for _ in range(6)]
+    ys = [torch.rand(B, device=DEV) * 19 + 26 for _ in range(6)]
+    base.eval()
+    with torch.no_grad():
+        want = [base(x).clone() for x in xs[:3]]
+    gi = svit.GraphedInference(base, xs[0])
+    for x, w in zip(xs[:3], want):
+        assert torch.equal(gi(x), w)
+    crit = lambda out, t: torch.nn.functional.mse_loss(out.squeeze(-1), t)   # noqa: E731
+    eager = svit.SiT(**cfg); eager.load_state_dict(base.state_dict()); eager.to(DEV).train()
+    graphed = svit.SiT(**cfg); graphed.load_state_dict(base.state_dict()); graphed.to(DEV).train()
+    oe = svit.FusedAdamW(eager.parameters(), lr=3e-3, weight_decay=0.0)
+    og = svit.FusedAdamW(graphed.parameters(), lr=3e-3, weight_decay=0.0)
+    step = svit.GraphedTrainStep(graphed, og, crit, xs[0], ys[0], warmup=3)    # 3 real warm-up steps on batch 0, then the capture
+    for _ in range(3):
+        oe.zero_grad(set_to_none=True); crit(eager(xs[0]), ys[0]).backward(); oe.step()
+    losses = []
+    for k in range(1, 6):
+        oe.zero_grad(set_to_none=True)
+        le = crit(eager(xs[k]), ys[k]); le.backward(); oe.step()
+        lg = step(xs[k], ys[k])
+        losses.append((le.item(), lg.item()))
+    torch.cuda.synchronize()
+    for le, lg in losses:
+        assert abs(le - lg) / abs(le) < 1e-3, losses
+    assert _param_rel(graphed, eager) < 1e-4
+    assert float(og.state[graphed.cls_token]["step"]) == float(oe.state[eager.cls_token]["step"]) == 8.0
+    og.param_groups[0]["lr"] = 1e-3
+    with pytest.raises(RuntimeError):
+        step(xs[0], ys[0])
+    step.recapture()
+    assert torch.isfinite(step(xs[0], ys[0])).all()
+
+
 # ------------------------------------------------------------------------------------------- dropout > 0 (8(f)-4)
 def _dropout_pair(cfg, p, emb_p, seed, step, check_mode):
     """B200 SiT with dropout and the oracle with MaskedDropout modules applying the very same keep decisions."""
