@@ -385,3 +385,15 @@ def test_dropout_state_follows_module_mode():
     assert plain._next_dropout_state() == (0.0, 0.0, 0, 0) and plain._drop_step == 0
     lib = _lib.load()
     assert lib.svit_set_dropout(m._engine, 1.0, 0.0, 0, 0) != 0 and b"[0, 1)" in lib.svit_last_error()
+
+
+def test_graph_capture_helpers_reject_what_they_cannot_replay():
+    """graphs.py validates before touching the GPU: the DataParallel wrapper, foreign modules and dropout > 0 (whose mask
+    offset is host state that a replay would not advance) are refused."""
+    from surface_vision_transformers_b200 import graphs
+    cfg = dict(dim=128, depth=1, heads=2, mlp_dim=128, num_patches=4, num_vertices=3)
+    assert graphs._check_model(svit.SiT(**cfg)) is not None
+    with pytest.raises(NotImplementedError):
+        graphs._check_model(svit.SiT(**cfg, dropout=0.1))
+    with pytest.raises(TypeError):
+        graphs._check_model(torch.nn.Linear(4, 4))
