@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const bool leader = threadIdx.x == 0;
         const float c = args.scale_log2e;
-        const int split = (tk / 2) & ~31;                 // half 0: columns [0, split), half 1: [split, tk)
+        // half 0: columns [0, split), half 1: [split, tk).  Rounded UP to a 32-column group: the last group of half 1 is the
+        // masked (slower) one, so half 1 gets the smaller share (T = 321: 6 full groups | 4 full + 1 masked)
+        const int split = min(tk, (tk / 2 + 31) & ~31);
         const int col_lo = hf == 0 ? 0 : split;
         const int col_hi = hf == 0 ? split : tk;
 
