@@ -418,6 +418,9 @@ def main():
                     algorithmic_bytes=a_bytes, peak_source=peaks["source"] + " (burst: kernel timed alone)",
                     us_per_launch=a_ms * 1e3, flops_per_launch=a_flops,
                     share_of_step=a_ms * m["depth"] / ms_step,
+                    note="fraction of the dense bf16 tensor peak at the algorithmic flop count; T=%d pads to 128x96 tiles "
+                         "(executed MMA work is 1.6x the algorithmic count at T=321) and the kernel is bound by the "
+                         "softmax / dS warps' issue slots and per-step hand-offs, not by the tensor pipe (DESIGN.md 3a)" % T,
                     step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
                     step_frac_of_nominal_2250=step_tf / 2250.0)
 
