@@ -335,6 +335,8 @@ class SiT(nn.Module):
 
     def forward(self, img):
         img = self._check_input(img)
+        if img.shape[0] == 0:   # an empty batch (e.g. an empty last shard): the reference returns an empty (0, classes) tensor too
+            return img.new_zeros((0, self.num_classes)) + 0.0 * self.mlp_head[1].bias.sum()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
             return _SiTFunction.apply(self, img, *self._plist)
         return self.infer(img)

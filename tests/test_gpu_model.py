@@ -462,6 +462,17 @@ def test_fit_mpp_tracks_reference_style_loop(tmp_path):
         assert torch.equal(fresh.state_dict()[k].cpu(), v.cpu()), k
 
 
+def test_empty_batch_returns_empty_prediction():
+    """B = 0 (an empty last shard of a sampler): like the reference, an empty (0, num_classes) tensor that still
+    back-propagates (zero gradients) instead of an engine error."""
+    model = svit.SiT(dim=128, depth=1, heads=2, mlp_dim=128, num_patches=20, num_vertices=15).to(DEV)
+    out = model(torch.empty(0, 4, 20, 15, device=DEV))
+    assert out.shape == (0, 1) and out.dtype == torch.float32
+    out.sum().backward()
+    with torch.no_grad():
+        assert model.eval()(torch.empty(0, 4, 20, 15, device=DEV)).shape == (0, 1)
+
+
 def _param_rel(a, b):
     num = sum(((p.detach() - q.detach()).float() ** 2).sum() for p, q in zip(a.parameters(), b.parameters()))
     den = sum((q.detach().float() ** 2).sum() for q in b.parameters())
