@@ -201,6 +201,7 @@ class masked_patch_pretraining(nn.Module):
         if masks is None:
             masks = draw_masks(b, n, self.dim_out, batch.device, self.mask_prob, self.replace_prob, self.swap_prob)
         training = torch.is_grad_enabled()
-        loss, out = _MPPFunction.apply(self, batch, masks, training, self.to_original.weight, self.to_original.bias,
-                                       self.mask_token, *t._plist)
+        with torch.cuda.device(batch.device):   # the engine launches on the CURRENT device's stream
+            loss, out = _MPPFunction.apply(self, batch, masks, training, self.to_original.weight, self.to_original.bias,
+                                           self.mask_token, *t._plist)
         return loss, out

@@ -137,11 +137,12 @@ class FusedAdamW(Optimizer):
                     st.seg_dev.copy_(st.seg_pinned)      # synchronous on purpose (rare)
                     st.table_key = key
                 self._note_step(owner, st, active)
-                check(lib.svit_adamw_advance(ptr(st.seg_dev), len(ps), beta1, beta2, stream), "svit_adamw_advance")
-                check(lib.svit_adamw_step(ptr(owner._flat), ptr(G), ptr(st.bufs[0]), ptr(st.bufs[1]), ptr(st.seg_dev),
-                                          len(ps), ptr(st.block_map), st.nblocks, group["lr"], beta1, beta2, group["eps"],
-                                          group["weight_decay"], 1 if group["decoupled"] else 0, self.grad_scale,
-                                          stream), "svit_adamw_step")
+                with torch.cuda.device(dev):   # kernels launch on the current device
+                    check(lib.svit_adamw_advance(ptr(st.seg_dev), len(ps), beta1, beta2, stream), "svit_adamw_advance")
+                    check(lib.svit_adamw_step(ptr(owner._flat), ptr(G), ptr(st.bufs[0]), ptr(st.bufs[1]), ptr(st.seg_dev),
+                                              len(ps), ptr(st.block_map), st.nblocks, group["lr"], beta1, beta2, group["eps"],
+                                              group["weight_decay"], 1 if group["decoupled"] else 0, self.grad_scale,
+                                              stream), "svit_adamw_step")
                 owner.mark_weights_dirty()
             self._generic_adam(group, loose)
         return loss
@@ -262,10 +263,11 @@ class FusedSGD(Optimizer):
                         off, n = owner._offsets[p._svit_index]
                         self.state[p] = {"momentum_buffer": st.bufs[0][off:off + n].view(p.shape)}
                 dev = owner._flat.device
-                check(lib.svit_sgd_step(ptr(owner._flat), ptr(G), ptr(st.bufs[0]), owner._flat.numel(), group["lr"],
-                                        group["momentum"], group["dampening"], group["weight_decay"],
-                                        1 if group["nesterov"] else 0, 1 if first else 0, self.grad_scale,
-                                        vp(torch.cuda.current_stream(dev).cuda_stream)), "svit_sgd_step")
+                with torch.cuda.device(dev):   # kernels launch on the current device
+                    check(lib.svit_sgd_step(ptr(owner._flat), ptr(G), ptr(st.bufs[0]), owner._flat.numel(), group["lr"],
+                                            group["momentum"], group["dampening"], group["weight_decay"],
+                                            1 if group["nesterov"] else 0, 1 if first else 0, self.grad_scale,
+                                            vp(torch.cuda.current_stream(dev).cuda_stream)), "svit_sgd_step")
                 owner.mark_weights_dirty()
             for p in loose:
                 if p.grad is None:

@@ -337,9 +337,10 @@ class SiT(nn.Module):
         img = self._check_input(img)
         if img.shape[0] == 0:   # an empty batch (e.g. an empty last shard): the reference returns an empty (0, classes) tensor too
             return img.new_zeros((0, self.num_classes)) + 0.0 * self.mlp_head[1].bias.sum()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
-            return _SiTFunction.apply(self, img, *self._plist)
-        return self.infer(img)
+        with torch.cuda.device(img.device):   # the engine launches on the CURRENT device's stream
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
+                return _SiTFunction.apply(self, img, *self._plist)
+            return self.infer(img)
 
     @torch.no_grad()
     def infer(self, img, table=None, n_mesh=0, ch_mean=None, ch_std=None):
@@ -359,15 +360,17 @@ class SiT(nn.Module):
         """raw ico-6 mesh (B,C,40962) + gather table (V,N) int32 -> prediction; the patch gather
         (tools/preprocessing.py:79-84) and optional z-score (:72) are fused into the patch packing kernel."""
         mesh = mesh.contiguous().float()
-        return self.infer(mesh, table=table.contiguous(), n_mesh=mesh.shape[-1], ch_mean=ch_mean, ch_std=ch_std)
+        with torch.cuda.device(mesh.device):
+            return self.infer(mesh, table=table.contiguous(), n_mesh=mesh.shape[-1], ch_mean=ch_mean, ch_std=ch_std)
 
     def _encoder(self, x):
         if not x.is_cuda:
             raise RuntimeError("SiT.transformer (B200) needs a CUDA input: there is no CPU fallback")
         x = x.contiguous().float()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._plist)):
-            return _EncoderFunction.apply(self, x, *self._plist)
-        with torch.no_grad():
+            with torch.cuda.device(x.device):
+                return _EncoderFunction.apply(self, x, *self._plist)
+        with torch.no_grad(), torch.cuda.device(x.device):
             B, dev = x.shape[0], x.device
             self._refresh_shadow(dev)
             lib = _lib.load()
