@@ -44,9 +44,14 @@ class GraphedInference:
             for _ in range(warmup):
                 model(self.x)
         torch.cuda.current_stream(self.x.device).wait_stream(side)
+        # capture the bf16 weight-shadow refresh with the pass: a replay then always reads the CURRENT fp32 weights (a graph
+        # captured over clean shadows would keep using them after the weights were trained or reloaded)
+        core = model if isinstance(model, SiT) else model.transformer
+        core.mark_weights_dirty()
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.y = model(self.x)
+        core.mark_weights_dirty()
 
     def __call__(self, x):
         self.x.copy_(x, non_blocking=True)

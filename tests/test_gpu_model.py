@@ -542,6 +542,11 @@ def test_cuda_graph_capture_of_inference_and_training_step():
     gi = svit.GraphedInference(base, xs[0])
     for x, w in zip(xs[:3], want):
         assert torch.equal(gi(x), w)
+    with torch.no_grad():                      # the graph re-derives the weight shadows: it follows weight updates
+        base.mlp_head[1].bias.add_(1.0)
+        base.transformer.layers[0][1].fn.net[0].weight.mul_(1.5)
+        base.mark_weights_dirty()
+        assert torch.equal(gi(xs[1]), base(xs[1])) and not torch.equal(gi(xs[1]), want[1])
     crit = lambda out, t: torch.nn.functional.mse_loss(out.squeeze(-1), t)   # noqa: E731
     eager = svit.SiT(**cfg); eager.load_state_dict(base.state_dict()); eager.to(DEV).train()
     graphed = svit.SiT(**cfg); graphed.load_state_dict(base.state_dict()); graphed.to(DEV).train()
