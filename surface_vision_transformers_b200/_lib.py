@@ -73,9 +73,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path) or (os.environ.get("SVIT_REBUILD") == "1"):
-        path = _build.build()
+    # a library that is stale relative to csrc/ or include/ is rebuilt, never loaded silently
+    path = _build.build(force=os.environ.get("SVIT_REBUILD") == "1")
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly

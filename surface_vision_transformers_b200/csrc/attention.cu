@@ -18,37 +18,41 @@ constexpr int TILE_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 // =================================================================================================
 // forward
 // =================================================================================================
-// One CTA per (sample, head); K and V (<= 384 keys) stay in shared memory, Q blocks of 128 rows stream through.
-// TMEM reads cost 64 B/clk/SM, as much as the exponentials themselves, so the scores are read ONCE: the softmax
-// shift is the row's score against key 0 (any shift is exact for softmax; the log-sum-exp is reported with the same
-// shift), and a guard on the row sum falls back to the classic max-shift pass in the (never observed) overflow case.
-// 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the key columns.
+// One CTA per (sample, head), TWO CTAs resident per SM.  K and V (<= 384 keys) stay in shared memory, Q blocks of 128
+// rows stream through.  What one CTA cannot overlap -- the S = Q K^T MMAs, the exponentials and the P V MMAs of a
+// query block form a dependent chain, and the load / store latencies of a block sit in front of and behind it -- the
+// second CTA on the SM fills: its softmax warps run while this one's tensor work, TMA loads or output stores are in
+// flight.  Two CTAs need half the TMEM and half the shared memory each, which is what shapes the kernel:
+//   * the keys of a query block are processed in two halves (<= 192 score columns each): S_h [0,192) + O [192,256) = 256
+//     TMEM columns per CTA;
+//   * shared memory holds exactly the padded keys (tk = T rounded up to 16 rows) and one Q tile; O leaves straight from
+//     registers (64 contiguous bytes per thread and block -- tiny next to the operand streams), so Q(i+1) can land while
+//     block i is still in its second half.
+// The scores are read from TMEM ONCE: the softmax shift is the row's score against key 0 (any shift is exact for
+// softmax; the log-sum-exp is reported with the same shift), which also makes the two key halves independent -- no
+// running maximum, no rescaling of O.  A guard on the row sum (it cannot underflow: key 0 contributes exp2(0) = 1)
+// detects overflow after the second half; the block is then redone with the classic max shift ("safe mode": max over
+// both halves first, then the exponentials).
+// 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the columns of the current key half.
 // P never touches shared memory: the bf16 probabilities are written back into TMEM over the consumed scores
-// (tcgen05.st, two per 32-bit column) and feed the PV product as the A operand FROM TMEM -- no STS / proxy fence in the
-// softmax (LSU shared-memory traffic crawls while the tensor core streams operands) and no A fetch for the PV MMAs.
-// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sO 16K | row sums / maxima | barriers   (~130 KB)
-constexpr int FWD_SQ = 0;
-constexpr int FWD_SK = FWD_SQ + TILE_BYTES;
-constexpr int FWD_SV = FWD_SK + 3 * TILE_BYTES;
-constexpr int FWD_SO = FWD_SV + 3 * TILE_BYTES;
-constexpr int FWD_RED = FWD_SO + TILE_BYTES;      // float [2][128]
-constexpr int FWD_BAR = FWD_RED + 2 * 128 * 4;
-constexpr int FWD_SMEM = 1024 + FWD_BAR + 128;
+// (tcgen05.st, two per 32-bit column) and feed the PV product as the A operand FROM TMEM.
+// shared memory map (bytes):  sQ 16K | sK tk*128 | sV tk*128 | row sums / maxima 1K | barriers   (T = 321: 102 KB)
 constexpr int FWD_THREADS = 288;
-constexpr int FWD_TMEM_O = 384;  // O accumulator columns [384, 448)
+constexpr int FWD_TMEM_COLS = 256;
+constexpr int FWD_TMEM_O = 192;  // O accumulator columns [192, 256)
+constexpr int FWD_HALF_MAX = 192;
+
+__host__ __device__ constexpr int fwd_smem_bytes(int tk) { return 1024 + TILE_BYTES + 2 * tk * 128 + 2 * 128 * 4 + 256; }
 
 struct AttnFwdArgs {
-    CUtensorMap tmQKV;  // (3*inner, T, B) bf16, box 64 x 128 x 1
-    CUtensorMap tmO;    // (inner, T, B) bf16, box 64 x 128 x 1
+    CUtensorMap tmQ;   // qkv (3*inner, T, B) bf16, box 64 x 128 x 1: Q_i loads
+    CUtensorMap tmKV;  // qkv                      box 64 x kv_box x 1: K / V loads (kv_box divides the padded key count)
+    __nv_bfloat16* out;  // [B, T, inner]
     float* lse;
     int B, H, T;
+    int kv_box;
     float scale, scale_log2e;
-    int debug;  // SVIT_ATTN_DEBUG: 8 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
 };
-
-// clock64 timeline of one CTA for scripts/prof_attn_*.py; costs nothing unless enabled
-__device__ long long g_attn_prof[256];
-#define PROFF(slot) do { if ((args.debug & 8) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
 
 // 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial for 2^f on [-0.5, 0.5], max relative error
 // 7.6e-5 -- far below the bf16 rounding of the probabilities): every fourth exponential of the forward pass takes this
@@ -68,15 +72,425 @@ __device__ __forceinline__ float fwd_ex2(float x) {
     return r;
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs args) {
+__global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem + FWD_SQ;
-    uint8_t* sK = smem + FWD_SK;
-    uint8_t* sV = smem + FWD_SV;
-    uint8_t* sO = smem + FWD_SO;
-    float* sRed = reinterpret_cast<float*>(smem + FWD_RED);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
+    const int T = args.T, H = args.H;
+    const int inner = H * 64;
+    const int tk = (T + 15) & ~15;  // keys padded to the UMMA K step
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;
+    uint8_t* sV = sK + tk * 128;
+    float* sRed = reinterpret_cast<float*>(sV + tk * 128);  // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 256);
+    uint64_t* bar_k = bars + 0;    // K landed                                   (TMA -> control)
+    uint64_t* bar_vv = bars + 1;   // V landed                                   (TMA -> control)
+    uint64_t* bar_q = bars + 2;    // Q_i landed                                 (TMA -> control)
+    uint64_t* bar_s = bars + 3;    // scores of a key half in TMEM               (MMA -> softmax, control)
+    uint64_t* bar_p = bars + 4;    // P of a key half in TMEM / scores consumed  (softmax -> control)
+    uint64_t* bar_pv = bars + 5;   // PV of the first half retired: the score columns may be overwritten (MMA -> control)
+    uint64_t* bar_o = bars + 6;    // every MMA of the block retired             (MMA -> softmax, control)
+    uint64_t* bar_of = bars + 7;   // O copied to registers                      (softmax -> control)
+    uint64_t* bar_v = bars + 8;    // verdict of the block published in *flag    (softmax -> control)
+    uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 9);
+    uint32_t* tmem_slot = flag + 1;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x / H;
+    const int h = blockIdx.x % H;
+    const int nqb = (T + 127) / 128;  // query blocks
+    // key halves: one when the padded keys fit the score columns, else two (both multiples of 16, both <= 192)
+    const int n0 = tk <= FWD_HALF_MAX ? tk : ((tk >> 1) + 15) & ~15;
+    const int n1 = tk - n0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&args.tmQ);
+        tma_prefetch_desc(&args.tmKV);
+        mbar_init(bar_k, 1);
+        mbar_init(bar_vv, 1);
+        mbar_init(bar_q, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, 8);
+        mbar_init(bar_pv, 1);
+        mbar_init(bar_o, 1);
+        mbar_init(bar_of, 8);
+        mbar_init(bar_v, 8);
+        *flag = 0;
+        fence_mbar_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, FWD_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ============================ control: TMA + MMA issue ============================
+        if (elect_one()) {
+            const int nbox = tk / args.kv_box;
+            mbar_expect_tx(bar_k, tk * 128);
+            for (int r = 0; r < nbox; ++r)
+                tma_load_3d(sK + r * args.kv_box * 128, &args.tmKV, bar_k, inner + h * 64, r * args.kv_box, b);
+            mbar_expect_tx(bar_q, TILE_BYTES);
+            tma_load_3d(sQ, &args.tmQ, bar_q, h * 64, 0, b);
+            mbar_expect_tx(bar_vv, tk * 128);
+            for (int r = 0; r < nbox; ++r)
+                tma_load_3d(sV + r * args.kv_box * 128, &args.tmKV, bar_vv, 2 * inner + h * 64, r * args.kv_box, b);
+            const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            uint32_t ph_q = 0, ph_p = 0, ph_pv = 0, ph_o = 0, ph_of = 0, ph_v = 0;
+            uint32_t s_cnt = 0;  // score batches issued so far: batch c completes phase parity c & 1 of bar_s
+            // S = Q K_h^T (K-major A and B) into the score columns
+            auto issue_s = [&](int key0, int nh) {
+                const uint32_t idesc = umma_idesc_bf16(128, nh, 0, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_ss(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024),
+                            umma_smem_desc(k_addr + key0 * 128 + k * 32, 16, 1024), idesc, k != 0);
+                umma_commit(bar_s);
+                ++s_cnt;
+            };
+            // O (+)= P_h V_h  (A = P from TMEM: lanes = query rows, 8 columns of packed bf16 pairs per 16-key step; B = V MN-major)
+            auto issue_pv = [&](int key0, int nh, bool acc) {
+                const int ks = nh >> 4;
+                for (int s = 0; s < ks; ++s)
+                    umma_ts(tmem_base + FWD_TMEM_O, tmem_base + s * 8,
+                            umma_smem_desc(v_addr + ((key0 >> 4) + s) * 2048, 8192, 1024), idesc_pv, (acc || s != 0) ? 1u : 0u);
+            };
+            auto load_q = [&](int i) {
+                mbar_expect_tx(bar_q, TILE_BYTES);
+                tma_load_3d(sQ, &args.tmQ, bar_q, h * 64, i * 128, b);
+            };
+            auto wait_last_s = [&]() { mbar_wait(bar_s, (s_cnt - 1) & 1); };
+            mbar_wait(bar_k, 0);
+            for (int i = 0; i < nqb; ++i) {
+                mbar_wait(bar_q, ph_q);
+                ph_q ^= 1;
+                tc_fence_after();
+                issue_s(0, n0);
+                if (n1 == 0) {
+                    wait_last_s();  // sQ is dead: the next block's queries may land
+                    if (i + 1 < nqb) load_q(i + 1);
+                }
+                mbar_wait(bar_p, ph_p);
+                ph_p ^= 1;
+                if (i > 0) {
+                    mbar_wait(bar_of, ph_of);  // the previous block's O left TMEM
+                    ph_of ^= 1;
+                } else {
+                    mbar_wait(bar_vv, 0);
+                }
+                tc_fence_after();
+                issue_pv(0, n0, false);
+                if (n1 > 0) {
+                    umma_commit(bar_pv);
+                    mbar_wait(bar_pv, ph_pv);  // P_h0 consumed: the score columns are free again
+                    ph_pv ^= 1;
+                    tc_fence_after();
+                    issue_s(n0, n1);
+                    wait_last_s();
+                    if (i + 1 < nqb) load_q(i + 1);
+                    mbar_wait(bar_p, ph_p);
+                    ph_p ^= 1;
+                    tc_fence_after();
+                    issue_pv(n0, n1, true);
+                }
+                umma_commit(bar_o);
+                mbar_wait(bar_o, ph_o);
+                ph_o ^= 1;
+                mbar_wait(bar_v, ph_v);
+                ph_v ^= 1;
+                if (*reinterpret_cast<volatile uint32_t*>(flag) != 0) {
+                    // ---- safe mode: redo block i with the max shift (see the softmax warps) ----
+                    if (i + 1 < nqb) {
+                        mbar_wait(bar_q, ph_q);  // the prefetched Q_{i+1} has landed; Q_i comes back first
+                        ph_q ^= 1;
+                    }
+                    if (nqb > 1) {
+                        load_q(i);
+                        mbar_wait(bar_q, ph_q);
+                        ph_q ^= 1;
+                    }
+                    tc_fence_after();
+                    issue_s(0, n0);  // maxima of half 0
+                    if (n1 > 0) {
+                        mbar_wait(bar_p, ph_p);
+                        ph_p ^= 1;
+                        tc_fence_after();
+                        issue_s(n0, n1);  // maxima of half 1, then its exponentials
+                        mbar_wait(bar_p, ph_p);
+                        ph_p ^= 1;
+                        tc_fence_after();
+                        issue_pv(n0, n1, false);
+                        umma_commit(bar_pv);
+                        mbar_wait(bar_pv, ph_pv);
+                        ph_pv ^= 1;
+                        tc_fence_after();
+                        issue_s(0, n0);  // half 0 again, now for its exponentials
+                        wait_last_s();
+                        if (i + 1 < nqb) load_q(i + 1);
+                        mbar_wait(bar_p, ph_p);
+                        ph_p ^= 1;
+                        tc_fence_after();
+                        issue_pv(0, n0, true);
+                    } else {
+                        wait_last_s();
+                        if (i + 1 < nqb) load_q(i + 1);
+                        mbar_wait(bar_p, ph_p);
+                        ph_p ^= 1;
+                        tc_fence_after();
+                        issue_pv(0, n0, false);
+                    }
+                    umma_commit(bar_o);
+                    mbar_wait(bar_o, ph_o);
+                    ph_o ^= 1;
+                }
+            }
+        }
+    } else {
+        // ============================ softmax + epilogue warps ============================
+        const int q = warp & 3;    // TMEM lane quadrant
+        const int hf = warp >> 2;  // column half within the current key half
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const float c = args.scale_log2e;
+        uint32_t ph_s = 0, ph_o = 0;
+        // the two warps of a quadrant (same TMEM lanes, complementary columns) synchronise among themselves
+        // (constant barrier ids: with a run-time id ptxas reserves all 16 named barriers and only one CTA fits an SM)
+        auto quadbar = [&]() {
+            tc_fence_before();
+            if (q == 0) named_bar_sync(1, 64);
+            else if (q == 1) named_bar_sync(2, 64);
+            else if (q == 2) named_bar_sync(3, 64);
+            else named_bar_sync(4, 64);
+            tc_fence_after();
+        };
+        // this warp's columns [lo, hi) of a key half with nh columns: half 0 gets the share rounded UP to a 32-column group,
+        // so that the (slower) masked tail group falls to half 1, which has fewer columns
+        auto col_range = [&](int nh, int& lo, int& hi) {
+            const int split = min(nh, (((nh + 1) >> 1) + 31) & ~31);
+            lo = hf == 0 ? 0 : split;
+            hi = hf == 0 ? split : nh;
+        };
+
+        // exp2((s - shift) * c) of this thread's columns of the key half [key0, key0 + nh) -> packed bf16 pairs in registers
+        // (up to 3 groups of 32 columns); returns the partial row sum.  Columns past the half or past T give exact zeros.
+        uint32_t pk[48];
+        auto softmax_pass = [&](int key0, int nh, float shift_c) {
+            int lo, hi;
+            col_range(nh, lo, hi);
+            float sm0 = 0.0f, sm1 = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const int c0 = lo + g * 32;
+                if (c0 < hi) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + c0, r);
+                    tmem_ld_wait();
+                    const int nv = min(hi, T - key0) - c0;  // real keys among the 32 columns of this group
+                    if (nv >= 32) {
+                        // The row sum adds the fp32 probabilities (their bf16 rounding in the PV product is unbiased; the
+                        // difference is ~1e-4 relative, far below bf16 resolution)
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            const float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
+                            const float x1 = fmaf(__uint_as_float(r[e + 1]), c, -shift_c);
+                            const float p1 = ((e >> 1) & 1) ? fwd_ex2_poly(x1) : fwd_ex2(x1);  // every 4th on the FMA pipe
+                            pk[g * 16 + e / 2] = pack_bf16(p0, p1);
+                            sm0 += p0;
+                            sm1 += p1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
+                            float p1 = fwd_ex2(fmaf(__uint_as_float(r[e + 1]), c, -shift_c));
+                            if (e >= nv) p0 = 0.0f;
+                            if (e + 1 >= nv) p1 = 0.0f;
+                            pk[g * 16 + e / 2] = pack_bf16(p0, p1);
+                            sm0 += p0;
+                            sm1 += p1;
+                        }
+                    }
+                }
+            }
+            return sm0 + sm1;
+        };
+        auto max_pass = [&](int key0, int nh) {
+            int lo, hi;
+            col_range(nh, lo, hi);
+            float mx = -INFINITY;
+            for (int c0 = lo; c0 < hi; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_wait();
+                const int nv = min(hi, T - key0) - c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) mx = fmaxf(mx, __uint_as_float(r[j]));
+            }
+            return mx;
+        };
+        // packed P -> TMEM, in place over the scores: the pair (2k, 2k+1) of S columns lands in column k.  The partner
+        // warp of the quadrant reads score columns that these stores overwrite, hence the pair barrier first.
+        auto store_p = [&](int nh) {
+            int lo, hi;
+            col_range(nh, lo, hi);
+            quadbar();
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const int c0 = lo + g * 32;
+                if (c0 < hi) tmem_st_32x16(t_row + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(&pk[g * 16]));
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive_warp(bar_p);
+        };
+        // the two warps of a quadrant hold complementary columns of the same rows
+        auto pair_exchange = [&](float mine, bool is_max) {
+            sRed[hf * 128 + row] = mine;
+            quadbar();
+            const float a = sRed[row], bb = sRed[128 + row];
+            quadbar();
+            return is_max ? fmaxf(a, bb) : a + bb;
+        };
+
+        for (int i = 0; i < nqb; ++i) {
+            // Normal mode: one pass per key half, shift = the row's score against key 0.  Safe mode (after an overflowing
+            // row sum; uniform for the CTA, the control warp replays the MMAs): maxima of half 0 and half 1 first, then
+            // the exponentials of half 1 (still in TMEM) and of half 0 (recomputed) with the max shift.
+            const int nhalves = n1 > 0 ? 2 : 1;
+            float shift = 0.0f, total = 0.0f;
+            bool safe = false;
+#pragma unroll 1
+            for (;;) {
+                if (safe) {
+                    float mx = -INFINITY;
+#pragma unroll 1
+                    for (int k = 0; k < nhalves; ++k) {
+                        mbar_wait(bar_s, ph_s);
+                        ph_s ^= 1;
+                        tc_fence_after();
+                        mx = fmaxf(mx, max_pass(k == 0 ? 0 : n0, k == 0 ? n0 : n1));
+                        if (k + 1 < nhalves) {
+                            tc_fence_before();
+                            mbar_arrive_warp(bar_p);  // half 0 read: the score columns may take half 1
+                        }
+                    }
+                    shift = pair_exchange(mx, true);
+                }
+                float part = 0.0f;
+#pragma unroll 1
+                for (int k = 0; k < nhalves; ++k) {
+                    const int half = (safe && nhalves == 2) ? 1 - k : k;
+                    if (!(safe && k == 0)) {  // (in safe mode the first half to exponentiate is already in TMEM)
+                        mbar_wait(bar_s, ph_s);
+                        ph_s ^= 1;
+                        tc_fence_after();
+                    }
+                    if (!safe && k == 0) {
+                        shift = __uint_as_float(tmem_ld_32x1(t_row));  // score against key 0
+                        tmem_ld_wait();
+                    }
+                    part += softmax_pass(half == 0 ? 0 : n0, half == 0 ? n0 : n1, shift * c);
+                    store_p(half == 0 ? n0 : n1);
+                }
+                total = pair_exchange(part, false);
+                if (safe) break;
+                // The row sum cannot underflow (key 0 contributes exp2(0) = 1), so "not < 1e30" (overflow, inf or NaN) is
+                // the whole test; the verdict is uniform for the CTA and published to the control warp.
+                const bool bad = named_bar_or(5, 256, !(total < 1e30f));
+                if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(flag) = bad ? 1u : 0u;
+                mbar_arrive_warp(bar_v);
+                if (!bad) break;
+                mbar_wait(bar_o, ph_o);  // the failed attempt's MMAs have retired
+                ph_o ^= 1;
+                safe = true;
+            }
+            mbar_wait(bar_o, ph_o);
+            ph_o ^= 1;
+            // ---- epilogue: O / sum -> bf16 -> global, straight from registers (each half converts 32 of the 64 columns) ----
+            tc_fence_after();
+            uint32_t o0[32];
+            tmem_ld_32x32(t_row + FWD_TMEM_O + hf * 32, o0);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_warp(bar_of);
+            const float inv = 1.0f / total;
+            const int t = i * 128 + row;
+            if (t < T) {
+                uint4* dst = reinterpret_cast<uint4*>(args.out + (static_cast<size_t>(b) * T + t) * inner + h * 64 + hf * 32);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t* src = &o0[g * 8];
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+                    o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+                    o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+                    o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+                    dst[g] = o;
+                }
+                if (hf == 0) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = shift * args.scale + logf(total);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, FWD_TMEM_COLS);
+    }
+}
+
+// =================================================================================================
+// forward v1 (one CTA per SM; kept for A/B timing, SVIT_ATTN_FWD_V1=1)
+// =================================================================================================
+// One CTA per (sample, head); K and V (<= 384 keys) stay in shared memory, Q blocks of 128 rows stream through.
+// TMEM reads cost 64 B/clk/SM, as much as the exponentials themselves, so the scores are read ONCE: the softmax
+// shift is the row's score against key 0 (any shift is exact for softmax; the log-sum-exp is reported with the same
+// shift), and a guard on the row sum falls back to the classic max-shift pass in the (never observed) overflow case.
+// 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the key columns.
+// P never touches shared memory: the bf16 probabilities are written back into TMEM over the consumed scores
+// (tcgen05.st, two per 32-bit column) and feed the PV product as the A operand FROM TMEM -- no STS / proxy fence in the
+// softmax (LSU shared-memory traffic crawls while the tensor core streams operands) and no A fetch for the PV MMAs.
+// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sO 16K | row sums / maxima | barriers   (~130 KB)
+constexpr int FW1_SQ = 0;
+constexpr int FW1_SK = FW1_SQ + TILE_BYTES;
+constexpr int FW1_SV = FW1_SK + 3 * TILE_BYTES;
+constexpr int FW1_SO = FW1_SV + 3 * TILE_BYTES;
+constexpr int FW1_RED = FW1_SO + TILE_BYTES;      // float [2][128]
+constexpr int FW1_BAR = FW1_RED + 2 * 128 * 4;
+constexpr int FW1_SMEM = 1024 + FW1_BAR + 128;
+constexpr int FW1_THREADS = 288;
+constexpr int FW1_TMEM_O = 384;  // O accumulator columns [384, 448)
+
+struct AttnFwdV1Args {
+    CUtensorMap tmQKV;  // (3*inner, T, B) bf16, box 64 x 128 x 1
+    CUtensorMap tmO;    // (inner, T, B) bf16, box 64 x 128 x 1
+    float* lse;
+    int B, H, T;
+    float scale, scale_log2e;
+    int debug;  // SVIT_ATTN_DEBUG: 8 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
+};
+
+// clock64 timeline of one CTA for scripts/prof_attn_*.py; costs nothing unless enabled
+__device__ long long g_attn_prof[256];
+#define PROFF(slot) do { if ((args.debug & 8) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
+
+
+__global__ void __launch_bounds__(FW1_THREADS, 1) attn_fwd_v1_kernel(const __grid_constant__ AttnFwdV1Args args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + FW1_SQ;
+    uint8_t* sK = smem + FW1_SK;
+    uint8_t* sV = smem + FW1_SV;
+    uint8_t* sO = smem + FW1_SO;
+    float* sRed = reinterpret_cast<float*>(smem + FW1_RED);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FW1_BAR);
     uint64_t* bar_kv = bars + 0;
     uint64_t* bar_q = bars + 1;
     uint64_t* bar_s = bars + 2;
@@ -161,7 +575,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 // O = P V  (A = P from TMEM: lanes = query rows, 8 columns of packed bf16 pairs per 16-key step; B = V MN-major)
                 const int ksteps = tk / 16;
                 for (int s = 0; s < ksteps; ++s)
-                    umma_ts(tmem_base + FWD_TMEM_O, tmem_base + s * 8, umma_smem_desc(v_addr + s * 2048, 8192, 1024), idesc_pv,
+                    umma_ts(tmem_base + FW1_TMEM_O, tmem_base + s * 8, umma_smem_desc(v_addr + s * 2048, 8192, 1024), idesc_pv,
                             s != 0);
                 umma_commit(bar_o);
                 PROFF(13 + i * 10);
@@ -279,7 +693,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             tc_fence_after();
             const float inv = 1.0f / total;
             uint32_t o0[32];
-            tmem_ld_32x32(t_row + FWD_TMEM_O + hf * 32, o0);
+            tmem_ld_32x32(t_row + FW1_TMEM_O + hf * 32, o0);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive_warp(bar_of);
@@ -866,19 +1280,18 @@ static int check_attn_shape(int B, int H, int T) {
     return 0;
 }
 
-int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
-    if (check_attn_shape(d.B, d.H, d.T)) return -1;
+static int launch_attn_fwd_v1(const AttnDesc& d, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW1_SMEM);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(attn_fwd) failed: %s", cudaGetErrorString(e));
+            set_error("cudaFuncSetAttribute(attn_fwd_v1) failed: %s", cudaGetErrorString(e));
             return -10;
         }
         configured = true;
     }
     const int inner = d.H * 64;
-    AttnFwdArgs a;
+    AttnFwdV1Args a;
     memset(&a, 0, sizeof(a));
     int rc = 0;
     rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
@@ -899,7 +1312,59 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
         static const char* dbg = getenv("SVIT_ATTN_DEBUG");
         a.debug = dbg ? atoi(dbg) : 0;
     }
-    attn_fwd_kernel<<<d.B * d.H, FWD_THREADS, FWD_SMEM, stream>>>(a);
+    attn_fwd_v1_kernel<<<d.B * d.H, FW1_THREADS, FW1_SMEM, stream>>>(a);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attn_fwd launch failed: %s", cudaGetErrorString(e));
+        return -11;
+    }
+    return 0;
+}
+
+int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
+    if (check_attn_shape(d.B, d.H, d.T)) return -1;
+    static const bool use_v1 = getenv("SVIT_ATTN_FWD_V1") != nullptr && atoi(getenv("SVIT_ATTN_FWD_V1")) != 0;
+    if (use_v1) return launch_attn_fwd_v1(d, stream);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(ATT_MAX_T));
+        if (e == cudaSuccess)  // two CTAs per SM need (nearly) the whole shared-memory carve-out
+            e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_fwd) failed: %s", cudaGetErrorString(e));
+            return -10;
+        }
+        configured = true;
+    }
+    const int inner = d.H * 64;
+    const int tk = (d.T + 15) & ~15;
+    // K / V arrive in equal boxes of kv_box rows (<= 256, a multiple of 16) that tile the padded key count exactly
+    int nbox = (tk + 255) / 256;
+    while ((tk / 16) % nbox != 0) ++nbox;
+    AttnFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kv_box = tk / nbox;
+    const uint64_t p_row = (uint64_t)3 * inner * 2;
+    int rc = 0;
+    rc |= make_tmap_3d(&a.tmQ, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_row, (uint64_t)d.T * p_row, 64, 128);
+    rc |= make_tmap_3d(&a.tmKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, p_row, (uint64_t)d.T * p_row, 64, a.kv_box);
+    if (rc) {
+        set_error("attn_fwd: tensor map creation failed: %s", tmap_last_error());
+        return -3;
+    }
+    if (reinterpret_cast<uintptr_t>(d.out) & 15) {
+        set_error("attn_fwd: the output must be 16-byte aligned");
+        return -2;
+    }
+    a.out = reinterpret_cast<__nv_bfloat16*>(d.out);
+    a.lse = d.lse;
+    a.B = d.B;
+    a.H = d.H;
+    a.T = d.T;
+    a.scale = d.scale;
+    a.scale_log2e = d.scale * 1.4426950408889634f;
+    attn_fwd_kernel<<<d.B * d.H, FWD_THREADS, fwd_smem_bytes(tk), stream>>>(a);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -5,6 +5,7 @@
 // forward and backward.  See gemm.cuh for the two entry points.
 #include "gemm.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -24,9 +25,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_last_error; }
-static unsigned long long g_launches = 0;
-void count_launch(int n) { g_launches += n; }
-unsigned long long launch_count() { return g_launches; }
+// incremented from the forward and the autograd (backward) host threads
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
 // exact (erf) GELU, as nn.GELU() in the reference FeedForward.

@@ -16,7 +16,17 @@ import torch
 
 from .gather import gather_patches, preprocessing_layout
 
-__all__ = ["preprocess_meshes", "PatchedNpyDataset"]
+__all__ = ["preprocess_meshes", "PatchedNpyDataset", "shard_order"]
+
+
+def shard_order(n, shuffle, generator, rank, world, equal_shards):
+    """Sample indices of rank ``rank`` for one pass over ``n`` samples (host logic, no CUDA)."""
+    order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+    if equal_shards and world > 1 and n % world != 0 and n > 0:
+        pad = world - n % world
+        reps = (pad + n - 1) // n
+        order = torch.cat([order] + [order] * reps)[: n + pad]       # wrap around, like DistributedSampler
+    return order[rank::world]
 
 
 def preprocess_meshes(hemis, means, stds, table):
@@ -53,12 +63,16 @@ class PatchedNpyDataset:
     def shape(self):
         return tuple(self.data.shape)
 
-    def batches(self, batch_size, shuffle=False, generator=None, drop_last=False, rank=0, world=1):
+    def batches(self, batch_size, shuffle=False, generator=None, drop_last=False, rank=0, world=1, equal_shards=None):
         """Yields (x, y) host batches.  With shuffle, a permutation drawn from ``generator`` (same on every rank) is
-        split into per-rank strided slices, so the ranks of a data-parallel job see disjoint samples."""
-        n = len(self)
-        order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
-        order = order[rank::world]
+        split into per-rank strided slices, so the ranks of a data-parallel job see disjoint samples.
+
+        ``equal_shards`` (default: ``shuffle``, i.e. on for training passes): the permutation is padded by wrapping
+        around to a multiple of ``world`` (as torch's DistributedSampler does), so that every rank yields the SAME
+        number of batches with the SAME sizes.  A training pass needs that: every batch ends in gradient all-reduces,
+        and a rank with one batch more (or a ragged last batch of another size) would hang or bias the average.
+        Evaluation passes (no per-batch collective) keep the exact, un-padded split."""
+        order = shard_order(len(self), shuffle, generator, rank, world, shuffle if equal_shards is None else equal_shards)
         pinned = self.data.is_pinned()
         for i in range(0, order.numel(), batch_size):
             idx = order[i:i + batch_size]

@@ -21,18 +21,22 @@ class FlatGradReducer:
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.pending = []
+        # NCCL averages inside the collective (ReduceOp.AVG): no separate scaling launches after the all-reduce.
+        # Other backends (gloo in the CPU tests) sum and scale.
+        self.native_avg = average and dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
     def reduce_range(self, G, start, numel):
         if self.world == 1 or numel == 0:
             return
         seg = G[start:start + numel]
-        work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
+        work = dist.all_reduce(seg, op=op, group=self.pg, async_op=True)
         self.pending.append((work, seg))
 
     def finish(self):
         for work, seg in self.pending:
             work.wait()
-            if self.average:
+            if self.average and not self.native_avg:
                 seg.mul_(1.0 / self.world)
         self.pending = []
 
@@ -62,6 +66,9 @@ class DataParallel(torch.nn.Module):
     def _on_stage(self, sit, stage, G):
         if stage is None:
             self.reducer.finish()
+            return
+        if stage == "all":
+            self.reducer.reduce_range(G, 0, G.numel())
             return
         start, numel = sit.stage_segment(stage)
         self.reducer.reduce_range(G, start, numel)

@@ -6,6 +6,7 @@ The masks are drawn on the host side with exactly the reference's torch RNG call
 corruption while packing the patch-embedding operand, runs the encoder, the decoder GEMM and the masked L2 loss.
 """
 import math
+import weakref
 
 import torch
 from torch import nn
@@ -66,8 +67,9 @@ class _MPPFunction(torch.autograd.Function):
     def forward(ctx, module, batch, masks, training, to_w, to_b, mask_token, *params):
         model = module.transformer
         B, dev = batch.shape[0], batch.device
-        model._refresh_shadow(dev)
-        module._refresh_shadow(dev)
+        model._refresh_shadow(dev, force=bool(training))
+        module._refresh_shadow(dev, force=bool(training))
+        ctx.shadow_gen = model._shadow_gen
         lib = _lib.load()
         mask, swap_sel, swap_src, replace_sel = masks
         mask8, swap8, repl8 = _u8(mask), _u8(swap_sel), _u8(replace_sel)
@@ -102,6 +104,7 @@ class _MPPFunction(torch.autograd.Function):
         model = module.transformer
         lib = _lib.load()
         batch, out_full, mask8, repl8, count = ctx.saved_tensors
+        model._check_shadow_gen(ctx.shadow_gen)
         coef = (dloss.float() * 2.0 / count).reshape(()).contiguous()
         G = torch.zeros_like(model._flat)
         MG = torch.zeros_like(module._flat)
@@ -159,12 +162,18 @@ class masked_patch_pretraining(nn.Module):
         dev = self.to_original.weight.device if len(devs) > 1 else devs.pop()
         flat = torch.zeros(K * D + 2 * K, dtype=torch.float32, device=dev)
         off = 0
-        for p in ps:
+        self._offsets = []
+        for i, p in enumerate(ps):
             n = p.numel()
             v = flat[off:off + n].view(p.shape)
             v.copy_(p.data.to(device=dev, dtype=torch.float32))
             p.data = v
+            # the fused optimizers (optim.py) update parameters that name their flat owner with ONE kernel launch
+            p._svit_owner = weakref.ref(self)
+            p._svit_index = i
+            self._offsets.append((off, n))
             off += n
+        self._plist = ps
         self._flat = flat
         self._shadow = None
         self._shadow_key = None
@@ -178,12 +187,18 @@ class masked_patch_pretraining(nn.Module):
     def mark_weights_dirty(self):
         self._shadow_key = None
 
-    def _refresh_shadow(self, dev):
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
+        out = super().load_state_dict(state_dict, strict=strict, **kwargs)
+        self.mark_weights_dirty()
+        self.transformer.mark_weights_dirty()
+        return out
+
+    def _refresh_shadow(self, dev, force=False):
         if self._flat.device != dev:
             raise RuntimeError(f"masked_patch_pretraining parameters are on {self._flat.device}, input on {dev}; "
                                "call ssl.to(device) as tools/pretrain.py:258 does")
         key = (self._flat.data_ptr(), self._flat._version, self.to_original.weight._version)
-        if self._shadow is not None and key == self._shadow_key:
+        if self._shadow is not None and key == self._shadow_key and not force:
             return
         lib = _lib.load()
         eng = self.transformer._engine

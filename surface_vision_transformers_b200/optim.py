@@ -47,6 +47,16 @@ def _flat_grad_for(owner, params):
     return G, active
 
 
+def _carry_over(old, new):
+    """Copies the moment buffers / step counters of a flat state whose parameter buffer was re-allocated."""
+    if old is None or len(old.bufs) != len(new.bufs) or old.bufs[0].numel() != new.bufs[0].numel():
+        return False
+    for a, b in zip(old.bufs, new.bufs):
+        b.copy_(a)
+    new.steps = list(old.steps)
+    return True
+
+
 class _FlatState:
     """Flat moment buffers + host-side segment table of one SiT owned by an optimizer."""
 
@@ -66,6 +76,7 @@ class _FlatState:
             if owner._flat.is_cuda else None
         self.seg_dev = torch.empty(ctypes.sizeof(self.seg_host), dtype=torch.uint8, device=owner._flat.device)
         self.table_key = None      # active pattern the device table was uploaded for (None: upload needed)
+        self.has_momentum = False  # FusedSGD: the momentum buffer holds a value (a step ran or a state_dict was loaded)
 
 
 class FusedAdamW(Optimizer):
@@ -81,7 +92,8 @@ class FusedAdamW(Optimizer):
     def _state_for(self, owner, rebind=True):
         st = self._flat_states.get(id(owner))
         if st is None or st.flat_ptr != owner._flat.data_ptr():
-            st = _FlatState(owner, 2)
+            old, st = st, _FlatState(owner, 2)
+            _carry_over(old, st)     # the flat buffer was re-created (model.to(), .float()): keep the moments and steps
             self._flat_states[id(owner)] = st
             if not rebind:
                 return st
@@ -255,13 +267,13 @@ class FusedSGD(Optimizer):
                     continue
                 G, _ = _flat_grad_for(owner, owner._plist)
                 st = self._flat_states.get(id(owner))
-                first = st is None or st.flat_ptr != owner._flat.data_ptr()
-                if first:
-                    st = _FlatState(owner, 1)
+                if st is None or st.flat_ptr != owner._flat.data_ptr():
+                    old, st = st, _FlatState(owner, 1)
+                    st.has_momentum = _carry_over(old, st) and old.has_momentum   # re-flattened model: keep the momentum
                     self._flat_states[id(owner)] = st
-                    for p in owner._plist:
-                        off, n = owner._offsets[p._svit_index]
-                        self.state[p] = {"momentum_buffer": st.bufs[0][off:off + n].view(p.shape)}
+                    self._bind_views(owner, st)
+                first = not st.has_momentum   # torch: the first step initialises the buffer with the gradient itself
+                st.has_momentum = True
                 dev = owner._flat.device
                 with torch.cuda.device(dev):   # kernels launch on the current device
                     check(lib.svit_sgd_step(ptr(owner._flat), ptr(G), ptr(st.bufs[0]), owner._flat.numel(), group["lr"],
@@ -269,19 +281,52 @@ class FusedSGD(Optimizer):
                                             1 if group["nesterov"] else 0, 1 if first else 0, self.grad_scale,
                                             vp(torch.cuda.current_stream(dev).cuda_stream)), "svit_sgd_step")
                 owner.mark_weights_dirty()
-            for p in loose:
-                if p.grad is None:
-                    continue
-                g = (p.grad * self.grad_scale).add(p, alpha=group["weight_decay"])
-                if group["momentum"] != 0:
-                    stp = self.state[p]
-                    if "momentum_buffer" not in stp:
-                        stp["momentum_buffer"] = g.clone()
-                    else:
-                        stp["momentum_buffer"].mul_(group["momentum"]).add_(g, alpha=1 - group["dampening"])
-                    g = g.add(stp["momentum_buffer"], alpha=group["momentum"]) if group["nesterov"] else stp["momentum_buffer"]
-                p.add_(g, alpha=-group["lr"])
-                o = _owner_of(p)
-                if o is not None:
-                    o.mark_weights_dirty()
+            self._generic_sgd(group, loose)
         return loss
+
+    def _bind_views(self, owner, st):
+        for p in owner._plist:
+            off, n = owner._offsets[p._svit_index]
+            self.state[p] = {"momentum_buffer": st.bufs[0][off:off + n].view(p.shape)}
+
+    def load_state_dict(self, state_dict):
+        """torch's loader replaces ``state[p]['momentum_buffer']`` with fresh tensors; copy them back into the flat
+        momentum buffer (the fused kernel updates that one), re-bind the views and keep the momentum (no 'first step')."""
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            owners = {}
+            for p in group["params"]:
+                o = _owner_of(p)
+                if o is not None and hasattr(o, "_offsets") and hasattr(p, "_svit_index"):
+                    owners[id(o)] = o
+            for owner in owners.values():
+                loaded = [self.state.get(p, {}).get("momentum_buffer") for p in owner._plist]
+                if not any(b is not None for b in loaded):
+                    continue
+                st = self._flat_states.get(id(owner))
+                if st is None or st.flat_ptr != owner._flat.data_ptr():
+                    st = _FlatState(owner, 1)
+                    self._flat_states[id(owner)] = st
+                for (off, n), b in zip(owner._offsets, loaded):
+                    if b is not None:
+                        st.bufs[0][off:off + n].copy_(b.reshape(-1))
+                st.has_momentum = True
+                self._bind_views(owner, st)
+
+    def _generic_sgd(self, group, loose):
+        """Parameters that do not belong to a flat B200 module (or a partial set of one): plain torch arithmetic."""
+        for p in loose:
+            if p.grad is None:
+                continue
+            g = (p.grad * self.grad_scale).add(p, alpha=group["weight_decay"])
+            if group["momentum"] != 0:
+                stp = self.state[p]
+                if "momentum_buffer" not in stp:
+                    stp["momentum_buffer"] = g.clone()
+                else:
+                    stp["momentum_buffer"].mul_(group["momentum"]).add_(g, alpha=1 - group["dampening"])
+                g = g.add(stp["momentum_buffer"], alpha=group["momentum"]) if group["nesterov"] else stp["momentum_buffer"]
+            p.add_(g, alpha=-group["lr"])
+            o = _owner_of(p)
+            if o is not None:
+                o.mark_weights_dirty()

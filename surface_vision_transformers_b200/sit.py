@@ -88,7 +88,8 @@ class _SiTFunction(torch.autograd.Function):
     def forward(ctx, model, img, *params):
         B = img.shape[0]
         dev = img.device
-        model._refresh_shadow(dev)
+        model._refresh_shadow(dev, force=True)
+        ctx.shadow_gen = model._shadow_gen
         lib = _lib.load()
         nbytes = lib.svit_workspace_bytes(model._engine, B, 1, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -107,6 +108,7 @@ class _SiTFunction(torch.autograd.Function):
     def backward(ctx, dout):
         model = ctx.model
         lib = _lib.load()
+        model._check_shadow_gen(ctx.shadow_gen)
         dout = dout.contiguous().float()
         G = torch.zeros_like(model._flat)
         with torch.cuda.device(ctx.dev):
@@ -124,7 +126,8 @@ class _EncoderFunction(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         B = x.shape[0]
         dev = x.device
-        model._refresh_shadow(dev)
+        model._refresh_shadow(dev, force=True)
+        ctx.shadow_gen = model._shadow_gen
         lib = _lib.load()
         training = 1
         nbytes = lib.svit_workspace_bytes(model._engine, B, training, 0)
@@ -146,6 +149,7 @@ class _EncoderFunction(torch.autograd.Function):
         model = ctx.model
         lib = _lib.load()
         (x,) = ctx.saved_tensors
+        model._check_shadow_gen(ctx.shadow_gen)
         dy = dy.contiguous().float()
         G = torch.zeros_like(model._flat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
@@ -153,6 +157,10 @@ class _EncoderFunction(torch.autograd.Function):
             model._apply_dropout_state(ctx.drop)
             check(lib.svit_encoder_backward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ctx.ws), ctx.B,
                                             ptr(x), ptr(dy), ptr(dx), ptr(G), _stream(ctx.dev)), "svit_encoder_backward")
+            if model._grad_hook is not None:
+                # the encoder-only backward has no per-stage progress callback: reduce the whole buffer at the end
+                model._grad_hook(model, "all", G)
+                model._grad_hook(model, None, G)
         ctx.ws = None
         return (None, dx) + model._grad_views(G)
 
@@ -197,7 +205,10 @@ class SiT(nn.Module):
         self._flat = None
         self._shadow = None
         self._shadow_key = None
+        self._shadow_dirty_gen = 0
+        self._shadow_gen = 0     # bumped every time the bf16 shadows are re-derived (backward checks it, see below)
         self._grad_hook = None   # set by ddp.DataParallel: called as hook(stage, G) while backward is being enqueued
+        self._hook_error = None
         self._flatten()
 
     # ------------------------------------------------------------------ parameters
@@ -272,17 +283,37 @@ class SiT(nn.Module):
         return bool(_lib.load().svit_get_check_mode(self._engine))
 
     def mark_weights_dirty(self):
-        """Called by optimizers that update the flat buffer through the C ABI (no autograd version bump)."""
+        """The fp32 masters changed behind autograd's back: the bf16 shadows are re-derived before the next forward.
+        Called by the fused optimizers and by ``load_state_dict``.  Every grad-enabled forward re-derives them anyway
+        (in a training loop the optimizer has just changed the weights, so that costs nothing extra); only INFERENCE
+        forwards trust the version counters, which writes through ``p.data`` (EMA / SWA swaps, ``p.data.copy_``) do
+        not bump -- call this method after such writes."""
         self._shadow_key = None
 
-    def _refresh_shadow(self, dev):
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
+        out = super().load_state_dict(state_dict, strict=strict, **kwargs)
+        self.mark_weights_dirty()
+        return out
+
+    def _check_shadow_gen(self, gen):
+        """Backward reads the same shadow buffer the forward used; if another forward re-derived it from CHANGED
+        weights in between, the gradients would silently belong to the new weights -- refuse instead."""
+        if gen != self._shadow_gen and self._shadow_changed_since(gen):
+            raise RuntimeError("SiT: the weights were modified between this forward and its backward (the bf16 weight "
+                               "shadows were re-derived from different values); run backward before updating the weights")
+
+    def _shadow_changed_since(self, gen):
+        return self._shadow_dirty_gen > gen
+
+    def _refresh_shadow(self, dev, force=False):
         if self._flat.device != dev or dev.type != 'cuda':
             raise RuntimeError(f"SiT parameters are on {self._flat.device} but the input is on {dev}: the sm_100a path "
                                "needs both on the same CUDA device (there is no CPU fallback)")
         if self._flat.dtype != torch.float32:
             raise RuntimeError("SiT parameters must be fp32 master weights")
         key = self._weights_version()
-        if self._shadow is not None and key == self._shadow_key:
+        clean = self._shadow is not None and key == self._shadow_key
+        if clean and not force:
             return
         lib = _lib.load()
         if self._shadow is None or self._shadow.device != dev:
@@ -290,6 +321,9 @@ class SiT(nn.Module):
         check(lib.svit_prepare_weights(self._engine, ptr(self._flat), ptr(self._shadow), _stream(dev)),
               "svit_prepare_weights")
         self._shadow_key = key
+        self._shadow_gen += 1
+        if not clean:
+            self._shadow_dirty_gen = self._shadow_gen   # last generation derived from weights known to have changed
 
     def _grad_views(self, G):
         return tuple(G[off:off + n].view(p.shape) for (off, n), p in zip(self._offsets, self._plist))
@@ -301,15 +335,26 @@ class SiT(nn.Module):
         hook = self._grad_hook
 
         def cb(stage, _user):
-            hook(self, stage, G)
+            # ctypes prints and then SWALLOWS exceptions raised inside a callback: stash the first one, it is re-raised
+            # by _finish_progress_hook once svit_backward has returned (a failed all-reduce must not pass silently)
+            if self._hook_error is not None:
+                return
+            try:
+                hook(self, stage, G)
+            except BaseException as e:   # noqa: BLE001
+                self._hook_error = e
 
+        self._hook_error = None
         self._cb_keepalive = _lib.PROGRESS_FN(cb)
         return ctypes.cast(self._cb_keepalive, vp)
 
     def _finish_progress_hook(self, G):
+        self._cb_keepalive = None
+        err, self._hook_error = self._hook_error, None
+        if err is not None:
+            raise RuntimeError("gradient hook failed during backward (replicas would diverge)") from err
         if self._grad_hook is not None:
             self._grad_hook(self, None, G)   # stage None == "backward fully enqueued": wait for outstanding work
-        self._cb_keepalive = None
 
     def stage_segment(self, stage):
         """(offset, numel) of the flat-buffer range whose gradients are final after `stage`

@@ -38,7 +38,7 @@ def _all_reduce_(t):
 
 def evaluate(model, dataset, batch_size, device, l1loss=False):
     """Validation pass of tools/train.py:311-337: returns (sum of batch losses, MAE, predictions, targets) with the
-    statistics of all ranks combined; predictions / targets are those of this rank (host tensors)."""
+    statistics AND the predictions / targets of all ranks combined (host tensors, dataset order)."""
     rank, world = _dist_info()
     criterion = torch.nn.L1Loss() if l1loss else torch.nn.MSELoss(reduction="mean")
     net = model.module if isinstance(model, DataParallel) else model
@@ -57,7 +57,20 @@ def evaluate(model, dataset, batch_size, device, l1loss=False):
     _all_reduce_(stats)
     s = stats.cpu()
     net.train(was_training)
-    return float(s[0]), float(s[1] / s[2].clamp(min=1)), torch.cat(preds).cpu(), torch.cat(targets).cpu()
+    p_all = torch.cat(preds).cpu() if preds else torch.zeros(0)
+    t_all = torch.cat(targets).cpu() if targets else torch.zeros(0)
+    if world > 1:
+        # every rank evaluated the strided slice [rank::world] of the split: put the pieces back in dataset order, so
+        # that what rank 0 saves as preds_test.pt covers the whole validation set (train.py:355-359), not its shard
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (p_all, t_all))
+        n = sum(int(pp.numel()) for pp, _ in pieces)
+        p_full, t_full = torch.empty(n), torch.empty(n)
+        for r, (pp, tt) in enumerate(pieces):
+            p_full[r::world] = pp
+            t_full[r::world] = tt
+        p_all, t_all = p_full, t_full
+    return float(s[0]), float(s[1] / s[2].clamp(min=1)), p_all, t_all
 
 
 def fit(model, optimizer, train_set, val_set=None, *, epochs, batch_size, val_batch_size=None, val_epoch=1, device=None,
