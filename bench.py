@@ -177,6 +177,86 @@ def run_reference_arm(args, wl, wl_name):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------- other BASELINE configs
+SWEEP_POINTS = [("sit_tiny_ico2_scan_age_train", 256), ("sit_small_ico1_birth_age_train", 256),
+                ("sit_small_ico2_mpp_pretrain", 256)] + \
+               [("sit_base_ico2_inference", b) for b in (64, 128, 256, 512, 1024, 2048, 4096)]
+
+
+def run_sweep(args):
+    """BASELINE.json configs[0,2,3,4] on one GPU: train samples/s for C1 / C3 / C4 and the C5 inference batch sweep
+    (tools/testing.py:76-88 is the reference's inference path).  One record per point, written as a JSON list."""
+    import torch
+    import surface_vision_transformers_b200 as svit
+    from surface_vision_transformers_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+    records = []
+    for wl_name, B in SWEEP_POINTS:
+        wl = WORKLOADS[wl_name]
+        m, kind = wl["model"], wl["kind"]
+        torch.manual_seed(0)
+        model = svit.SiT(dim=m["dim"], depth=m["depth"], heads=m["heads"], mlp_dim=m["mlp_dim"], num_patches=m["num_patches"],
+                         num_classes=m["num_classes"], num_channels=m["num_channels"], num_vertices=m["num_vertices"],
+                         dim_head=m["dim_head"]).to(dev)
+        runner, opt = model, None
+        if kind == "mpp":
+            K = m["num_channels"] * m["num_vertices"]
+            runner = svit.masked_patch_pretraining(transformer=model, dim_in=m["dim"], dim_out=K, device=dev, mask_prob=0.5,
+                                                   replace_prob=0.8, swap_prob=0.02, channels=m["num_channels"],
+                                                   num_vertices=m["num_vertices"]).to(dev)
+        if kind != "infer":
+            opt = svit.FusedAdamW(model.parameters(), lr=1e-5 if kind == "train" else 3e-4, weight_decay=0.0)
+        else:
+            model.eval()
+        x = torch.randn(B, m["num_channels"], m["num_patches"], m["num_vertices"], device=dev)
+        y = torch.rand(B, device=dev) * 19 + 26
+
+        def step():
+            if kind == "infer":
+                with torch.no_grad():
+                    return model(x)
+            opt.zero_grad(set_to_none=True)
+            loss = runner(x)[0] if kind == "mpp" else torch.nn.functional.mse_loss(runner(x).squeeze(), y)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(max(3, args.warmup)):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(0)
+        sampler.start()
+        l0 = lib.svit_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        clocks = sampler.stop()
+        value = B / (ms * 1e-3)
+        tf = value * wl["gflop_per_sample"] / 1e3
+        rec = dict(metric="SiT train samples/sec" if kind != "infer" else "SiT inference samples/sec", value=value,
+                   unit="samples/s", n_gpus=1, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, dtype="bf16",
+                   data="synthetic", config=dict(workload=wl_name, batch_per_gpu=B, **m), clocks=clocks,
+                   gpu_launches=int(lib.svit_launch_count() - l0),
+                   roofline=dict(bound="tensor", scope="whole step", achieved=tf, unit="TFLOP/s",
+                                 peak=peaks["tflops_sustained"], frac=tf / peaks["tflops_sustained"],
+                                 gflop_per_sample=wl["gflop_per_sample"], peak_source=peaks["source"] + " (sustained)"))
+        records.append(rec)
+        print(json.dumps(rec), flush=True)
+        del model, runner, opt, x, y
+        torch.cuda.empty_cache()
+    with open(args.sweep, "w") as f:
+        json.dump(records, f, indent=1)
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -188,6 +268,10 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", metavar="OUT.json", default=None,
+                    help="instead of the headline line: time the other BASELINE.json configs (C1 tiny / C3 ico-1 / C4 MPP "
+                         "training at the per-GPU batch, C5 SiT-base inference at batch 64..4096) and write one record per "
+                         "point to OUT.json (device-resident timing, same clocks / roofline fields)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -195,6 +279,9 @@ def main():
     wl = WORKLOADS[wl_name]
     if args.impl == "reference":
         run_reference_arm(args, wl, wl_name)
+        return
+    if args.sweep:
+        run_sweep(args)
         return
 
     import torch
@@ -426,9 +513,9 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, ms_cpu, cores = cpu_reference_step_rate(wl, args.cpu_batch, 3, 1)
+        rate, ms_cpu, cores = cpu_reference_step_rate(wl, args.cpu_batch, 10, 3)   # 3 warm-up + >= 10 timed
         cpu = dict(value=rate, unit="samples/s", cores=cores, kind="port",
-                   sample=f"oracle port (fp32 PyTorch restatement of the reference), batch {args.cpu_batch}, 1 warm-up + 3 "
+                   sample=f"oracle port (fp32 PyTorch restatement of the reference), batch {args.cpu_batch}, 3 warm-up + 10 "
                           f"timed steps of the same workload ({ms_cpu:.0f} ms/step)")
 
     if rank == 0:

@@ -397,3 +397,20 @@ def test_graph_capture_helpers_reject_what_they_cannot_replay():
         graphs._check_model(svit.SiT(**cfg, dropout=0.1))
     with pytest.raises(TypeError):
         graphs._check_model(torch.nn.Linear(4, 4))
+
+
+@pytest.mark.parametrize("n,world,bs", [(65, 2, 16), (66, 4, 16), (64, 2, 16), (7, 8, 2), (1, 2, 4)])
+def test_training_shards_are_equal_on_every_rank(n, world, bs):
+    """a training pass all-reduces gradients after EVERY batch, so every rank must see the same number
+    of batches with the same sizes whatever len(dataset) % world is (padding by wrap-around, like DistributedSampler);
+    evaluation passes keep the exact split."""
+    from surface_vision_transformers_b200.data import shard_order
+    gens = [torch.Generator().manual_seed(3) for _ in range(world)]
+    shards = [shard_order(n, True, gens[r], r, world, True) for r in range(world)]
+    sizes = [[len(s[i:i + bs]) for i in range(0, len(s), bs)] for s in shards]
+    assert all(sz == sizes[0] for sz in sizes), sizes
+    covered = set(torch.cat(shards).tolist())
+    assert covered == set(range(n))                                   # nobody is dropped
+    assert sum(len(s) for s in shards) == -(-n // world) * world       # padded to a multiple of world
+    exact = [shard_order(n, False, None, r, world, False) for r in range(world)]
+    assert sorted(torch.cat(exact).tolist()) == list(range(n))        # evaluation: every sample exactly once
