@@ -19,30 +19,32 @@ constexpr int TILE_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 // forward
 // =================================================================================================
 // One CTA per (sample, head), TWO CTAs resident per SM.  K and V (<= 384 keys) stay in shared memory, Q blocks of 128
-// rows stream through.  What one CTA cannot overlap -- the S = Q K^T MMAs, the exponentials and the P V MMAs of a
-// query block form a dependent chain, and the load / store latencies of a block sit in front of and behind it -- the
-// second CTA on the SM fills: its softmax warps run while this one's tensor work, TMA loads or output stores are in
-// flight.  Two CTAs need half the TMEM and half the shared memory each, which is what shapes the kernel:
-//   * the keys of a query block are processed in two halves (<= 192 score columns each): S_h [0,192) + O [192,256) = 256
-//     TMEM columns per CTA;
-//   * shared memory holds exactly the padded keys (tk = T rounded up to 16 rows) and one Q tile; O leaves straight from
-//     registers (64 contiguous bytes per thread and block -- tiny next to the operand streams), so Q(i+1) can land while
-//     block i is still in its second half.
+// rows stream through.  Inside a CTA the keys of a query block are processed in chunks of 96 that ping-pong between two
+// TMEM score buffers and two groups of four softmax warps:
+//     tensor pipe :  S(0) S(1) | PV(0) S(2) | PV(1) S(3) | PV(2) PV(3)             S = Q K_c^T, O += P_c V_c
+//     group 0     :       exp(0) ........ exp(2) ........
+//     group 1     :            exp(1) ........ exp(3) ....
+// so the exponentials of one chunk run while the tensor core produces the next scores and consumes the previous
+// probabilities, and what a CTA still cannot overlap (the load of the next Q tile, the block epilogue) the second CTA on
+// the SM fills.  Two CTAs per SM need half the TMEM and half the shared memory each:
+//   * TMEM: 2 x 96 score columns + 64 O columns = 256;
+//   * shared memory holds exactly the padded keys (tk = T rounded up to 16 rows) and ONE Q tile; O leaves straight from
+//     registers (64 contiguous bytes per thread and block -- tiny next to the operand streams).
 // The scores are read from TMEM ONCE: the softmax shift is the row's score against key 0 (any shift is exact for
-// softmax; the log-sum-exp is reported with the same shift), which also makes the two key halves independent -- no
-// running maximum, no rescaling of O.  A guard on the row sum (it cannot underflow: key 0 contributes exp2(0) = 1)
-// detects overflow after the second half; the block is then redone with the classic max shift ("safe mode": max over
-// both halves first, then the exponentials).
-// 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the columns of the current key half.
-// P never touches shared memory: the bf16 probabilities are written back into TMEM over the consumed scores
-// (tcgen05.st, two per 32-bit column) and feed the PV product as the A operand FROM TMEM.
-// shared memory map (bytes):  sQ 16K | sK tk*128 | sV tk*128 | row sums / maxima 1K | barriers   (T = 321: 102 KB)
+// softmax; the log-sum-exp is reported with the same shift), which makes the chunks independent -- no running maximum,
+// no rescaling of O.  A guard on the row sum (it cannot underflow: key 0 contributes exp2(0) = 1) detects overflow at
+// the end of the block; the block is then redone in "safe mode" with the classic max shift (a pass over all chunks for
+// the maxima, then the exponentials).
+// A warp owns one TMEM lane quadrant (32 query rows, one per thread) and ALL columns of its chunk, so the bf16
+// probabilities go back into TMEM over the scores just read (tcgen05.st, two per 32-bit column) without any cross-warp
+// hazard, and feed the PV product as the A operand FROM TMEM: P never touches shared memory.
+// shared memory map (bytes):  sQ 16K | sK tk*128 | sV tk*128 | shift / row sums 1.5K | barriers   (T = 321: 103 KB)
 constexpr int FWD_THREADS = 288;
 constexpr int FWD_TMEM_COLS = 256;
+constexpr int FWD_CHUNK = 96;    // keys per chunk = score columns per buffer
 constexpr int FWD_TMEM_O = 192;  // O accumulator columns [192, 256)
-constexpr int FWD_HALF_MAX = 192;
 
-__host__ __device__ constexpr int fwd_smem_bytes(int tk) { return 1024 + TILE_BYTES + 2 * tk * 128 + 2 * 128 * 4 + 256; }
+__host__ __device__ constexpr int fwd_smem_bytes(int tk) { return 1024 + TILE_BYTES + 2 * tk * 128 + 3 * 128 * 4 + 256; }
 
 struct AttnFwdArgs {
     CUtensorMap tmQ;   // qkv (3*inner, T, B) bf16, box 64 x 128 x 1: Q_i loads
@@ -72,7 +74,7 @@ __device__ __forceinline__ float fwd_ex2(float x) {
     return r;
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs args) {
+__global__ void __launch_bounds__(384, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int T = args.T, H = args.H;
@@ -81,28 +83,27 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;
     uint8_t* sV = sK + tk * 128;
-    float* sRed = reinterpret_cast<float*>(sV + tk * 128);  // [2][128]
+    float* sShift = reinterpret_cast<float*>(sV + tk * 128);  // [128]   softmax shift of every query row of the block
+    float* sRed = sShift + 128;                                // [2][128] per-group partial row sums / maxima
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 256);
-    uint64_t* bar_k = bars + 0;    // K landed                                   (TMA -> control)
-    uint64_t* bar_vv = bars + 1;   // V landed                                   (TMA -> control)
-    uint64_t* bar_q = bars + 2;    // Q_i landed                                 (TMA -> control)
-    uint64_t* bar_s = bars + 3;    // scores of a key half in TMEM               (MMA -> softmax, control)
-    uint64_t* bar_p = bars + 4;    // P of a key half in TMEM / scores consumed  (softmax -> control)
-    uint64_t* bar_pv = bars + 5;   // PV of the first half retired: the score columns may be overwritten (MMA -> control)
-    uint64_t* bar_o = bars + 6;    // every MMA of the block retired             (MMA -> softmax, control)
-    uint64_t* bar_of = bars + 7;   // O copied to registers                      (softmax -> control)
-    uint64_t* bar_v = bars + 8;    // verdict of the block published in *flag    (softmax -> control)
-    uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* bar_k = bars + 0;     // K landed                                      (TMA -> control)
+    uint64_t* bar_vv = bars + 1;    // V landed                                      (TMA -> control)
+    uint64_t* bar_q = bars + 2;     // Q_i landed                                    (TMA -> control)
+    uint64_t* s_full = bars + 3;    // [2] scores of a chunk in buffer b             (MMA -> softmax group b, control)
+    uint64_t* p_full = bars + 5;    // [2] P of a chunk in buffer b / scores consumed (softmax group b -> control)
+    uint64_t* pv_done = bars + 7;   // [2] the PV product that read buffer b retired (MMA -> control)
+    uint64_t* bar_o = bars + 9;     // every MMA of the block retired                (MMA -> softmax, control)
+    uint64_t* bar_of = bars + 10;   // O copied to registers                         (softmax -> control)
+    uint64_t* bar_v = bars + 11;    // verdict of the block published in *flag       (softmax -> control)
+    uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 12);
     uint32_t* tmem_slot = flag + 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x / H;
     const int h = blockIdx.x % H;
-    const int nqb = (T + 127) / 128;  // query blocks
-    // key halves: one when the padded keys fit the score columns, else two (both multiples of 16, both <= 192)
-    const int n0 = tk <= FWD_HALF_MAX ? tk : ((tk >> 1) + 15) & ~15;
-    const int n1 = tk - n0;
+    const int nqb = (T + 127) / 128;                  // query blocks
+    const int nch = (tk + FWD_CHUNK - 1) / FWD_CHUNK;  // key chunks (<= 4); chunk c lives in buffer c & 1, group c & 1
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmQ);
@@ -110,9 +111,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
         mbar_init(bar_k, 1);
         mbar_init(bar_vv, 1);
         mbar_init(bar_q, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_p, 8);
-        mbar_init(bar_pv, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&pv_done[i], 1);
+        }
         mbar_init(bar_o, 1);
         mbar_init(bar_of, 8);
         mbar_init(bar_v, 8);
@@ -142,63 +145,81 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
                 tma_load_3d(sV + r * args.kv_box * 128, &args.tmKV, bar_vv, 2 * inner + h * 64, r * args.kv_box, b);
             const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
             const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            uint32_t ph_q = 0, ph_p = 0, ph_pv = 0, ph_o = 0, ph_of = 0, ph_v = 0;
-            uint32_t s_cnt = 0;  // score batches issued so far: batch c completes phase parity c & 1 of bar_s
-            // S = Q K_h^T (K-major A and B) into the score columns
-            auto issue_s = [&](int key0, int nh) {
-                const uint32_t idesc = umma_idesc_bf16(128, nh, 0, 0);
+            uint32_t ph_q = 0, ph_o = 0, ph_of = 0, ph_v = 0;
+            // per-buffer state as scalars (an indexed local array would live in local memory: with ~210 KB of the SM's
+            // unified L1 / shared memory given to the two CTAs' tiles, every such access is an L2 round trip)
+            uint32_t ph_p0 = 0, ph_p1 = 0, ph_pv0 = 0, ph_pv1 = 0;
+            uint32_t s_cnt0 = 0, s_cnt1 = 0;  // score batches issued into buffer b so far: batch n completes parity n & 1 of s_full[b]
+            auto chunk_keys = [&](int c) { return min(FWD_CHUNK, tk - c * FWD_CHUNK); };
+            // S(c) = Q K_c^T (K-major A and B) into score buffer c & 1
+            auto issue_s = [&](int c) {
+                const int bf = c & 1;
+                const uint32_t idesc = umma_idesc_bf16(128, chunk_keys(c), 0, 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_ss(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024),
-                            umma_smem_desc(k_addr + key0 * 128 + k * 32, 16, 1024), idesc, k != 0);
-                umma_commit(bar_s);
-                ++s_cnt;
+                    umma_ss(tmem_base + bf * FWD_CHUNK, umma_smem_desc(q_addr + k * 32, 16, 1024),
+                            umma_smem_desc(k_addr + c * FWD_CHUNK * 128 + k * 32, 16, 1024), idesc, k != 0);
+                umma_commit(&s_full[bf]);
+                if (bf) ++s_cnt1; else ++s_cnt0;
             };
-            // O (+)= P_h V_h  (A = P from TMEM: lanes = query rows, 8 columns of packed bf16 pairs per 16-key step; B = V MN-major)
-            auto issue_pv = [&](int key0, int nh, bool acc) {
-                const int ks = nh >> 4;
+            // O (+)= P_c V_c  (A = P from TMEM: lanes = query rows, 8 columns of packed bf16 pairs per 16-key step; B = V MN-major)
+            auto issue_pv = [&](int c) {
+                const int bf = c & 1, ks = chunk_keys(c) >> 4;
                 for (int s = 0; s < ks; ++s)
-                    umma_ts(tmem_base + FWD_TMEM_O, tmem_base + s * 8,
-                            umma_smem_desc(v_addr + ((key0 >> 4) + s) * 2048, 8192, 1024), idesc_pv, (acc || s != 0) ? 1u : 0u);
+                    umma_ts(tmem_base + FWD_TMEM_O, tmem_base + bf * FWD_CHUNK + s * 8,
+                            umma_smem_desc(v_addr + (c * (FWD_CHUNK >> 4) + s) * 2048, 8192, 1024), idesc_pv,
+                            (c > 0 || s != 0) ? 1u : 0u);
             };
             auto load_q = [&](int i) {
                 mbar_expect_tx(bar_q, TILE_BYTES);
                 tma_load_3d(sQ, &args.tmQ, bar_q, h * 64, i * 128, b);
             };
-            auto wait_last_s = [&]() { mbar_wait(bar_s, (s_cnt - 1) & 1); };
+            auto wait_p = [&](int bf) {
+                mbar_wait(&p_full[bf], bf ? ph_p1 : ph_p0);
+                if (bf) ph_p1 ^= 1; else ph_p0 ^= 1;
+            };
+            // the last score batch of the block has retired -> sQ is dead: the next block's queries may land
+            auto prefetch_q = [&](int i) {
+                const int bf = (nch - 1) & 1;
+                mbar_wait(&s_full[bf], ((bf ? s_cnt1 : s_cnt0) - 1) & 1);
+                if (i + 1 < nqb) load_q(i + 1);
+            };
+            // one pass over the chunks of block i: scores for everybody, and (exp pass) the PV products behind them
+            auto run_pass = [&](int i, bool exp_pass, bool first_attempt) {
+                auto do_pv = [&](int c) {
+                    const int bf = c & 1;
+                    wait_p(bf);
+                    if (!exp_pass) return;
+                    if (c == 0 && first_attempt) {
+                        if (i > 0) {
+                            mbar_wait(bar_of, ph_of);  // the previous block's O left TMEM
+                            ph_of ^= 1;
+                        } else {
+                            mbar_wait(bar_vv, 0);
+                        }
+                    }
+                    tc_fence_after();
+                    issue_pv(c);
+                    if (c + 2 < nch) umma_commit(&pv_done[bf]);
+                };
+                for (int c = 0; c < nch; ++c) {
+                    const int bf = c & 1;
+                    if (c >= 2 && exp_pass) {
+                        mbar_wait(&pv_done[bf], bf ? ph_pv1 : ph_pv0);  // PV(c-2) consumed P(c-2): the buffer is free
+                        if (bf) ph_pv1 ^= 1; else ph_pv0 ^= 1;
+                    }
+                    tc_fence_after();
+                    issue_s(c);
+                    if (c >= 1) do_pv(c - 1);   // (max pass, c >= 2: this is also the "buffer consumed" wait for S(c+1))
+                    if (c == nch - 1 && exp_pass) prefetch_q(i);
+                }
+                do_pv(nch - 1);
+            };
             mbar_wait(bar_k, 0);
             for (int i = 0; i < nqb; ++i) {
                 mbar_wait(bar_q, ph_q);
                 ph_q ^= 1;
-                tc_fence_after();
-                issue_s(0, n0);
-                if (n1 == 0) {
-                    wait_last_s();  // sQ is dead: the next block's queries may land
-                    if (i + 1 < nqb) load_q(i + 1);
-                }
-                mbar_wait(bar_p, ph_p);
-                ph_p ^= 1;
-                if (i > 0) {
-                    mbar_wait(bar_of, ph_of);  // the previous block's O left TMEM
-                    ph_of ^= 1;
-                } else {
-                    mbar_wait(bar_vv, 0);
-                }
-                tc_fence_after();
-                issue_pv(0, n0, false);
-                if (n1 > 0) {
-                    umma_commit(bar_pv);
-                    mbar_wait(bar_pv, ph_pv);  // P_h0 consumed: the score columns are free again
-                    ph_pv ^= 1;
-                    tc_fence_after();
-                    issue_s(n0, n1);
-                    wait_last_s();
-                    if (i + 1 < nqb) load_q(i + 1);
-                    mbar_wait(bar_p, ph_p);
-                    ph_p ^= 1;
-                    tc_fence_after();
-                    issue_pv(n0, n1, true);
-                }
+                run_pass(i, true, true);
                 umma_commit(bar_o);
                 mbar_wait(bar_o, ph_o);
                 ph_o ^= 1;
@@ -215,36 +236,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
                         mbar_wait(bar_q, ph_q);
                         ph_q ^= 1;
                     }
-                    tc_fence_after();
-                    issue_s(0, n0);  // maxima of half 0
-                    if (n1 > 0) {
-                        mbar_wait(bar_p, ph_p);
-                        ph_p ^= 1;
-                        tc_fence_after();
-                        issue_s(n0, n1);  // maxima of half 1, then its exponentials
-                        mbar_wait(bar_p, ph_p);
-                        ph_p ^= 1;
-                        tc_fence_after();
-                        issue_pv(n0, n1, false);
-                        umma_commit(bar_pv);
-                        mbar_wait(bar_pv, ph_pv);
-                        ph_pv ^= 1;
-                        tc_fence_after();
-                        issue_s(0, n0);  // half 0 again, now for its exponentials
-                        wait_last_s();
-                        if (i + 1 < nqb) load_q(i + 1);
-                        mbar_wait(bar_p, ph_p);
-                        ph_p ^= 1;
-                        tc_fence_after();
-                        issue_pv(0, n0, true);
-                    } else {
-                        wait_last_s();
-                        if (i + 1 < nqb) load_q(i + 1);
-                        mbar_wait(bar_p, ph_p);
-                        ph_p ^= 1;
-                        tc_fence_after();
-                        issue_pv(0, n0, false);
-                    }
+                    run_pass(i, false, false);
+                    run_pass(i, true, false);
                     umma_commit(bar_o);
                     mbar_wait(bar_o, ph_o);
                     ph_o ^= 1;
@@ -253,45 +246,47 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
         }
     } else {
         // ============================ softmax + epilogue warps ============================
-        const int q = warp & 3;    // TMEM lane quadrant
-        const int hf = warp >> 2;  // column half within the current key half
+        const int q = warp & 3;     // TMEM lane quadrant
+        const int grp = warp >> 2;  // softmax group = score buffer = parity of the chunks this warp processes
         const int row = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t t_buf = t_row + grp * FWD_CHUNK;
         const float c = args.scale_log2e;
         uint32_t ph_s = 0, ph_o = 0;
-        // the two warps of a quadrant (same TMEM lanes, complementary columns) synchronise among themselves
+        // the two warps of a quadrant (one per group) hold the same query rows
         // (constant barrier ids: with a run-time id ptxas reserves all 16 named barriers and only one CTA fits an SM)
-        auto quadbar = [&]() {
-            tc_fence_before();
+        auto pairbar = [&]() {
             if (q == 0) named_bar_sync(1, 64);
             else if (q == 1) named_bar_sync(2, 64);
             else if (q == 2) named_bar_sync(3, 64);
             else named_bar_sync(4, 64);
+        };
+        auto pair_exchange = [&](float mine, bool is_max) {
+            sRed[grp * 128 + row] = mine;
+            pairbar();
+            const float a = sRed[row], bb = sRed[128 + row];
+            pairbar();
+            return is_max ? fmaxf(a, bb) : a + bb;
+        };
+        auto wait_scores = [&]() {
+            mbar_wait(&s_full[grp], ph_s);
+            ph_s ^= 1;
             tc_fence_after();
         };
-        // this warp's columns [lo, hi) of a key half with nh columns: half 0 gets the share rounded UP to a 32-column group,
-        // so that the (slower) masked tail group falls to half 1, which has fewer columns
-        auto col_range = [&](int nh, int& lo, int& hi) {
-            const int split = min(nh, (((nh + 1) >> 1) + 31) & ~31);
-            lo = hf == 0 ? 0 : split;
-            hi = hf == 0 ? split : nh;
-        };
-
-        // exp2((s - shift) * c) of this thread's columns of the key half [key0, key0 + nh) -> packed bf16 pairs in registers
-        // (up to 3 groups of 32 columns); returns the partial row sum.  Columns past the half or past T give exact zeros.
-        uint32_t pk[48];
-        auto softmax_pass = [&](int key0, int nh, float shift_c) {
-            int lo, hi;
-            col_range(nh, lo, hi);
+        // exp2((s - shift) * c) of chunk ch, 32 columns at a time; the packed bf16 pairs go straight back into TMEM over
+        // the scores just read (pair (2k, 2k+1) of the chunk's columns lands in column k).  Returns the partial row sum.
+        auto softmax_chunk = [&](int ch, float shift_c) {
+            const int nk = min(FWD_CHUNK, tk - ch * FWD_CHUNK);  // columns of this chunk
+            const int nreal = T - ch * FWD_CHUNK;                // real (un-padded) keys from column 0 on
             float sm0 = 0.0f, sm1 = 0.0f;
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                const int c0 = lo + g * 32;
-                if (c0 < hi) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_row + c0, r);
+            for (int g = 0; g < FWD_CHUNK / 32; ++g) {
+                const int c0 = g * 32;
+                if (c0 < nk) {
+                    uint32_t r[32], pk[16];
+                    tmem_ld_32x32(t_buf + c0, r);
                     tmem_ld_wait();
-                    const int nv = min(hi, T - key0) - c0;  // real keys among the 32 columns of this group
+                    const int nv = min(nk, nreal) - c0;  // real keys among the 32 columns of this group
                     if (nv >= 32) {
                         // The row sum adds the fp32 probabilities (their bf16 rounding in the PV product is unbiased; the
                         // difference is ~1e-4 relative, far below bf16 resolution)
@@ -300,7 +295,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
                             const float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
                             const float x1 = fmaf(__uint_as_float(r[e + 1]), c, -shift_c);
                             const float p1 = ((e >> 1) & 1) ? fwd_ex2_poly(x1) : fwd_ex2(x1);  // every 4th on the FMA pipe
-                            pk[g * 16 + e / 2] = pack_bf16(p0, p1);
+                            pk[e / 2] = pack_bf16(p0, p1);
                             sm0 += p0;
                             sm1 += p1;
                         }
@@ -311,93 +306,69 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
                             float p1 = fwd_ex2(fmaf(__uint_as_float(r[e + 1]), c, -shift_c));
                             if (e >= nv) p0 = 0.0f;
                             if (e + 1 >= nv) p1 = 0.0f;
-                            pk[g * 16 + e / 2] = pack_bf16(p0, p1);
+                            pk[e / 2] = pack_bf16(p0, p1);
                             sm0 += p0;
                             sm1 += p1;
                         }
                     }
+                    tmem_st_32x16(t_buf + (c0 >> 1), pk);
                 }
             }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive_warp(&p_full[grp]);
             return sm0 + sm1;
         };
-        auto max_pass = [&](int key0, int nh) {
-            int lo, hi;
-            col_range(nh, lo, hi);
+        auto max_chunk = [&](int ch) {
+            const int nk = min(FWD_CHUNK, tk - ch * FWD_CHUNK);
+            const int nreal = T - ch * FWD_CHUNK;
             float mx = -INFINITY;
-            for (int c0 = lo; c0 < hi; c0 += 32) {
+            for (int c0 = 0; c0 < nk; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_32x32(t_buf + c0, r);
                 tmem_ld_wait();
-                const int nv = min(hi, T - key0) - c0;
+                const int nv = min(nk, nreal) - c0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (j < nv) mx = fmaxf(mx, __uint_as_float(r[j]));
             }
-            return mx;
-        };
-        // packed P -> TMEM, in place over the scores: the pair (2k, 2k+1) of S columns lands in column k.  The partner
-        // warp of the quadrant reads score columns that these stores overwrite, hence the pair barrier first.
-        auto store_p = [&](int nh) {
-            int lo, hi;
-            col_range(nh, lo, hi);
-            quadbar();
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                const int c0 = lo + g * 32;
-                if (c0 < hi) tmem_st_32x16(t_row + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(&pk[g * 16]));
-            }
-            tmem_st_wait();
             tc_fence_before();
-            mbar_arrive_warp(bar_p);
-        };
-        // the two warps of a quadrant hold complementary columns of the same rows
-        auto pair_exchange = [&](float mine, bool is_max) {
-            sRed[hf * 128 + row] = mine;
-            quadbar();
-            const float a = sRed[row], bb = sRed[128 + row];
-            quadbar();
-            return is_max ? fmaxf(a, bb) : a + bb;
+            mbar_arrive_warp(&p_full[grp]);  // scores consumed
+            return mx;
         };
 
         for (int i = 0; i < nqb; ++i) {
-            // Normal mode: one pass per key half, shift = the row's score against key 0.  Safe mode (after an overflowing
-            // row sum; uniform for the CTA, the control warp replays the MMAs): maxima of half 0 and half 1 first, then
-            // the exponentials of half 1 (still in TMEM) and of half 0 (recomputed) with the max shift.
-            const int nhalves = n1 > 0 ? 2 : 1;
             float shift = 0.0f, total = 0.0f;
             bool safe = false;
 #pragma unroll 1
             for (;;) {
-                if (safe) {
+                bool have_scores = false;  // group 0 has already waited for chunk 0 (to read the shift)
+                if (!safe) {
+                    // shift = the row's score against key 0 (column 0 of chunk 0, which group 0 owns)
+                    if (grp == 0) {
+                        wait_scores();
+                        have_scores = true;
+                        shift = __uint_as_float(tmem_ld_32x1(t_buf));
+                        tmem_ld_wait();
+                        sShift[row] = shift;
+                    }
+                    pairbar();
+                    if (grp == 1) shift = sShift[row];
+                } else {
                     float mx = -INFINITY;
 #pragma unroll 1
-                    for (int k = 0; k < nhalves; ++k) {
-                        mbar_wait(bar_s, ph_s);
-                        ph_s ^= 1;
-                        tc_fence_after();
-                        mx = fmaxf(mx, max_pass(k == 0 ? 0 : n0, k == 0 ? n0 : n1));
-                        if (k + 1 < nhalves) {
-                            tc_fence_before();
-                            mbar_arrive_warp(bar_p);  // half 0 read: the score columns may take half 1
-                        }
+                    for (int ch = grp; ch < nch; ch += 2) {
+                        wait_scores();
+                        mx = fmaxf(mx, max_chunk(ch));
                     }
                     shift = pair_exchange(mx, true);
                 }
                 float part = 0.0f;
 #pragma unroll 1
-                for (int k = 0; k < nhalves; ++k) {
-                    const int half = (safe && nhalves == 2) ? 1 - k : k;
-                    if (!(safe && k == 0)) {  // (in safe mode the first half to exponentiate is already in TMEM)
-                        mbar_wait(bar_s, ph_s);
-                        ph_s ^= 1;
-                        tc_fence_after();
-                    }
-                    if (!safe && k == 0) {
-                        shift = __uint_as_float(tmem_ld_32x1(t_row));  // score against key 0
-                        tmem_ld_wait();
-                    }
-                    part += softmax_pass(half == 0 ? 0 : n0, half == 0 ? n0 : n1, shift * c);
-                    store_p(half == 0 ? n0 : n1);
+                for (int ch = grp; ch < nch; ch += 2) {
+                    if (!have_scores) wait_scores();
+                    have_scores = false;
+                    part += softmax_chunk(ch, shift * c);
                 }
                 total = pair_exchange(part, false);
                 if (safe) break;
@@ -413,17 +384,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
             }
             mbar_wait(bar_o, ph_o);
             ph_o ^= 1;
-            // ---- epilogue: O / sum -> bf16 -> global, straight from registers (each half converts 32 of the 64 columns) ----
+            // ---- epilogue: O / sum -> bf16 -> global, straight from registers (each group converts 32 of the 64 columns) ----
             tc_fence_after();
             uint32_t o0[32];
-            tmem_ld_32x32(t_row + FWD_TMEM_O + hf * 32, o0);
+            tmem_ld_32x32(t_row + FWD_TMEM_O + grp * 32, o0);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive_warp(bar_of);
             const float inv = 1.0f / total;
             const int t = i * 128 + row;
             if (t < T) {
-                uint4* dst = reinterpret_cast<uint4*>(args.out + (static_cast<size_t>(b) * T + t) * inner + h * 64 + hf * 32);
+                uint4* dst = reinterpret_cast<uint4*>(args.out + (static_cast<size_t>(b) * T + t) * inner + h * 64 + grp * 32);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t* src = &o0[g * 8];
@@ -434,7 +405,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) attn_fwd_kernel(const __grid_c
                     o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
                     dst[g] = o;
                 }
-                if (hf == 0) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = shift * args.scale + logf(total);
+                if (grp == 0) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = shift * args.scale + logf(total);
             }
         }
     }

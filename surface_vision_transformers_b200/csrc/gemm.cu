@@ -82,13 +82,9 @@ __device__ __forceinline__ float dgelu_f(float x) {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int WBUF_BYTES = 32 * 128;        // one epilogue-warp staging box: 32 rows x 128 B (128B-swizzled)
 #ifndef SVIT_EPI_WARPS
 #define SVIT_EPI_WARPS 8
 #endif
-constexpr int EPI_WARPS = SVIT_EPI_WARPS;   // multiple of 4: EPI_NP warps per TMEM lane quadrant
-constexpr int EPI_NP = EPI_WARPS / 4;
-constexpr int TN_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + the epilogue warps
 constexpr int SMEM_LIMIT = 232448;          // 227 KB
 
 struct TnArgs {
@@ -101,20 +97,33 @@ struct TnArgs {
 
 constexpr int ARES_KB = 6;  // A-resident mode: up to 6 K blocks (K <= 384) of the A row block stay in shared memory
 
+// Epilogue geometry.  EW epilogue warps (a multiple of 4: EW / 4 warps per TMEM lane quadrant); a warp's staging box is
+// 32 rows x BOXB bytes.  The GELU epilogues (~20 instructions per element, two MUFU among them) are bound by the issue
+// rate of their warps: with 8 warps (2 per SM sub-partition) dependent-issue latency caps them at ~57 % of the issue
+// slots, so those modes run 16 warps (4 per sub-partition) on 64-byte boxes -- half-width units, the same 64 KB of
+// staging, the same operand ring depth.
 template <int MODE, bool ARES>
 struct EpiTraits {
     static constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU || MODE == EPI_MUL);
     static constexpr bool TWO_OUT = (MODE == EPI_GELU || MODE == EPI_GELU_GRAD);
+    static constexpr bool HEAVY = (MODE == EPI_GELU || MODE == EPI_GELU_GRAD || MODE == EPI_GELU_ONLY);
+    static constexpr int EW = HEAVY ? 16 : SVIT_EPI_WARPS;   // epilogue warps
+    static constexpr int NP = EW / 4;                          // warps per TMEM lane quadrant
+    static constexpr int BOXB = HEAVY ? 64 : 128;              // bytes per staging-box row (= TMA swizzle span)
+    static constexpr int WBUF = 32 * BOXB;                     // one staging box
+    static constexpr int THREADS = 128 + 32 * EW;              // 4 control warps + the epilogue warps
     // staging boxes per epilogue warp: in-place aux/out rotation of 3, two outputs double-buffered, or one output x2
     // (the A-resident variant gives 96 KB to the A row block and makes do with 2 boxes per warp)
-    static constexpr int NBUF = (ARES || EPI_WARPS > 8) ? 2 : (HAS_AUX ? 3 : 2);
+    static constexpr int NBUF = (HEAVY || ARES || EW > 8) ? 2 : (HAS_AUX ? 3 : 2);
 };
 
 template <int BN, int CG, int MODE, bool ARES>
 struct TnCfg {
+    using ET = EpiTraits<MODE, ARES>;
     static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;  // with a CTA pair every CTA holds half of the B rows
-    static constexpr int EPI_BYTES = EPI_WARPS * EpiTraits<MODE, ARES>::NBUF * WBUF_BYTES;
-    static constexpr int FIXED_BYTES = 1024 /*align slack*/ + EPI_BYTES + EPI_WARPS * 256 /*bias*/ + 1024 /*barriers*/;
+    static constexpr int EPI_BYTES = ET::EW * ET::NBUF * ET::WBUF;
+    static constexpr int BAR_BYTES = ET::EW > 8 ? 2048 : 1024;
+    static constexpr int FIXED_BYTES = 1024 /*align slack*/ + EPI_BYTES + ET::EW * 256 /*bias*/ + BAR_BYTES;
     // A and B share one ring (stage = A block + B block) -- or A keeps ARES_KB fixed slots and only B is a ring
     static constexpr int STAGE_BYTES = ARES ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int A_SLOTS_FIXED = ARES ? ARES_KB : 0;
@@ -142,11 +151,12 @@ struct TnCfg {
 // only its B tile past it.  Tiles are then handed out as contiguous m-major ranges (one range per cluster) so that a
 // cluster re-loads A only when it crosses into the next row block.
 template <typename OutT, int MODE, int BN, int CG, bool ARES>
-__global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_constant__ TnArgs args) {
+__global__ void __launch_bounds__((EpiTraits<MODE, ARES>::THREADS), 1) gemm_tn_kernel(const __grid_constant__ TnArgs args) {
     using Cfg = TnCfg<BN, CG, MODE, ARES>;
     using ET = EpiTraits<MODE, ARES>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr int UC = 128 / (int)sizeof(OutT);  // columns per epilogue unit (one 128-byte row of the staging box)
+    constexpr int EPI_WARPS = ET::EW, EPI_NP = ET::NP, BOXB = ET::BOXB, WBUF_BYTES = ET::WBUF;
+    constexpr int UC = BOXB / (int)sizeof(OutT);  // columns per epilogue unit (one row of the staging box)
     constexpr int UNITS = BN / UC;
     static_assert(BN % UC == 0, "BN must be a multiple of the epilogue unit");
     constexpr bool HAS_AUX = ET::HAS_AUX;
@@ -339,14 +349,19 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         // ===================== aux (residual / pre-activation) loader =====================
         // serves the per-warp rings in job order; job k of a warp lands in ring slot k % 3
         if (HAS_AUX && elect_one()) {
-            int kcnt[EPI_NP] = {};  // jobs issued so far per warp group
+            // jobs issued so far per warp group -- scalars, not an indexed array: a dynamically indexed local array lives
+            // in local memory, and with ~227 KB of the unified L1 / shared memory taken by the tiles every access of this
+            // (single, latency-critical) thread would be an L2 round trip
+            static_assert(EPI_NP <= 4, "job counters are kept in four scalars");
+            int kc0 = 0, kc1 = 0, kc2 = 0, kc3 = 0;
             int it = 0;
             for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
                 const int m0 = (tile / tiles_n) * TM + row_off;
                 const int n0 = (tile % tiles_n) * BN;
                 for (int u = 0; u < UNITS; ++u) {
                     const int p = (it * UNITS + u) % EPI_NP;
-                    const int k = kcnt[p]++;
+                    const int k = p == 0 ? kc0 : p == 1 ? kc1 : p == 2 ? kc2 : kc3;
+                    if (p == 0) ++kc0; else if (p == 1) ++kc1; else if (p == 2) ++kc2; else ++kc3;
                     const int slot = k % NBUF;
                     const uint32_t ph = (k / NBUF) & 1;
 #pragma unroll 1
@@ -367,7 +382,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
         const int p = ew >> 2;         // this warp owns the units u with (it * UNITS + u) % EPI_NP == p
         uint8_t* wbuf = sEpi + ew * NBUF * WBUF_BYTES;
         float* wbias = sBias + ew * 64;
-        const int sw = lane & 7;       // swizzle key of this thread's row inside a 32-row box
+        // swizzle key of this thread's row inside a 32-row box: 128-byte rows XOR the 16-byte chunk index with row % 8,
+        // 64-byte rows (SWIZZLE_64B) with (row / 2) % 4
+        const int sw = BOXB == 128 ? (lane & 7) : ((lane >> 1) & 3);
         constexpr int CPH = 32 * (int)sizeof(OutT) / 16;  // 16-byte chunks per 32-column half of a unit (4 bf16, 8 fp32)
         int it = 0, k = 0;             // k = jobs done by this warp
         for (int tile = first_tile; tile < end_tile; tile += tile_stride, ++it) {
@@ -415,7 +432,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                     if (lane == 0) tma_store_wait_read<1>();
                     __syncwarp();
                 }
-                uint8_t* orow = obuf + lane * 128;
+                uint8_t* orow = obuf + lane * BOXB;
                 // ---- the unit in 32-column halves: TMEM -> registers -> fused epilogue -> staging box ----
 #pragma unroll 1
                 for (int hh = 0; hh < UC / 32; ++hh) {
@@ -491,7 +508,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                         }
                     } else {
                         if constexpr (MODE == EPI_GELU_GRAD) {
-                            uint8_t* orow2 = obuf2 + lane * 128;
+                            uint8_t* orow2 = obuf2 + lane * BOXB;
 #pragma unroll
                             for (int c = 0; c < CPH; ++c) {
                                 float g[8], dg[8];
@@ -522,7 +539,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_kernel(const __grid_con
                             }
                         }
                         if (MODE == EPI_GELU || MODE == EPI_GELU_ONLY) {
-                            uint8_t* orow2 = (MODE == EPI_GELU) ? obuf2 + lane * 128 : orow;
+                            uint8_t* orow2 = (MODE == EPI_GELU) ? obuf2 + lane * BOXB : orow;
 #pragma unroll
                             for (int c = 0; c < CPH; ++c) {
                                 float g[8];
@@ -792,7 +809,7 @@ static int launch_tn_inst(const TnArgs& a, int num_sms, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(groups * CG);
-    cfg.blockDim = dim3(TN_THREADS);
+    cfg.blockDim = dim3(EpiTraits<MODE, ARES>::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -858,10 +875,13 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
     rc |= make_tmap_2d(&a.tmB, d.B, TmapDtype::BF16, d.K, d.N, (uint64_t)d.ldb * 2, BK, BN / cg);
     const TmapDtype odt = d.out_f32 ? TmapDtype::F32 : TmapDtype::BF16;
     const int osz = d.out_f32 ? 4 : 2;
-    rc |= make_tmap_2d(&a.tmOut, d.out, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
-    if (d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD) rc |= make_tmap_2d(&a.tmOut2, d.out2, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
+    // staging-box row of the mode's epilogue (EpiTraits::BOXB): the GELU epilogues use 64-byte boxes
+    const bool heavy = d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD || d.mode == EPI_GELU_ONLY;
+    const int box_cols = (heavy ? 64 : 128) / osz;
+    rc |= make_tmap_2d(&a.tmOut, d.out, odt, d.N, d.M, (uint64_t)d.ldo * osz, box_cols, 32);
+    if (d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD) rc |= make_tmap_2d(&a.tmOut2, d.out2, odt, d.N, d.M, (uint64_t)d.ldo * osz, box_cols, 32);
     if (d.mode == EPI_RESID || d.mode == EPI_DGELU || d.mode == EPI_MUL)
-        rc |= make_tmap_2d(&a.tmAux, d.aux, odt, d.N, d.M, (uint64_t)d.ldo * osz, 128 / osz, 32);
+        rc |= make_tmap_2d(&a.tmAux, d.aux, odt, d.N, d.M, (uint64_t)d.ldo * osz, box_cols, 32);
     if (rc != 0) {
         set_error("gemm_tn: tensor map creation failed: %s", tmap_last_error());
         return -3;

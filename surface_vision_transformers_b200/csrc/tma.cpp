@@ -33,7 +33,8 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, TmapDtype dt, uint64_t inne
     std::call_once(g_once, resolve);
     if (!g_encode) return -1;
     const uint32_t esz = dt == TmapDtype::BF16 ? 2 : 4;
-    if (box_inner * esz != 128 || box_outer == 0 || box_outer > 256 || (row_pitch_bytes & 15) ||
+    const uint32_t span = box_inner * esz;  // bytes per box row = swizzle span
+    if ((span != 128 && span != 64) || box_outer == 0 || box_outer > 256 || (row_pitch_bytes & 15) ||
         (reinterpret_cast<uintptr_t>(gptr) & 15)) {
         snprintf(g_err, sizeof(g_err),
                  "make_tmap_2d: bad geometry ptr=%p inner=%llu outer=%llu pitch=%llu box=%ux%u", gptr,
@@ -47,7 +48,7 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, TmapDtype dt, uint64_t inne
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(out, dt == TmapDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                           2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(g_err, sizeof(g_err),

@@ -9,8 +9,8 @@ namespace svit {
 
 enum class TmapDtype { BF16, F32 };
 
-// 2-D row-major tensor [outer][inner] with a row pitch in bytes, 128-byte swizzled box.
-// box_inner * elem_size must be 128 bytes; box_outer <= 256.
+// 2-D row-major tensor [outer][inner] with a row pitch in bytes, swizzled box.
+// box_inner * elem_size must be 128 bytes (SWIZZLE_128B) or 64 bytes (SWIZZLE_64B); box_outer <= 256.
 // Returns 0 on success, a CUresult otherwise.
 int make_tmap_2d(CUtensorMap* out, const void* gptr, TmapDtype dt, uint64_t inner, uint64_t outer,
                  uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer);

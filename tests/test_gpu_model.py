@@ -30,14 +30,20 @@ def global_grad_rel(named_ours, named_ref):
     return (num / den).sqrt().item()
 
 
-def check_grads(ours, oracle, tol=2 * TOL):
+def check_grads(ours, oracle, tol=TOL):
+    """EVERY gradient tensor within the north-star tolerance (1e-2 relative L2) of the fp32 oracle; the worst one is
+    printed (pytest -s / the failure message) so the margin stays visible."""
     ref = dict(oracle.named_parameters())
+    worst = (0.0, None)
     for n, p in ours.named_parameters():
         assert (p.grad is None) == (ref[n].grad is None), n
         if p.grad is not None:
             assert torch.isfinite(p.grad).all(), n
-            assert rel_l2(p.grad, ref[n].grad) < tol, n
-    assert global_grad_rel(list(ours.named_parameters()), oracle.named_parameters()) < TOL
+            worst = max(worst, (rel_l2(p.grad, ref[n].grad), n))
+    glob = global_grad_rel(list(ours.named_parameters()), oracle.named_parameters())
+    print(f"gradients: worst tensor {worst[1]} rel-L2 {worst[0]:.2e}, all tensors together {glob:.2e}")
+    assert worst[0] < tol, worst
+    assert glob < TOL
 
 
 @pytest.mark.parametrize("name", ["sit_cls", "sit_mean"])
@@ -60,7 +66,7 @@ def test_sit_matches_golden_and_oracle(name):
     assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < TOL
     for k, p in model.named_parameters():
         assert not bool(g["grad_none/" + k]) and p.grad is not None
-        assert rel_l2(subsample(p.grad.cpu()), g["grad_sub/" + k]) < 2 * TOL, k
+        assert rel_l2(subsample(p.grad.cpu()), g["grad_sub/" + k]) < TOL, k
     # eval / no_grad path (tools/testing.py:76-88), also with batch 1 (bs_val: 1)
     model.eval()
     with torch.no_grad():
@@ -90,7 +96,7 @@ def test_mpp_matches_golden():
     for k, p in ssl.named_parameters():
         assert bool(g["grad_none/" + k]) == (p.grad is None), k       # mlp_head.* unreachable -> None, like the reference
         if p.grad is not None:
-            assert rel_l2(subsample(p.grad.cpu()), g["grad_sub/" + k]) < 2 * TOL, k
+            assert rel_l2(subsample(p.grad.cpu()), g["grad_sub/" + k]) < TOL, k
     # eval + no_grad keeps masking active (tools/pretrain.py:345-356)
     ssl.eval()
     with torch.no_grad():
@@ -129,7 +135,11 @@ def test_sit_vs_oracle_full_configs(name):
         xe = oracle.to_patch_embedding(x)
         xe = torch.cat((oracle.cls_token.expand(B, -1, -1), xe), 1) + oracle.pos_embedding
         assert rel_l2(model.transformer(xe), oracle.transformer(xe)) < TOL
-    assert rel_l2(out_m, out_o) < 3 * TOL
+    # the scalar head output nearly cancels (LayerNorm of the cls row, then a dot product): its relative error amplifies
+    # the encoder's, so it keeps a 3e-2 bound -- the measured value is printed; every other tensor is held to 1e-2
+    head_err = rel_l2(out_m, out_o)
+    print(f"{name}: head output rel-L2 {head_err:.2e}")
+    assert head_err < 3 * TOL
     check_grads(model, oracle)
 
 
@@ -637,7 +647,11 @@ def test_dropout_bf16_matches_oracle_with_same_masks(name):
     torch.nn.functional.mse_loss(out_o.squeeze(), y).backward()
     out_m = model(x)                                       # offset 0
     torch.nn.functional.mse_loss(out_m.squeeze(), y).backward()
-    assert rel_l2(out_m, out_o) < 3 * TOL
+    # the scalar head output nearly cancels (LayerNorm of the cls row, then a dot product): its relative error amplifies
+    # the encoder's, so it keeps a 3e-2 bound -- the measured value is printed; every other tensor is held to 1e-2
+    head_err = rel_l2(out_m, out_o)
+    print(f"{name}: head output rel-L2 {head_err:.2e}")
+    assert head_err < 3 * TOL
     check_grads(model, oracle)
     from oracle.dropout import install
     install(oracle, 0.1, 0.1, 77, 1)                       # the next forward of `model` uses offset 1
@@ -650,7 +664,7 @@ def test_dropout_bf16_matches_oracle_with_same_masks(name):
     w = torch.randn_like(yo)
     (ye * w).sum().backward()
     (yo * w).sum().backward()
-    assert rel_l2(xe.grad, xo.grad) < 2 * TOL
+    assert rel_l2(xe.grad, xo.grad) < TOL
     enc = [(n, p) for n, p in model.named_parameters() if n.startswith("transformer.")]
     assert global_grad_rel(enc, oracle.named_parameters()) < TOL
 
