@@ -221,7 +221,7 @@ def run_sweep(args):
                 with torch.no_grad():
                     return model(x)
             opt.zero_grad(set_to_none=True)
-            loss = runner(x)[0] if kind == "mpp" else torch.nn.functional.mse_loss(runner(x).squeeze(), y)
+            loss = runner(x)[0] if kind == "mpp" else svit.regression_loss(runner(x), y)
             loss.backward()
             opt.step()
             return loss
@@ -334,7 +334,7 @@ def main():
         if kind == "mpp":
             loss, _ = runner(x)
         else:
-            loss = torch.nn.functional.mse_loss(runner(x).squeeze(), y)
+            loss = svit.regression_loss(runner(x), y)     # MSELoss(mean) of train.py:245-248 in one launch
         loss.backward()
         opt.step()
         return loss

@@ -158,6 +158,11 @@ int svit_adamw_advance(svit_adam_segment* segs_dev, int nsegs, float beta1, floa
 int svit_sgd_step(float* p, const float* g, float* momentum_buf, long long n, float lr, float momentum, float dampening,
                   float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 
+/* Regression criterion of the reference's training loop (tools/train.py:245-248 constructor, :288 use): nn.MSELoss(mean)
+ * (l1 = 0) or nn.L1Loss() (l1 = 1) of out[n] (= outputs.squeeze(), fp32) against target[n].  One launch writes the scalar
+ * *loss and dout[n] = d loss / d out, so the criterion's backward needs no kernel of its own. */
+int svit_regression_loss(const float* out, const float* target, int n, int l1, float* loss, float* dout, void* stream);
+
 /* ---- kernel-level entry points ---- */
 int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void* aux, const float* bias,
                  const float* rowtab, int rowtab_period, int M, int N, int K, int lda, int ldb, int ldo, int mode,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "svit_adamw_step": (ci, [vp, vp, vp, vp, vp, ci, vp, ci, cf, cf, cf, cf, cf, ci, cf, vp]),
     "svit_adamw_advance": (ci, [vp, ci, cf, cf, vp]),
     "svit_sgd_step": (ci, [vp, vp, vp, cll, cf, cf, cf, cf, ci, ci, cf, vp]),
+    "svit_regression_loss": (ci, [vp, vp, ci, ci, vp, vp, vp]),
     "svit_gemm_tn": (ci, [vp] * 7 + [ci] * 10 + [vp]),
     "svit_gemm_wgrad": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),
     "svit_gemm_wgrad_bias": (ci, [vp, vp, vp, vp] + [ci] * 7 + [vp]),

@@ -941,4 +941,43 @@ int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, floa
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// regression criterion of tools/train.py:245-248, 288: nn.MSELoss(reduction='mean') or nn.L1Loss() on outputs.squeeze()
+// vs targets.  ONE launch produces the scalar loss and d loss / d out (so the backward pass of the criterion is free);
+// one block, fixed-order tree reduction: deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void regression_loss_kernel(const float* __restrict__ out, const float* __restrict__ target, int n, int l1,
+                                       float* __restrict__ loss, float* __restrict__ dout) {
+    __shared__ float red[256];
+    const float inv_n = 1.0f / static_cast<float>(n);
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float d = out[i] - target[i];
+        if (l1) {
+            acc += fabsf(d);
+            dout[i] = (d > 0.0f ? inv_n : (d < 0.0f ? -inv_n : 0.0f));   // torch: sign(0) = 0
+        } else {
+            acc += d * d;
+            dout[i] = 2.0f * d * inv_n;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = red[0] * inv_n;
+}
+int launch_regression_loss(const float* out, const float* target, int n, int l1, float* loss, float* dout, cudaStream_t st) {
+    if (n <= 0) {
+        set_error("regression_loss: empty batch");
+        return -1;
+    }
+    regression_loss_kernel<<<1, 256, 0, st>>>(out, target, n, l1, loss, dout);
+    SVIT_CHECK_LAUNCH("regression_loss");
+    return 0;
+}
+
 }  // namespace svit

@@ -100,4 +100,7 @@ int launch_adamw(float* p, const float* g, float* m, float* v, const AdamSegment
 int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float dampening,
                float weight_decay, int nesterov, int first_step, float grad_scale, cudaStream_t st);
 
+// loss = mean((out - target)^2) (l1 = 0) or mean(|out - target|) (l1 = 1) over n elements; dout[i] = d loss / d out[i]
+int launch_regression_loss(const float* out, const float* target, int n, int l1, float* loss, float* dout, cudaStream_t st);
+
 }  // namespace svit

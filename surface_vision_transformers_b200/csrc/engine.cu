@@ -871,6 +871,10 @@ int svit_sgd_step(float* p, const float* g, float* mom, long long n, float lr, f
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+int svit_regression_loss(const float* out, const float* target, int n, int l1, float* loss, float* dout, void* stream) {
+    return launch_regression_loss(out, target, n, l1, loss, dout, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void* aux, const float* bias, const float* rowtab,
                  int rowtab_period, int M, int N, int K, int lda, int ldb, int ldo, int mode, int out_f32, int num_sms,
                  void* stream) {

@@ -45,10 +45,17 @@ class DataParallel(torch.nn.Module):
     """Wraps a B200 ``SiT`` or ``masked_patch_pretraining``: forwards calls unchanged and installs the gradient
     hooks that overlap the flat-buffer all-reduce with backward.  ``broadcast_parameters`` syncs the replicas once."""
 
-    def __init__(self, module, process_group=None, broadcast_parameters=True):
+    def __init__(self, module, process_group=None, broadcast_parameters=True, overlap=None):
+        """``overlap``: True = all-reduce every stage's range as soon as its gradients are final (communication runs
+        under the remaining backward kernels); False = one all-reduce of the whole flat buffer after backward.
+        Default: the SVIT_DDP_OVERLAP environment variable if set, else True."""
         super().__init__()
         self.module = module
         self.reducer = FlatGradReducer(process_group)
+        if overlap is None:
+            import os
+            overlap = os.environ.get("SVIT_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
         sit = getattr(module, "transformer", None)
         self._sit = module if hasattr(module, "stage_segment") else sit
         if self._sit is None or not hasattr(self._sit, "stage_segment"):
@@ -65,7 +72,11 @@ class DataParallel(torch.nn.Module):
 
     def _on_stage(self, sit, stage, G):
         if stage is None:
+            if not self.overlap:
+                self.reducer.reduce_range(G, 0, G.numel())
             self.reducer.finish()
+            return
+        if not self.overlap:
             return
         if stage == "all":
             self.reducer.reduce_range(G, 0, G.numel())

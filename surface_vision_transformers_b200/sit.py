@@ -85,7 +85,9 @@ def _stream(device):
 
 class _SiTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, img, *params):
+    def forward(ctx, model, img, mesh_args, *params):
+        # mesh_args: None for pre-patched input (B,C,N,V), or (table, n_mesh, ch_mean, ch_std) for raw meshes (B,C,n_mesh):
+        # the gather (tools/preprocessing.py:79-84) and z-score (:72) then run inside the patch-packing kernel
         B = img.shape[0]
         dev = img.device
         model._refresh_shadow(dev, force=True)
@@ -96,8 +98,9 @@ class _SiTFunction(torch.autograd.Function):
         out = torch.empty(B, model.num_classes, dtype=torch.float32, device=dev)
         ctx.drop = model._next_dropout_state()
         model._apply_dropout_state(ctx.drop)
+        table, n_mesh, ch_mean, ch_std = mesh_args if mesh_args is not None else (None, 0, None, None)
         check(lib.svit_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(img), B,
-                               vp(0), 0, vp(0), vp(0), ptr(out), 1, _stream(dev)), "svit_forward")
+                               ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std), ptr(out), 1, _stream(dev)), "svit_forward")
         ctx.model = model
         ctx.ws = ws
         ctx.B = B
@@ -118,7 +121,7 @@ class _SiTFunction(torch.autograd.Function):
                                     ptr(G), hook, vp(0), _stream(ctx.dev)), "svit_backward")
             model._finish_progress_hook(G)
         ctx.ws = None
-        return (None, None) + model._grad_views(G)
+        return (None, None, None) + model._grad_views(G)
 
 
 class _EncoderFunction(torch.autograd.Function):
@@ -384,7 +387,7 @@ class SiT(nn.Module):
             return img.new_zeros((0, self.num_classes)) + 0.0 * self.mlp_head[1].bias.sum()
         with torch.cuda.device(img.device):   # the engine launches on the CURRENT device's stream
             if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
-                return _SiTFunction.apply(self, img, *self._plist)
+                return _SiTFunction.apply(self, img, None, *self._plist)
             return self.infer(img)
 
     @torch.no_grad()
@@ -403,10 +406,25 @@ class SiT(nn.Module):
 
     def forward_mesh(self, mesh, table, ch_mean=None, ch_std=None):
         """raw ico-6 mesh (B,C,40962) + gather table (V,N) int32 -> prediction; the patch gather
-        (tools/preprocessing.py:79-84) and optional z-score (:72) are fused into the patch packing kernel."""
+        (tools/preprocessing.py:79-84) and optional z-score (:72) are fused into the patch packing kernel that writes
+        the embedding GEMM's bf16 operand -- no gathered fp32 copy of the input exists.  Works with autograd (training
+        straight from raw meshes: the backward pass reads the packed operand the forward left in its workspace)."""
+        if mesh.dim() != 3 or mesh.shape[1] != self.num_channels:
+            raise ValueError(f"expected raw meshes (B,{self.num_channels},n_vertices), got {tuple(mesh.shape)}")
+        if not mesh.is_cuda:
+            raise RuntimeError("SiT (B200) needs a CUDA input: there is no CPU fallback")
+        if tuple(table.shape) != (self.num_vertices, self.num_patches) or table.dtype != torch.int32:
+            raise ValueError(f"gather table must be int32 ({self.num_vertices},{self.num_patches}), got {table.dtype} "
+                             f"{tuple(table.shape)}")
         mesh = mesh.contiguous().float()
+        table = table.contiguous()
+        if ch_mean is not None:
+            ch_mean = torch.as_tensor(ch_mean, dtype=torch.float32, device=mesh.device).contiguous()
+            ch_std = torch.as_tensor(ch_std, dtype=torch.float32, device=mesh.device).contiguous()
         with torch.cuda.device(mesh.device):
-            return self.infer(mesh, table=table.contiguous(), n_mesh=mesh.shape[-1], ch_mean=ch_mean, ch_std=ch_std)
+            if mesh.shape[0] > 0 and torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
+                return _SiTFunction.apply(self, mesh, (table, mesh.shape[-1], ch_mean, ch_std), *self._plist)
+            return self.infer(mesh, table=table, n_mesh=mesh.shape[-1], ch_mean=ch_mean, ch_std=ch_std)
 
     def _encoder(self, x):
         if not x.is_cuda:

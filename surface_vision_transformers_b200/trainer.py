@@ -20,6 +20,7 @@ import torch.distributed as dist
 
 from .ddp import DataParallel
 from .loader import DevicePrefetcher
+from .loss import RegressionLoss
 
 __all__ = ["fit", "evaluate", "fit_mpp"]
 
@@ -40,7 +41,7 @@ def evaluate(model, dataset, batch_size, device, l1loss=False):
     """Validation pass of tools/train.py:311-337: returns (sum of batch losses, MAE, predictions, targets) with the
     statistics AND the predictions / targets of all ranks combined (host tensors, dataset order)."""
     rank, world = _dist_info()
-    criterion = torch.nn.L1Loss() if l1loss else torch.nn.MSELoss(reduction="mean")
+    criterion = RegressionLoss(l1loss)      # train.py:245-248, one launch for loss and its gradient
     net = model.module if isinstance(model, DataParallel) else model
     was_training = net.training
     net.eval()
@@ -88,7 +89,7 @@ def fit(model, optimizer, train_set, val_set=None, *, epochs, batch_size, val_ba
     if world > 1 and not isinstance(model, DataParallel):
         net = DataParallel(model)
     core = net.module if isinstance(net, DataParallel) else net
-    criterion = torch.nn.L1Loss() if l1loss else torch.nn.MSELoss(reduction="mean")
+    criterion = RegressionLoss(l1loss)      # train.py:245-248, one launch for loss and its gradient
     gen = torch.Generator()
     history = dict(train_loss=[], train_mae=[], val_loss=[], val_mae=[], lr=[])
     best_mae, best_epoch = float("inf"), None

@@ -367,3 +367,55 @@ def test_full_batch_256_two_layer_slice_vs_oracle():
         xe = oracle.to_patch_embedding(x[:64])
         xe = torch.cat((oracle.cls_token.expand(64, -1, -1), xe), 1) + oracle.pos_embedding
         assert rel_l2(model.transformer(xe), oracle.transformer(xe)) < TOL
+
+
+def test_training_from_raw_meshes_vs_oracle():
+    """SURVEY 8(f)-1 with autograd: forward_mesh() gathers (tools/preprocessing.py:79-84) and z-scores (:72) the raw ico-6
+    meshes inside the kernel that packs the patch-embedding operand, and trains from there.  Reference side: the numpy
+    restatement of the reference's preprocessing produces the patched array, the fp32 oracle trains on it.  Loss,
+    prediction and every gradient (the patch-embedding weight in particular) agree within the bf16 tolerance."""
+    from oracle import gather_oracle
+    cfg = dict(dim=192, depth=2, heads=3, mlp_dim=768, num_patches=320, num_vertices=153)
+    B = 3
+    torch.manual_seed(0)
+    rs = np.random.RandomState(11)
+    mesh = (rs.standard_normal((B, 4, 40962)) * 2 + 1).astype(np.float32)
+    means = np.array([1.15, 0.037, 1.0, 0.07], dtype=np.float32)
+    stds = np.array([0.41, 0.19, 0.39, 4.05], dtype=np.float32)
+    table = svit.load_index_table(2)
+    normalised = (mesh - means.reshape(1, 4, 1)) / stds.reshape(1, 4, 1)
+    patched = torch.from_numpy(gather_oracle.gather_patches(normalised, table.numpy()).astype(np.float32))
+    assert tuple(patched.shape) == (B, 4, 320, 153)
+    oracle = OracleSiT(**cfg).to(DEV)
+    model = svit.SiT(**cfg)
+    model.load_state_dict(oracle.state_dict())
+    model.to(DEV)
+    y = torch.rand(B, device=DEV) * 19 + 26
+    out_o = oracle(patched.to(DEV)); lo = F.mse_loss(out_o.squeeze(), y); lo.backward()
+    out_m = model.forward_mesh(torch.from_numpy(mesh).to(DEV), table.to(DEV), torch.from_numpy(means).to(DEV),
+                               torch.from_numpy(stds).to(DEV))
+    lm = F.mse_loss(out_m.squeeze(), y); lm.backward()
+    assert rel_l2(out_m, out_o) < 3 * TOL and abs(lm.item() - lo.item()) / lo.item() < 3 * TOL
+    w = worst_grad(model, oracle)
+    print(f"training from raw meshes: worst gradient tensor {w[1]} rel-L2 {w[0]:.2e}")
+    assert w[0] < TOL, w
+
+
+@pytest.mark.parametrize("l1", [False, True])
+def test_fused_regression_loss_matches_torch_criterion(l1):
+    """svit.regression_loss == nn.MSELoss(reduction='mean') / nn.L1Loss() on outputs.squeeze() (train.py:245-248, 288):
+    value and gradient, incl. an exact zero residual (sign(0) = 0 for L1) and an upstream scale."""
+    torch.manual_seed(0)
+    out = (torch.rand(37, 1, device=DEV) * 19 + 26).requires_grad_(True)
+    tgt = torch.rand(37, device=DEV) * 19 + 26
+    with torch.no_grad():
+        out[5, 0] = tgt[5]
+    ref_out = out.detach().clone().requires_grad_(True)
+    crit = nn.L1Loss() if l1 else nn.MSELoss(reduction="mean")
+    ref = crit(ref_out.squeeze(), tgt)
+    (ref * 3.0).backward()
+    got = svit.regression_loss(out, tgt, l1loss=l1)
+    (got * 3.0).backward()
+    assert got.dim() == 0 and abs(got.item() - ref.item()) / ref.item() < 1e-6
+    assert torch.allclose(out.grad, ref_out.grad, rtol=1e-6, atol=1e-9)
+    assert float(out.grad[5, 0]) == 0.0
