@@ -167,6 +167,12 @@ int svit_regression_loss(const float* out, const float* target, int n, int l1, f
 int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void* aux, const float* bias,
                  const float* rowtab, int rowtab_period, int M, int N, int K, int lda, int ldb, int ldo, int mode,
                  int out_f32, int num_sms, void* stream);
+/* Residual Linear + the LayerNorm that follows it, one kernel (dim 384): x_out = A W^T + bias + x_in (fp32),
+ * a_out = LayerNorm(x_out) * gamma + beta (bf16), mean / rstd per row.  Replaces `x = fn(x) + x` of one PreNorm block and
+ * the `norm` of the next (vit_pytorch Transformer.forward; keys utils/utils.py:18-23,28-31). */
+int svit_gemm_ln(const void* A, const void* W, const float* bias, const float* x_in, float* x_out, void* a_out,
+                 const float* gamma, const float* beta, float* mean, float* rstd, int M, int D, int K, int lda, int ldb,
+                 float eps, int num_sms, void* stream);
 int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int K, int ldy, int ldx, int ldw,
                     int num_sms, void* stream);
 /* same, and dbias[N] += sum over the M rows of dY (bias gradient of the Linear, fused as one extra MMA) */

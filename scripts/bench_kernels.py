@@ -52,6 +52,16 @@ if "gemm" in which:
     gemm("gemm dfc2  [M,384]x[1536] * stored gelu'", 1536, 384, 6, False)
     gemm("gemm dfc1  [M,1536]x[384] store bf16", 384, 1536, 0, False)
     gemm("gemm dqkv  [M,1152]x[384] store bf16", 384, 1152, 0, False)
+if "gemm" in which:
+    # residual Linear + the next LayerNorm in one kernel (gemm_ln.cu) vs the two launches it replaces
+    for (K, nm) in ((384, "out"), (1536, "fc2")):
+        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16(); W = (torch.randn(D, K, device=dev) * 0.05).bfloat16()
+        bias = torch.zeros(D, device=dev); xin = torch.randn(M, D, device=dev); xo = torch.empty(M, D, device=dev)
+        ao = torch.empty(M, D, device=dev, dtype=torch.bfloat16); g = torch.ones(D, device=dev); bt = torch.zeros(D, device=dev)
+        mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
+        by = M*K*2 + D*K*2 + M*D*4*2 + M*D*2
+        timeit(f"gemm_ln {nm}  [M,{K}]x[384] resid f32 + LN", lambda: lib.svit_gemm_ln(ptr(A), ptr(W), ptr(bias), ptr(xin), ptr(xo), ptr(ao), ptr(g), ptr(bt), ptr(mean), ptr(rstd), M, D, K, K, K, 1e-5, SMS, st()),
+               bytes_=by, flops=2.0*M*D*K)
 if "wgrad" in which:
     for (N, K) in [(1152, 384), (384, 384), (1536, 384), (384, 1536), (384, 640)]:
         dY = (torch.randn(M, N, device=dev) * 0.5).bfloat16(); X = (torch.randn(M, K, device=dev) * 0.5).bfloat16()

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct svit_engine {
     // dropout state of the next forward / backward (svit_set_dropout); p = 0 disables a site
     float drop_p, drop_emb_p;
     unsigned long long drop_seed, drop_offset;
+    int no_fuse_ln;  // SVIT_NO_FUSE_LN=1: keep the stand-alone LayerNorm kernels (A/B timing)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -171,6 +173,14 @@ static int wgrad(const svit_engine* e, cudaStream_t st, const void* dY, int ldy,
     return launch_gemm_wgrad(d, e->num_sms, st);
 }
 
+// x_out = A W^T + bias + x_in and, in the same kernel, the LayerNorm that follows (gemm_ln.cu)
+static int gemm_ln(const svit_engine* e, cudaStream_t st, const void* A, int lda, const void* W, int ldb, const float* bias,
+                   const float* x_in, float* x_out, const float* gamma, const float* beta, void* a_out, float* mean,
+                   float* rstd, int M, int K) {
+    GemmLnDesc d{A, W, bias, x_in, x_out, a_out, gamma, beta, mean, rstd, M, e->D, K, lda, ldb, 1e-5f};
+    return launch_gemm_ln(d, e->num_sms, st);
+}
+
 static inline DropoutSite drop_layer(const svit_engine* e, int l, int which) {
     return DropoutSite{e->drop_seed, e->drop_offset, dropout_site_layer(l, which), e->drop_p};
 }
@@ -208,21 +218,30 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
     const float scale = 0.125f;  // dim_head ** -0.5 with dim_head = 64
     const bool drop = e->drop_p > 0.0f;  // extra passes (dropout.cuh); the p = 0 launch sequence is unchanged
+    // Without dropout (every shipped config) and for the width the fused tile is built for, each residual Linear also
+    // produces the LayerNorm of the NEXT sub-layer (gemm_ln.cu): to_out -> LN2 of the same block, fc2 -> LN1 of the
+    // next block.  Only the very first LayerNorm of the encoder is a kernel of its own then.
+    const bool fuse_ln = !drop && gemm_ln_supported(D) && !e->no_fuse_ln;
     const size_t nD = static_cast<size_t>(M) * D, nmlp = static_cast<size_t>(M) * mlp;
     const float* xin = x_in;
     for (int l = 0; l < e->depth; ++l) {
         LayerWs& L = w.L[l];
         const float* lp = P;
         auto pp = [&](int which) { return lp + e->poff[pidx_layer(l, which)]; };
-        RET_IF(launch_ln_fwd(xin, pp(LN1_W), pp(LN1_B), L.a1, L.mean1, L.rstd1, M, D, 1e-5f, st));
+        if (l == 0 || !fuse_ln) RET_IF(launch_ln_fwd(xin, pp(LN1_W), pp(LN1_B), L.a1, L.mean1, L.rstd1, M, D, 1e-5f, st));
         RET_IF(gemm(e, st, L.a1, D, shp(sh, e->sh_qkv) + static_cast<size_t>(l) * 3 * I * D, D, L.qkv, 3 * I, M, 3 * I, D,
                     EPI_STORE, 0));
         AttnDesc ad{L.qkv, L.O, L.lse, w.B, e->H, e->T, scale};
         RET_IF(launch_attn_fwd(ad, st));
-        RET_IF(gemm(e, st, L.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, L.xmid, D, M, D, I, EPI_RESID, 1,
-                    pp(OUT_B), xin));
-        if (drop) RET_IF(launch_dropout_residual(L.xmid, xin, nD, drop_layer(e, l, DROP_SITE_TO_OUT), st));
-        RET_IF(launch_ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
+        if (fuse_ln) {
+            RET_IF(gemm_ln(e, st, L.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, pp(OUT_B), xin, L.xmid,
+                           pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, I));
+        } else {
+            RET_IF(gemm(e, st, L.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, L.xmid, D, M, D, I, EPI_RESID, 1,
+                        pp(OUT_B), xin));
+            if (drop) RET_IF(launch_dropout_residual(L.xmid, xin, nD, drop_layer(e, l, DROP_SITE_TO_OUT), st));
+            RET_IF(launch_ln_fwd(L.xmid, pp(LN2_W), pp(LN2_B), L.a2, L.mean2, L.rstd2, M, D, 1e-5f, st));
+        }
         if (w.training) {
             // training keeps gelu'(u) (in L.u) instead of u: the backward epilogue is then a single multiply
             RET_IF(gemm(e, st, L.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, L.u, mlp, M, mlp, D,
@@ -233,9 +252,16 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
         }
         // the same mask on gelu(u) and on the stored gelu'(u): d/du [gelu(u) m / (1-p)] = gelu'(u) m / (1-p)
         if (drop) RET_IF(launch_dropout_scale(L.h, w.training ? L.u : nullptr, nmlp, 1, drop_layer(e, l, DROP_SITE_FF_ACT), st));
-        RET_IF(gemm(e, st, L.h, mlp, shp(sh, e->sh_w2) + static_cast<size_t>(l) * D * mlp, mlp, L.xout, D, M, D, mlp,
-                    EPI_RESID, 1, pp(FC2_B), L.xmid));
-        if (drop) RET_IF(launch_dropout_residual(L.xout, L.xmid, nD, drop_layer(e, l, DROP_SITE_FF_OUT), st));
+        if (fuse_ln && l + 1 < e->depth) {
+            LayerWs& Ln = w.L[l + 1];
+            auto pn = [&](int which) { return P + e->poff[pidx_layer(l + 1, which)]; };
+            RET_IF(gemm_ln(e, st, L.h, mlp, shp(sh, e->sh_w2) + static_cast<size_t>(l) * D * mlp, mlp, pp(FC2_B), L.xmid, L.xout,
+                           pn(LN1_W), pn(LN1_B), Ln.a1, Ln.mean1, Ln.rstd1, M, mlp));
+        } else {
+            RET_IF(gemm(e, st, L.h, mlp, shp(sh, e->sh_w2) + static_cast<size_t>(l) * D * mlp, mlp, L.xout, D, M, D, mlp,
+                        EPI_RESID, 1, pp(FC2_B), L.xmid));
+            if (drop) RET_IF(launch_dropout_residual(L.xout, L.xmid, nD, drop_layer(e, l, DROP_SITE_FF_OUT), st));
+        }
         xin = L.xout;
     }
     *x_final = xin;
@@ -554,6 +580,7 @@ svit_engine* svit_create(const svit_config* cfg) {
     e->wdec_f32 = nullptr;
     e->drop_p = e->drop_emb_p = 0.0f;
     e->drop_seed = e->drop_offset = 0;
+    e->no_fuse_ln = getenv("SVIT_NO_FUSE_LN") != nullptr && atoi(getenv("SVIT_NO_FUSE_LN")) != 0;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int sms = 0;
@@ -869,6 +896,13 @@ int svit_sgd_step(float* p, const float* g, float* mom, long long n, float lr, f
                   float weight_decay, int nesterov, int first_step, float grad_scale, void* stream) {
     return launch_sgd(p, g, mom, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int svit_gemm_ln(const void* A, const void* W, const float* bias, const float* x_in, float* x_out, void* a_out,
+                 const float* gamma, const float* beta, float* mean, float* rstd, int M, int D, int K, int lda, int ldb, float eps,
+                 int num_sms, void* stream) {
+    GemmLnDesc d{A, W, bias, x_in, x_out, a_out, gamma, beta, mean, rstd, M, D, K, lda, ldb, eps};
+    return launch_gemm_ln(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int svit_regression_loss(const float* out, const float* target, int n, int l1, float* loss, float* dout, void* stream) {

@@ -53,6 +53,25 @@ struct GemmWgradDesc {
 };
 int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream);
 
+// Residual Linear + the following LayerNorm in one kernel (gemm_ln.cu):
+//   x_out = A W^T + bias + x_in (fp32) ; a_out = LayerNorm(x_out) * gamma + beta (bf16) ; mean, rstd per row
+struct GemmLnDesc {
+    const void* A;       // bf16 [M, K], row pitch lda
+    const void* W;       // bf16 [D, K], row pitch ldb
+    const float* bias;   // [D] or nullptr
+    const float* x_in;   // fp32 [M, D] residual
+    float* x_out;        // fp32 [M, D]
+    void* a_out;         // bf16 [M, D]
+    const float* gamma;  // [D]
+    const float* beta;   // [D]
+    float* mean;         // [M]
+    float* rstd;         // [M]
+    int M, D, K, lda, ldb;
+    float eps;
+};
+bool gemm_ln_supported(int D);
+int launch_gemm_ln(const GemmLnDesc& d, int num_sms, cudaStream_t stream);
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);  // kernels launched through this library (svit_launch_count)
 

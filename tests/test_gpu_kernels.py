@@ -358,3 +358,41 @@ def test_adamw_kernel_matches_torch(env):
         assert torch.allclose(p, q, rtol=2e-5, atol=1e-6)
     sd = a.state_dict()
     assert len(sd["state"]) == len(ref)
+
+
+@pytest.mark.parametrize("M,K", [(845, 384), (845, 1536), (5, 384), (256, 64), (20544, 1536), (82176, 384)])
+def test_gemm_ln_residual_linear_plus_layernorm(env, M, K):
+    """svit_gemm_ln (gemm_ln.cu): x_out = A W^T + bias + x_in in fp32 and, from the same accumulator tile, the LayerNorm
+    of the next sub-layer (bf16 output, mean, rstd) -- against fp32 torch on the same bf16 operands.  Ragged M (partial
+    256-row tile), a single K block, several persistent waves."""
+    dev, lib = env["dev"], env["lib"]
+    D = 384
+    torch.manual_seed(M + K)
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    W = (torch.randn(D, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(D, device=dev) * 0.1
+    x_in = torch.randn(M, D, device=dev) * 2 + 0.3
+    gamma = torch.rand(D, device=dev) + 0.5
+    beta = torch.randn(D, device=dev) * 0.1
+    x_out = torch.full((M, D), float("nan"), device=dev)
+    a_out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    mean = torch.empty(M, device=dev)
+    rstd = torch.empty(M, device=dev)
+    check(lib.svit_gemm_ln(ptr(A), ptr(W), ptr(bias), ptr(x_in), ptr(x_out), ptr(a_out), ptr(gamma), ptr(beta), ptr(mean),
+                           ptr(rstd), M, D, K, K, K, 1e-5, env["sms"], stream()), "gemm_ln")
+    torch.cuda.synchronize()
+    ref_x = A.float() @ W.float().t() + bias + x_in
+    assert rel_l2(x_out, ref_x) < 1e-5
+    ref_mean = ref_x.mean(1)
+    ref_rstd = (ref_x.var(1, unbiased=False) + 1e-5).rsqrt()
+    assert rel_l2(mean, ref_mean) < 1e-5 and rel_l2(rstd, ref_rstd) < 1e-5
+    ref_a = torch.nn.functional.layer_norm(ref_x, (D,), gamma, beta, 1e-5)
+    assert rel_l2(a_out.float(), ref_a) < 4e-3        # bf16 rounding of the output only
+    # the stand-alone kernels give the same answer (what the fused launch replaces)
+    x2 = torch.empty(M, D, device=dev)
+    a2 = torch.empty_like(a_out); m2 = torch.empty(M, device=dev); r2 = torch.empty(M, device=dev)
+    check(lib.svit_gemm_tn(ptr(A), ptr(W), ptr(x2), vp(0), ptr(x_in), ptr(bias), vp(0), 1, M, D, K, K, K, D, 2, 1, env["sms"],
+                           stream()), "gemm_tn")
+    check(lib.svit_layernorm_fwd(ptr(x2), ptr(gamma), ptr(beta), ptr(a2), ptr(m2), ptr(r2), M, D, 1e-5, stream()), "ln")
+    torch.cuda.synchronize()
+    assert rel_l2(x_out, x2) < 1e-6 and rel_l2(a_out.float(), a2.float()) < 2e-3
