@@ -1,0 +1,25 @@
+#!/bin/bash
+# GPU batch r2f: full GPU suite (no -x), ARES experiment for the GELU / MUL GEMMs, step bench, all-kernel ncu capture, workload sweep
+O=gpurun_out
+python -m pytest tests -m gpu -q -s 2>&1 | grep -v Warning | grep -E "passed|failed|FAILED|Error|worst|rel-L2" | tail -40 > $O/r2f_tests.log
+python scripts/bench_kernels.py gemm > $O/r2f_kernels.log 2>&1
+SVIT_GEMM_ARES=1 python scripts/bench_kernels.py gemm > $O/r2f_kernels_ares.log 2>&1
+python bench.py --steps 20 --warmup 5 > $O/r2f_bench.log 2>&1
+python bench.py --sweep $O/r2f_workloads.json --steps 10 --warmup 3 > $O/r2f_sweep.log 2>&1
+python scripts/ncu_all.py > $O/r2f_all_plain.log 2>&1 && ncu --set full --clock-control none --import-source on --profile-from-start off -o $O/r2f_all python scripts/ncu_all.py > $O/r2f_all_ncu.log 2>&1
+cat $O/r2f_tests.log; paste -d'|' $O/r2f_kernels.log $O/r2f_kernels_ares.log | awk -F'|' '{printf "%-46s %s   ARES: %s\n", substr($1,1,44), substr($1,45,12), substr($2,45,12)}'
+python - <<'PY'
+import json
+for f in ('gpurun_out/r2f_bench.log',):
+    l=[x for x in open(f) if x.startswith('{')]
+    if l:
+        d=json.loads(l[-1]); print(f, 'bench', d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'], d['gpu_launches'])
+    else:
+        print(f, open(f).read()[-1500:])
+try:
+    for r in json.load(open('gpurun_out/r2f_workloads.json')):
+        print(r['config']['workload'], r['config']['batch_per_gpu'], round(r['value']), round(r['ms_per_step'],2), round(r['roofline']['frac'],3))
+except Exception as e:
+    print('sweep failed', e, open('gpurun_out/r2f_sweep.log').read()[-800:])
+PY
+tail -3 $O/r2f_all_ncu.log
