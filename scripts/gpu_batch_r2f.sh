@@ -1,6 +1,16 @@
 #!/bin/bash
 # GPU batch r2f: full GPU suite (no -x), ARES experiment for the GELU / MUL GEMMs, step bench, all-kernel ncu capture, workload sweep
 O=gpurun_out
+# the attention backward with 16 compute warps is new: fall back to the previous schedule for the rest of the batch if
+# its kernel tests do not pass
+if ! python -m pytest tests/test_gpu_kernels.py -q -x -k "attn or attention" > $O/r2f_attn_tests.log 2>&1; then
+  echo "ATTENTION TESTS FAILED with the new backward -> SVIT_ATTN_BWD_V1=1 for the rest" | tee -a $O/r2f_attn_tests.log
+  export SVIT_ATTN_BWD_V1=1
+fi
+tail -3 $O/r2f_attn_tests.log
+python scripts/bench_attn.py > $O/r2f_attn.log 2>&1; SVIT_ATTN_BWD_V1=1 python scripts/bench_attn.py > $O/r2f_attn_v1.log 2>&1
+cat $O/r2f_attn.log $O/r2f_attn_v1.log
+python scripts/prof_attn_bwd.py > $O/r2f_bwd_timeline.log 2>&1; head -14 $O/r2f_bwd_timeline.log
 python -m pytest tests -m gpu -q -s 2>&1 | grep -v Warning | grep -E "passed|failed|FAILED|Error|worst|rel-L2" | tail -40 > $O/r2f_tests.log
 python scripts/bench_kernels.py gemm > $O/r2f_kernels.log 2>&1
 SVIT_GEMM_ARES=1 python scripts/bench_kernels.py gemm > $O/r2f_kernels_ares.log 2>&1

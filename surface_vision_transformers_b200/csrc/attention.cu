@@ -743,8 +743,12 @@ constexpr int BK_BAR = BK_SDS + 3 * TILE_BYTES;
 constexpr int BK_DELTA = BK_BAR + 256;          // [3][128] fp32: delta * scale of every query row
 constexpr int BK_SMEM = 1024 + BK_DELTA + 3 * 128 * 4;
 static_assert(BK_SMEM <= 232448, "attn_bwd shared memory");
-constexpr int BK_THREADS = 512;  // warp group 0: MMA warps X and Y (+ 2 idle warps), warp groups 1..3: 12 compute warps
-constexpr int BK_REGS_MMA = 56, BK_REGS_COMPUTE = 152;  // setmaxnreg: 4 * 56 + 12 * 152 = 16 * 128
+constexpr int BK_COMPUTE_WARPS = 16;
+constexpr int BK_COMPUTE_THREADS = 32 * BK_COMPUTE_WARPS;
+constexpr int BK_THREADS = 128 + BK_COMPUTE_THREADS;  // warp group 0: MMA warps X and Y (+ 2 idle warps), then 16 compute warps
+constexpr int BK_SLAB = BK_KEYS / (BK_COMPUTE_WARPS / 4);  // 24 key columns per compute warp
+constexpr int BK1_THREADS = 512;
+constexpr int BK_REGS_MMA = 56, BK_REGS_COMPUTE = 152;  // (v1) setmaxnreg: 4 * 56 + 12 * 152 = 16 * 128
 constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
@@ -773,6 +777,453 @@ __device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
 }
 
 __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + BK_SQ;
+    uint8_t* sdO = smem + BK_SDO;
+    uint8_t* sKV = smem + BK_SKV;
+    uint8_t* sP = smem + BK_SP;
+    uint8_t* sdS = smem + BK_SDS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BK_BAR);
+    uint64_t* q_full = bars + 0;     // [3] Q_i and dO_i landed (once per CTA)
+    uint64_t* kv_full = bars + 4;    // [2]
+    uint64_t* s_full = bars + 8;     // S in TMEM                      (MMA -> compute warps)
+    uint64_t* s_free = bars + 9;     // S copied to registers          (compute warps -> MMA)
+    uint64_t* dp_full = bars + 10;   // dP in TMEM                     (MMA -> compute warps)
+    uint64_t* dp_free = bars + 11;   // dP copied to registers         (compute warps -> MMA)
+    uint64_t* p_full = bars + 12;    // P tile written                 (compute warps -> MMA)
+    uint64_t* p_free = bars + 13;    // c(p) retired                   (MMA X -> compute warps)
+    uint64_t* ds_full = bars + 14;   // [2] dS tile p & 1 written      (compute warps -> MMA)
+    uint64_t* ds_free = bars + 16;   // [2] d(p) retired               (MMA -> compute warps)
+    uint64_t* dv_full = bars + 18;   // dV_j final (c(j, last) retired)  (MMA X -> compute warps)
+    uint64_t* dv_free = bars + 19;   // dV_j copied to registers         (compute warps -> MMA X)
+    uint64_t* dk_full = bars + 20;   // dK_j final (d(j, last) retired)  (MMA Y -> compute warps)
+    uint64_t* dk_free = bars + 21;   // dK_j copied to registers         (compute warps -> MMA Y)
+    uint64_t* dq_full = bars + 22;   // every MMA of the CTA retired     (MMA -> compute warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int T = args.T, H = args.H;
+    const int inner = H * 64;
+    const int nqb = (T + 127) / 128;
+    const int nkb = (T + BK_KEYS - 1) / BK_KEYS;
+    const int total = nqb * nkb;
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&args.tmQ);
+        tma_prefetch_desc(&args.tmDO);
+        tma_prefetch_desc(&args.tmKV);
+        tma_prefetch_desc(&args.tmDQ);
+        tma_prefetch_desc(&args.tmO);
+        tma_prefetch_desc(&args.tmDKV);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&ds_full[s], BK_COMPUTE_WARPS);
+            mbar_init(&ds_free[s], 1);
+        }
+        for (int i = 0; i < 3; ++i) mbar_init(&q_full[i], 1);
+        mbar_init(s_full, 1);
+        mbar_init(s_free, BK_COMPUTE_WARPS);
+        mbar_init(dp_full, 1);
+        mbar_init(dp_free, BK_COMPUTE_WARPS);
+        mbar_init(p_full, BK_COMPUTE_WARPS);
+        mbar_init(p_free, 1);
+        mbar_init(dv_full, 1);
+        mbar_init(dv_free, 8);
+        mbar_init(dk_full, 1);
+        mbar_init(dk_free, 8);
+        mbar_init(dq_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // The issuing warps need few registers, the compute warps many: move them (per warp group of 4 warps).  Each
+    // setmaxnreg sits at the top of the role branch it governs: ptxas allocates a region by the setmaxnreg that dominates
+    // it (after a common if / else it may fall back to the smaller limit).
+
+    auto load_kv = [&](int j) {  // K_j, V_j -> stage j & 1 (called by one thread)
+        const int s = j & 1;
+        uint8_t* dst = sKV + s * 2 * BK_KV_TILE;
+        mbar_expect_tx(&kv_full[s], 2 * BK_KV_TILE);
+        tma_load_3d(dst, &args.tmKV, &kv_full[s], inner + h * 64, j * BK_KEYS, b);
+        tma_load_3d(dst + BK_KV_TILE, &args.tmKV, &kv_full[s], 2 * inner + h * 64, j * BK_KEYS, b);
+    };
+
+    if (warp < 4) {
+      if (warp == 0) {
+        // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
+        if (elect_one()) {
+            auto load_q = [&](int i) {
+                mbar_expect_tx(&q_full[i], 3 * TILE_BYTES);
+                tma_load_3d(sQ + i * TILE_BYTES, &args.tmQ, &q_full[i], h * 64, i * 128, b);
+                tma_load_3d(sdO + i * TILE_BYTES, &args.tmDO, &q_full[i], h * 64, i * 128, b);
+                tma_load_3d(sdS + i * TILE_BYTES, &args.tmO, &q_full[i], h * 64, i * 128, b);  // O_i: only for delta, before any dS
+            };
+            load_q(0);
+            load_kv(0);
+            for (int i = 1; i < nqb; ++i) load_q(i);
+            if (nkb > 1) load_kv(1);
+        }
+      }
+      if (warp < 2) {
+        // ================================ MMA issuers ================================
+        // warp 0 (X): a(p+1) = S, c(p) = dV.   warp 1 (Y): b(p+1) = dP, d(p) = dQ, dK.
+        // Descriptors are (lo, hi) 32-bit pairs; a K-step adds a constant to lo (see ptx.cuh).
+        if (elect_one()) {
+            const bool X = warp == 0;
+            constexpr uint32_t hi = umma_desc_hi(1024);
+            const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);   // dK / dV: A = P^T / dS^T (MN-major), B MN-major
+            const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ    : A = dS (K-major), B = K (MN-major)
+            // K-major operand tile (Q, dO, K, V): K-step = 32 B;  MN-major operand: K-step = 16 rows = 2048 B
+            const uint32_t kmaj0 = umma_desc_lo(smem_u32(X ? sQ : sdO), 16);          // A of a / b, + slot * TILE
+            const uint32_t kv0 = umma_desc_lo(smem_u32(sKV + (X ? 0 : BK_KV_TILE)), 16);  // B of a (K_j) / b (V_j), + stage
+            const uint32_t tr0 = umma_desc_lo(smem_u32(X ? sP : sdS), TILE_BYTES);    // A of c / dK: P^T / dS^T (+ dS buffer)
+            const uint32_t mn0 = umma_desc_lo(smem_u32(X ? sdO : sQ), 8192);          // B of c / dK: dO_i / Q_i, + slot * TILE
+            const uint32_t dsk0 = umma_desc_lo(smem_u32(sdS), 16);                    // A of dQ: dS, K-major (+ dS buffer)
+            const uint32_t kmn0 = umma_desc_lo(smem_u32(sKV), 8192);                  // B of dQ: K_j MN-major, + stage
+            auto keys_in = [&](int j) { return min(BK_KEYS, T - j * BK_KEYS); };
+            auto rows_in = [&](int i) { return min(128, T - i * 128); };
+            auto issue_ab = [&](int j, int i) {  // X: S = Q_i K_j^T      Y: dP = dO_i V_j^T
+                const uint32_t a_lo = kmaj0 + i * (TILE_BYTES >> 4);
+                const uint32_t b_lo = kv0 + (j & 1) * (2 * BK_KV_TILE >> 4);
+                const uint32_t idesc = umma_idesc_bf16(128, (keys_in(j) + 15) & ~15, 0, 0);
+                const uint32_t d = tmem_base + (X ? BK_T_S : BK_T_DP);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss_lohi(d, a_lo + k * 2, b_lo + k * 2, hi, idesc, k != 0);
+                umma_commit(X ? s_full : dp_full);
+            };
+            if (X) PROF(0);
+            mbar_wait(&q_full[0], 0);
+            mbar_wait(&kv_full[0], 0);
+            if (X) PROF(1);
+            tc_fence_after();
+            issue_ab(0, 0);
+            int p = 0;
+            for (int j = 0; j < nkb; ++j) {
+                const int ks_k = (keys_in(j) + 15) >> 4;  // K steps over the keys of this block
+                for (int i = 0; i < nqb; ++i, ++p) {
+                    const uint32_t pp = p & 1;
+                    const bool has_next = p + 1 < total;
+                    const int jn = (i + 1 < nqb) ? j : j + 1;
+                    const int in = (i + 1 < nqb) ? i + 1 : 0;
+                    const int ks_q = (rows_in(i) + 15) >> 4;  // K steps over the queries of this block
+                    if (has_next) {
+                        mbar_wait(X ? s_free : dp_free, pp);
+                        if (in == 0) mbar_wait(&kv_full[jn & 1], (jn >> 1) & 1);
+                        mbar_wait(&q_full[in], 0);
+                        tc_fence_after();
+                        issue_ab(jn, in);
+                    }
+                    if (p < 8) PROF((X ? 10 : 12) + p * 4);
+                    if (X) mbar_wait(p_full, pp);
+                    else mbar_wait(&ds_full[pp], (p >> 1) & 1);
+                    if (p < 8) PROF((X ? 11 : 13) + p * 4);
+                    if (i == 0 && j > 0) mbar_wait(X ? dv_free : dk_free, (j - 1) & 1);  // dV_{j-1} / dK_{j-1} were copied out
+                    tc_fence_after();
+                    const uint32_t b_lo = mn0 + i * (TILE_BYTES >> 4);
+                    if (X) {
+                        // c(p): dV_j += P^T dO_i
+#pragma unroll
+                        for (int s = 0; s < 8; ++s)
+                            if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DV, tr0 + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
+                        umma_commit(p_free);
+                    } else {
+                        // d(p): dQ_i += dS K_j ; dK_j += dS^T Q_i
+                        const uint32_t k_lo = kmn0 + (j & 1) * (2 * BK_KV_TILE >> 4);
+#pragma unroll
+                        for (int s = 0; s < 6; ++s)
+                            if (s < ks_k)
+                                umma_ss_lohi(tmem_base + BK_T_DQ + i * 64,
+                                             (s < 4 ? dsk0 + pp * (TILE_BYTES >> 4) + s * 2
+                                                    : dsk0 + (2 * TILE_BYTES >> 4) + pp * 4 + (s - 4) * 2),
+                                             k_lo + s * 128, hi, idesc_dq, (j | s) != 0);
+                        // dS^T as MN-major A: keys 0..63 from tile pp, keys 64..127 from the shared tile (LBO spans the gap)
+                        const uint32_t dst_lo = umma_desc_lo(smem_u32(sdS) + pp * TILE_BYTES, (2 - pp) * TILE_BYTES + pp * 64);
+#pragma unroll
+                        for (int s = 0; s < 8; ++s)
+                            if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DK, dst_lo + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
+                        umma_commit(&ds_free[pp]);
+                    }
+                    if (i == nqb - 1) umma_commit(X ? dv_full : dk_full);
+                }
+            }
+            if (!X) umma_commit(dq_full);
+            if (X) PROF(2);
+        }
+      }
+    } else {
+        // ================================ compute warps ================================
+        // 16 warps (four per SM sub-partition): warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and
+        // the 24 key columns [24 slab, 24 slab + 24) of every 96-key block -- for the probabilities AND for dS, so P(p)
+        // stays in registers (packed bf16) from the step that computes it to the step that needs it.
+        const int q = warp & 3;
+        const int slab = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int c0 = slab * BK_SLAB;
+        const float c = args.scale_log2e;
+        const int sw = row & 7;
+        const bool prof_thread = threadIdx.x == 128;
+        // ---- prologue: delta * scale = rowsum(dO * O) * scale of query block `slab` -> smem, then everybody reads its rows.
+        // O_i arrives by TMA in the (still unused) dS tiles next to dO_i: per-thread global loads of these rows took
+        // 11,000 clocks here, the TMA tiles land in about 1,500.
+        float* sdl = reinterpret_cast<float*>(smem + BK_DELTA);
+        if (prof_thread) PROF(90);
+        if (slab < nqb) {
+            mbar_wait(&q_full[slab], 0);
+            const uint8_t* orow = sdS + slab * TILE_BYTES + row * 128;
+            const uint8_t* drow = sdO + slab * TILE_BYTES + row * 128;
+            float acc = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                acc += dot8_bf16(*reinterpret_cast<const uint4*>(orow + ((g ^ sw) << 4)), *reinterpret_cast<const uint4*>(drow + ((g ^ sw) << 4)));
+            sdl[slab * 128 + row] = acc * args.scale;  // rows past T were zero-filled by the TMA
+        }
+        // Query rows past T: lse = +inf makes their probabilities exact zeros (S = 0 there: the TMA zero-fills Q), and with
+        // P = 0, dP = 0 (dO zero-filled) and delta = 0 their dS is an exact zero too -- no masking needed for rows.
+        float lse2[3], sdelta[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int t = i * 128 + row;
+            lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : __int_as_float(0x7f800000);
+        }
+        if (prof_thread) PROF(91);
+        named_bar_sync(1, BK_COMPUTE_THREADS);
+        if (prof_thread) PROF(92);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sdelta[i] = sdl[i * 128 + row];
+
+        // Key block jb is complete: dK | dV (TMEM columns [192, 320), lane = key, eight 16-column parts, two per slab: slabs
+        // 0, 1 take dK, slabs 2, 3 take dV) -> bf16 -> the block's own K / V stage (every MMA that read it has retired) ->
+        // two TMA stores; then the stage is refilled with block jb+2.  Per-thread global stores from here crawl (32 rows
+        // per request, and the LSU starves while the tensor core streams operands from shared memory).
+        auto store_kv = [&](int jb) {
+            const bool key_warp = q * 32 < min(BK_KEYS, T - jb * BK_KEYS);
+            uint8_t* stage = sKV + (jb & 1) * 2 * BK_KV_TILE;
+            if (slab < 2) mbar_wait(dk_full, jb & 1);
+            else mbar_wait(dv_full, jb & 1);
+            if (prof_thread && jb == 0) PROF(70);
+            tc_fence_after();
+            if (key_warp) {
+#pragma unroll 1
+                for (int a = slab * 2; a < slab * 2 + 2; ++a) {
+                    uint32_t o[16];
+                    tmem_ld_32x16(t_row + BK_T_DK + a * 16, o);
+                    tmem_ld_wait();
+                    uint8_t* trow = stage + (a >> 2) * BK_KV_TILE + row * 128;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+                        v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                        v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                        v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                        *reinterpret_cast<uint4*>(trow + ((((a & 3) * 2 + g) ^ sw) << 4)) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            if (slab < 2) mbar_arrive_warp(dk_free);
+            else mbar_arrive_warp(dv_free);
+            if (prof_thread && jb == 0) PROF(71);
+            fence_proxy_async_smem();
+            named_bar_sync(2, BK_COMPUTE_THREADS);
+            if (prof_thread && jb == 0) PROF(72);
+            if (warp == 4 && lane == 0) {
+                tma_store_3d(&args.tmDKV, stage, inner + h * 64, jb * BK_KEYS, b);
+                tma_store_3d(&args.tmDKV, stage + BK_KV_TILE, 2 * inner + h * 64, jb * BK_KEYS, b);
+                tma_store_commit();
+            }
+        };
+        // one step later the stores have long read the stage: refill it with block jb+2 (waiting right away would stall
+        // this warp, and with it every hand-off of the step, for the ~1,500 clocks the TMA needs to drain 24 KB)
+        auto reload_kv = [&](int jb) {
+            if (warp == 4 && lane == 0 && jb + 2 < nkb) {
+                tma_store_wait_read<0>();
+                load_kv(jb + 2);
+            }
+        };
+
+        // Step p = pair (j, i) first turns P(p) (in registers since the previous step) and dP(p) into dS(p) and hands it
+        // to the tensor core (dQ_i, dK_j), then computes P(p+1) from S(p+1) (dV_j needs it, and so does the next step).
+        // S(p+1) and dP(p) were issued one step earlier, as soon as their TMEM buffers had been read out, so neither wait
+        // sees the tensor pipe's latency.  The two halves of a step are NOT interleaved by hand: with four warps per
+        // sub-partition the FMA-heavy dS half of one warp overlaps the MUFU-heavy P half of another, and keeping only one
+        // 24-column operand live at a time leaves the registers that let four warps fit.
+        // Both halves compute all 24 columns unconditionally; slabs that contain keys past the block's end (the last key
+        // block only) then clear those entries with integer masks, which also kills whatever stale TMEM contents (columns
+        // beyond the MMA's N extent) may have produced.
+        uint32_t pk[BK_SLAB / 2];  // P(p), then dS(p), of this thread's 24 columns, packed bf16 (exact zeros where masked)
+        auto clear_unreal = [&](int jj) {
+            const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns
+            if (nv >= BK_SLAB) return;                            // warp-uniform
+#pragma unroll
+            for (int k = 0; k < BK_SLAB / 2; ++k) pk[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
+        };
+        auto load_slab = [&](uint32_t col, uint32_t (&v)[BK_SLAB]) {
+#pragma unroll
+            for (int g = 0; g < BK_SLAB / 8; ++g)   // 8-column loads: every address is aligned to the width of its load
+                tmem_ld_32x8(t_row + col + c0 + g * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[g * 8]));
+            tmem_ld_wait();
+        };
+        auto p_math = [&](const uint32_t (&sv)[BK_SLAB], int ii) {
+            const float l2 = ii == 0 ? lse2[0] : (ii == 1 ? lse2[1] : lse2[2]);
+#pragma unroll
+            for (int e = 0; e < BK_SLAB; e += 2)
+                pk[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
+                                      ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
+        };
+        auto ds_math = [&](const uint32_t (&dv)[BK_SLAB], int ii) {
+            const float sd = ii == 0 ? sdelta[0] : (ii == 1 ? sdelta[1] : sdelta[2]);
+#pragma unroll
+            for (int e = 0; e < BK_SLAB; e += 2) {
+                const uint32_t pa = pk[e / 2];
+                pk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(dv[e]), args.scale, -sd),
+                                      bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
+            }
+        };
+        // this slab's three 16-byte chunks of a [128 x 96] tile row: chunk gc = 3 slab + g of the 12 chunks of the row
+        auto p_store = [&]() {
+            uint8_t* prow = sP + row * 128;
+#pragma unroll
+            for (int g = 0; g < BK_SLAB / 8; ++g) {
+                const int gc = slab * (BK_SLAB / 8) + g;
+                *reinterpret_cast<uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4)) =
+                    make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive_warp(p_full);
+        };
+        auto ds_store = [&](int p) {
+            const uint32_t pp = p & 1;
+            if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired: this dS buffer is free
+            uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;  // keys 0..63
+            uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;   // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
+#pragma unroll
+            for (int g = 0; g < BK_SLAB / 8; ++g) {
+                const int gc = slab * (BK_SLAB / 8) + g;
+                const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                if (gc < 8) *reinterpret_cast<uint4*>(dsrow0 + ((gc ^ sw) << 4)) = o;
+                else *reinterpret_cast<uint4*>(dsrow1 + ((((gc - 8) + 4 * pp) ^ sw) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive_warp(&ds_full[pp]);
+        };
+        // P(pair) from S in TMEM -> registers (and the S buffer back to the tensor core)
+        auto make_p = [&](uint32_t parity, int jj, int ii) {
+            uint32_t sv[BK_SLAB];
+            mbar_wait(s_full, parity);
+            tc_fence_after();
+            load_slab(BK_T_S, sv);
+            tc_fence_before();
+            mbar_arrive_warp(s_free);
+            p_math(sv, ii);
+            clear_unreal(jj);
+        };
+        // dS(pair) from P (registers) and dP in TMEM -> registers (and the dP buffer back to the tensor core)
+        auto make_ds = [&](uint32_t parity, int jj, int ii) {
+            uint32_t dv[BK_SLAB];
+            mbar_wait(dp_full, parity);
+            tc_fence_after();
+            load_slab(BK_T_DP, dv);
+            tc_fence_before();
+            mbar_arrive_warp(dp_free);
+            ds_math(dv, ii);
+            clear_unreal(jj);
+        };
+
+        // ---- step -1: P(0)
+        make_p(0, 0, 0);
+        if (prof_thread) PROF(93);
+        p_store();
+        if (prof_thread) PROF(94);
+        // ---- steps 0 .. total-2: dS(p), then P(p+1);  pair p = (j, i), pair p+1 = (jn, in)
+        int j = 0, i = 0, jn = nqb > 1 ? 0 : 1, in = nqb > 1 ? 1 : 0;
+#pragma unroll 1
+        for (int p = 0; p + 1 < total; ++p) {
+            if (prof_thread && p < 8) PROF(100 + p * 4);
+            make_ds(p & 1, j, i);
+            if (prof_thread && p < 8) PROF(101 + p * 4);
+            // Key block j-1 is final: copy dK / dV out.  Here rather than at the top of the step: d(p-1) needs ~1,000 clocks
+            // after the previous step's dS hand-off to retire, and the arithmetic above has just covered them.
+            if (i == 0 && j > 0) {
+                if (prof_thread) PROF(80 + j * 2);
+                store_kv(j - 1);
+                if (prof_thread) PROF(81 + j * 2);
+            }
+            ds_store(p);
+            if (prof_thread && p < 8) PROF(102 + p * 4);
+            make_p((p + 1) & 1, jn, in);
+            mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
+            p_store();
+            if (prof_thread && p < 8) PROF(103 + p * 4);
+            if (i == 0 && j > 0) reload_kv(j - 1);
+            j = jn, i = in;
+            if (++in == nqb) in = 0, ++jn;
+        }
+        // ---- last step: dS(total-1)
+        {
+            const int p = total - 1;
+            if (i == 0 && j > 0) store_kv(j - 1);
+            make_ds(p & 1, j, i);
+            ds_store(p);
+        }
+        if (prof_thread) PROF(95);
+        store_kv(nkb - 1);
+        if (prof_thread) PROF(96);
+        // ---- epilogue: slab i converts dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store ----
+        mbar_wait(dq_full, 0);
+        if (prof_thread) PROF(97);
+        tc_fence_after();
+        if (slab < nqb && slab * 128 + q * 32 < T) {  // rows past T are clipped by the store anyway
+            const int i = slab;
+            uint8_t* orow = (i < 2 ? sP + i * TILE_BYTES : sdS) + row * 128;
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                uint32_t o0[32];
+                tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + part * 32, o0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t* src = &o0[g * 8];
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
+                    o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
+                    o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
+                    o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+                    *reinterpret_cast<uint4*>(orow + (((part * 4 + g) ^ sw) << 4)) = o;
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, BK_COMPUTE_THREADS);
+        if (warp == 4 && lane == 0) {
+            for (int i = 0; i < nqb; ++i)
+                tma_store_3d(&args.tmDQ, i < 2 ? sP + i * TILE_BYTES : sdS, h * 64, i * 128, b);
+            tma_store_commit();
+            tma_store_wait_all<0>();
+            PROF(3);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+
+// ---- previous schedule (12 compute warps, 32-column slabs, hand-merged dS / P streams): kept for A/B timing, SVIT_ATTN_BWD_V1=1 ----
+__global__ void __launch_bounds__(BK1_THREADS, 1) attn_bwd_v1_kernel(const __grid_constant__ AttnBwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem + BK_SQ;
@@ -1350,6 +1801,7 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attn_bwd) failed: %s", cudaGetErrorString(e));
             return -10;
@@ -1381,7 +1833,9 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
         static const char* dbg = getenv("SVIT_ATTN_DEBUG");
         a.debug = dbg ? atoi(dbg) : 0;
     }
-    attn_bwd_kernel<<<d.B * d.H, BK_THREADS, BK_SMEM, stream>>>(a);
+    static const bool use_v1 = getenv("SVIT_ATTN_BWD_V1") != nullptr && atoi(getenv("SVIT_ATTN_BWD_V1")) != 0;
+    if (use_v1) attn_bwd_v1_kernel<<<d.B * d.H, BK1_THREADS, BK_SMEM, stream>>>(a);
+    else attn_bwd_kernel<<<d.B * d.H, BK_THREADS, BK_SMEM, stream>>>(a);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
