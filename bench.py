@@ -475,8 +475,7 @@ def main():
             dqkv = torch.empty_like(qkv)
 
             def attn():
-                _lib.check(lib.svit_attn_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse), _lib.vp(0), _lib.vp(0),
-                                             _lib.ptr(dqkv), B, Hh, T, scale, st), "attn_bwd")
+                _lib.check(lib.svit_attn_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse), _lib.ptr(dqkv), B, Hh, T, scale, st), "attn_bwd")
             a_flops, a_name, a_key = 10.0 * T * T * 64 * B * Hh, "attn_bwd_kernel", "attn_bwd"
             a_bytes = 2.0 * B * T * (3 * inner + inner + inner + 3 * inner) + 4.0 * B * Hh * T
         for _ in range(3):

@@ -179,10 +179,9 @@ int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int 
 int svit_gemm_wgrad_bias(const void* dY, const void* X, float* dW, float* dbias, int M, int N, int K, int ldy, int ldx,
                          int ldw, int num_sms, void* stream);
 int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, float scale, void* stream);
-/* delta and dq_accum are unused scratch arguments kept for ABI stability (may be NULL): the backward kernel computes
- * rowsum(dout*out) itself and accumulates dQ on chip */
-int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum,
-                  void* dqkv, int B, int H, int T, float scale, void* stream);
+/* (rowsum(dout * out) is computed inside the kernel and dQ accumulates on chip: no scratch arguments) */
+int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H, int T,
+                  float scale, void* stream);
 int svit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd,
                        int M, int D, float eps, void* stream);
 int svit_layernorm_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,

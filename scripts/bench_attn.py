@@ -27,7 +27,7 @@ for name, mul in (("N(0,1) logits", 1.0), ("peaky logits (qkv x 8)", 8.0)):
     out = torch.empty(B, T, inner, device=dev, dtype=torch.bfloat16); lse = torch.zeros(B, H, T, device=dev)
     dout = torch.randn(B, T, inner, device=dev).bfloat16(); dqkv = torch.empty_like(qkv)
     fwd = lambda: check(lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, f, st()), "fwd")
-    bwd = lambda: check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), vp(0), vp(0), ptr(dqkv), B, H, T, f, st()), "bwd")
+    bwd = lambda: check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, f, st()), "bwd")
     if once:
         for _ in range(2): fwd(); bwd()
         torch.cuda.synchronize()

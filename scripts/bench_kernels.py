@@ -73,7 +73,7 @@ if "attn" in which:
     inner = H * 64
     qkv = torch.randn(B, T, 3 * inner, device=dev).bfloat16(); out = torch.empty(B, T, inner, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(B, H, T, device=dev); dout = torch.randn(B, T, inner, device=dev).bfloat16()
-    delta = torch.zeros(B, H, T, device=dev); dqkv = torch.empty_like(qkv); dqacc = torch.empty(B, T, inner, device=dev)
+    dqkv = torch.empty_like(qkv)
     fl = 4.0 * B * H * T * T * 64
     timeit("attn_fwd", lambda: lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, 0.125, st()), flops=fl)
-    timeit("attn_bwd", lambda: lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, 0.125, st()), flops=2.5 * fl)
+    timeit("attn_bwd", lambda: lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, 0.125, st()), flops=2.5 * fl)

@@ -7,9 +7,9 @@ lib = _lib.load()
 B, H, T = int(os.environ.get("B", 256)), 6, 321; inner = 384; dev = torch.device("cuda:0")
 qkv = torch.randn(B, T, 3 * inner, device=dev).bfloat16(); out = torch.empty(B, T, inner, device=dev, dtype=torch.bfloat16)
 lse = torch.zeros(B, H, T, device=dev); dout = torch.randn(B, T, inner, device=dev).bfloat16()
-delta = torch.zeros(B, H, T, device=dev); dqkv = torch.empty_like(qkv); dqacc = torch.empty(B, T, inner, device=dev)
+dqkv = torch.empty_like(qkv)
 st = vp(torch.cuda.current_stream().cuda_stream)
 lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, ctypes.c_float(0.125), st)
 for _ in range(2):
-    lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, ctypes.c_float(0.125), st)
+    lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, ctypes.c_float(0.125), st)
 torch.cuda.synchronize()

@@ -20,7 +20,7 @@ da = torch.randn(M, D, device=dev).bfloat16(); gi = torch.randn(M, D, device=dev
 dg = torch.zeros(D, device=dev); dbt = torch.zeros(D, device=dev); cs = torch.zeros(D, device=dev)
 for _ in range(2):
     check(lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, f(0.125), st), "fwd")
-    check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), vp(0), vp(0), ptr(dqkv), B, H, T, f(0.125), st), "bwd")
+    check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, f(0.125), st), "bwd")
     check(lib.svit_gemm_wgrad_bias(ptr(dY), ptr(X), ptr(dW), ptr(db), M, MLP, D, MLP, D, D, 148, st), "wgrad")
     check(lib.svit_layernorm_fwd(ptr(x), ptr(g), ptr(bt), ptr(a), ptr(mean), ptr(rstd), M, D, f(1e-5), st), "ln")
     check(lib.svit_layernorm_bwd(ptr(da), ptr(x), ptr(mean), ptr(rstd), ptr(g), ptr(gi), ptr(go), ptr(g16), ptr(dg), ptr(dbt), ptr(cs), M, D, st), "lnb")

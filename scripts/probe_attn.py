@@ -7,7 +7,7 @@ lib = ctypes.CDLL(LIB)
 lib.svit_last_error.restype = ctypes.c_char_p
 vp = ctypes.c_void_p; ci = ctypes.c_int; cf = ctypes.c_float
 lib.svit_attn_fwd.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp]
-lib.svit_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, vp]
+lib.svit_attn_bwd.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, cf, vp]
 dev = torch.device("cuda:0")
 def ptr(t): return vp(t.data_ptr())
 def st(): return vp(torch.cuda.current_stream().cuda_stream)
@@ -42,7 +42,7 @@ def run(B, H, T, bench=False):
     delta = torch.zeros(B, H, T, device=dev)
     dqacc = torch.empty(B, T, inner, device=dev)
     dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
-    rc = lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, scale, st())
+    rc = lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, scale, st())
     assert rc == 0, lib.svit_last_error()
     torch.cuda.synchronize()
     ref.backward(dout.float())
@@ -61,7 +61,7 @@ def run(B, H, T, bench=False):
             print("#bad", bad.shape[0], bad[:10].tolist(), bad[-5:].tolist())
     if bench:
         for name, f in (("fwd", lambda: lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, scale, st())),
-                        ("bwd", lambda: lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, scale, st()))):
+                        ("bwd", lambda: lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, scale, st()))):
             for _ in range(3): f()
             a = torch.cuda.Event(enable_timing=True); bb = torch.cuda.Event(enable_timing=True)
             a.record()

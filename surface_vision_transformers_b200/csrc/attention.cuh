@@ -24,11 +24,9 @@ struct AttnBwdDesc {
     const void* out;   // bf16 [B, T, H*64]
     const void* dout;  // bf16 [B, T, H*64]
     const float* lse;  // fp32 [B, H, T]
-    float* delta;      // unused (kept for ABI stability): rowsum(dout * out) is computed inside the kernel
     void* dqkv;        // bf16 [B, T, 3*H*64]
     int B, H, T;
     float scale;
-    float* dq_accum;   // unused (kept for ABI stability): dQ accumulates in TMEM
 };
 int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream);
 

@@ -309,7 +309,7 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         }
         RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
         RET_IF(wgrad(e, st, gb, D, L.O, I, gp(OUT_W), I, M, D, I, drop ? gp(OUT_B) : nullptr));
-        AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, nullptr, w.dqkv, w.B, e->H, e->T, scale, nullptr};
+        AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, scale};
         RET_IF(launch_attn_bwd(bd, st));
         RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
                     EPI_STORE, 0));
@@ -929,9 +929,9 @@ int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, f
     AttnDesc d{qkv, out, lse, B, H, T, scale};
     return launch_attn_fwd(d, reinterpret_cast<cudaStream_t>(stream));
 }
-int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum,
-                  void* dqkv, int B, int H, int T, float scale, void* stream) {
-    AttnBwdDesc d{qkv, out, dout, lse, delta, dqkv, B, H, T, scale, dq_accum};
+int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H, int T,
+                  float scale, void* stream) {
+    AttnBwdDesc d{qkv, out, dout, lse, dqkv, B, H, T, scale};
     return launch_attn_bwd(d, reinterpret_cast<cudaStream_t>(stream));
 }
 int svit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd, int M,

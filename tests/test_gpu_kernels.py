@@ -152,10 +152,8 @@ def test_attention_fwd_bwd(env, B, H, T):
     assert rel_l2(out, ref) < TOL
     assert rel_l2(lse, torch.logsumexp(dots, -1)) < 1e-3
     dout = torch.randn(B, T, inner, device=dev).bfloat16()
-    delta = torch.zeros(B, H, T, device=dev)
-    dqacc = torch.empty(B, T, inner, device=dev)
     dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
-    check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
+    check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
     ref.backward(dout.float())
     torch.cuda.synchronize()
     dref = torch.cat([g.permute(0, 2, 1, 3).reshape(B, T, inner) for g in (q.grad, k.grad, v.grad)], dim=-1)
@@ -191,12 +189,12 @@ def test_attention_boundary_lengths(env, T):
     bd = torch.empty_like(big)
     for _ in range(2):
         check(lib.svit_attn_fwd(ptr(big), ptr(bo), ptr(bl), B, H, 384, scale, stream()), "attn_fwd")
-        check(lib.svit_attn_bwd(ptr(big), ptr(bo), ptr(bo), ptr(bl), vp(0), vp(0), ptr(bd), B, H, 384, scale, stream()), "attn_bwd")
+        check(lib.svit_attn_bwd(ptr(big), ptr(bo), ptr(bo), ptr(bl), ptr(bd), B, H, 384, scale, stream()), "attn_bwd")
         out = torch.full((B, T, inner), float("nan"), device=dev, dtype=torch.bfloat16)
         lse = torch.full((B, H, T), float("nan"), device=dev)
         dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
         check(lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, scale, stream()), "attn_fwd")
-        check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), vp(0), vp(0), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
+        check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
         torch.cuda.synchronize()
         assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all() and torch.isfinite(dqkv.float()).all()
         assert rel_l2(out, ref) < TOL
@@ -226,9 +224,9 @@ def test_attention_bitwise_repeatable_at_full_size(env):
         lse = torch.empty(B, H, T, device=dev)
         dqkv = torch.empty_like(qkv)
         check(lib.svit_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, H, T, scale, stream()), "attn_fwd")
-        check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), vp(0), vp(0), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
+        check(lib.svit_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, H, T, scale, stream()), "attn_bwd")
         check(lib.svit_attn_fwd(ptr(other), ptr(oo), ptr(ol), B, H, 200, scale, stream()), "attn_fwd")
-        check(lib.svit_attn_bwd(ptr(other), ptr(oo), ptr(oo), ptr(ol), vp(0), vp(0), ptr(od), B, H, 200, scale, stream()), "attn_bwd")
+        check(lib.svit_attn_bwd(ptr(other), ptr(oo), ptr(oo), ptr(ol), ptr(od), B, H, 200, scale, stream()), "attn_bwd")
         torch.cuda.synchronize()
         cur = (out.clone(), lse.clone(), dqkv.clone())
         if ref is None:
