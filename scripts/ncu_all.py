@@ -1,6 +1,12 @@
 """One launch of EVERY kernel of the training step at the benchmark shapes (SiT-small ico-2, per-GPU batch 256), for
 
-    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r02_all python scripts/ncu_all.py
+    ncu --section LaunchStats --section Occupancy --section SpeedOfLight --section MemoryWorkloadAnalysis \
+        --section ComputeWorkloadAnalysis --section WarpStateStats --clock-control none --profile-from-start off \
+        -o gpurun_out/r02_all python scripts/ncu_all.py
+
+(the sections that hold duration, DRAM bytes, pipe utilisation, occupancy and stall reasons: ~10 replay passes per launch
+instead of the ~40 of --set full, which took 20 GPU-minutes for this script; the attention and GEMM kernels additionally
+have --set full captures with source, scripts/bench_attn.py once / scripts/ncu_kernels.py)
 
 A 2-block SiT-small (same kernels and shapes as the 12-block model, 1/6 of the launches) runs one un-profiled warm-up
 iteration, then -- inside cudaProfilerStart/Stop -- one iteration of: weight-shadow refresh, forward, fused criterion,
@@ -15,7 +21,7 @@ cfg = dict(dim=384, depth=2, heads=6, mlp_dim=1536, num_patches=320, num_vertice
 torch.manual_seed(0)
 model = svit.SiT(**cfg).to(dev)
 opt = svit.FusedAdamW(model.parameters(), lr=1e-5, weight_decay=0.0)
-ssl = svit.masked_patch_pretraining(transformer=svit.SiT(**cfg), dim_in=384, dim_out=612, device=dev, mask_prob=0.5,
+ssl = svit.masked_patch_pretraining(transformer=svit.SiT(**dict(cfg, depth=1)), dim_in=384, dim_out=612, device=dev, mask_prob=0.5,
                                     replace_prob=0.8, swap_prob=0.02, channels=4, num_vertices=153).to(dev)
 opt2 = svit.FusedAdamW(ssl.parameters(), lr=1e-4, weight_decay=0.0)
 sgd_model = svit.SiT(**dict(cfg, depth=1)).to(dev)
@@ -38,8 +44,6 @@ def iteration():
     svit.regression_loss(sgd_model(x[:32]), y[:32]).backward()
     sgd.step()
     svit.gather_patches(mesh, table)
-    with torch.no_grad():
-        model.eval(); model(x); model.train()
 
 iteration()
 torch.cuda.synchronize()

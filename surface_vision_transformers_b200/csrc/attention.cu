@@ -748,7 +748,8 @@ constexpr int BK_COMPUTE_THREADS = 32 * BK_COMPUTE_WARPS;
 constexpr int BK_THREADS = 128 + BK_COMPUTE_THREADS;  // warp group 0: MMA warps X and Y (+ 2 idle warps), then 16 compute warps
 constexpr int BK_SLAB = BK_KEYS / (BK_COMPUTE_WARPS / 4);  // 24 key columns per compute warp
 constexpr int BK1_THREADS = 512;
-constexpr int BK_REGS_MMA = 56, BK_REGS_COMPUTE = 152;  // (v1) setmaxnreg: 4 * 56 + 12 * 152 = 16 * 128
+constexpr int BK_REGS_MMA = 56, BK_REGS_COMPUTE = 104;    // setmaxnreg: 4 * 56 + 16 * 104 <= 20 * 96 (the launch-bound allocation)
+constexpr int BK1_REGS_COMPUTE = 152;                      // (v1) 4 * 56 + 12 * 152 = 16 * 128
 constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
@@ -858,6 +859,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     };
 
     if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BK_REGS_MMA));
       if (warp == 0) {
         // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
         if (elect_one()) {
@@ -960,6 +962,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         }
       }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK_REGS_COMPUTE));
         // ================================ compute warps ================================
         // 16 warps (four per SM sub-partition): warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and
         // the 24 key columns [24 slab, 24 slab + 24) of every 96-key block -- for the probabilities AND for dS, so P(p)
@@ -1062,11 +1065,12 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         // block only) then clear those entries with integer masks, which also kills whatever stale TMEM contents (columns
         // beyond the MMA's N extent) may have produced.
         uint32_t pk[BK_SLAB / 2];  // P(p), then dS(p), of this thread's 24 columns, packed bf16 (exact zeros where masked)
-        auto clear_unreal = [&](int jj) {
+        uint32_t pn[BK_SLAB / 2];  // (P-first warps) P(p+1) while pk still holds P(p) / dS(p)
+        auto clear_unreal = [&](uint32_t (&dst)[BK_SLAB / 2], int jj) {
             const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns
             if (nv >= BK_SLAB) return;                            // warp-uniform
 #pragma unroll
-            for (int k = 0; k < BK_SLAB / 2; ++k) pk[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
+            for (int k = 0; k < BK_SLAB / 2; ++k) dst[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
         };
         auto load_slab = [&](uint32_t col, uint32_t (&v)[BK_SLAB]) {
 #pragma unroll
@@ -1074,11 +1078,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 tmem_ld_32x8(t_row + col + c0 + g * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[g * 8]));
             tmem_ld_wait();
         };
-        auto p_math = [&](const uint32_t (&sv)[BK_SLAB], int ii) {
+        auto p_math = [&](uint32_t (&dst)[BK_SLAB / 2], const uint32_t (&sv)[BK_SLAB], int ii) {
             const float l2 = ii == 0 ? lse2[0] : (ii == 1 ? lse2[1] : lse2[2]);
 #pragma unroll
             for (int e = 0; e < BK_SLAB; e += 2)
-                pk[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
+                dst[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
                                       ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
         };
         auto ds_math = [&](const uint32_t (&dv)[BK_SLAB], int ii) {
@@ -1118,15 +1122,15 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             mbar_arrive_warp(&ds_full[pp]);
         };
         // P(pair) from S in TMEM -> registers (and the S buffer back to the tensor core)
-        auto make_p = [&](uint32_t parity, int jj, int ii) {
+        auto make_p = [&](uint32_t (&dst)[BK_SLAB / 2], uint32_t parity, int jj, int ii) {
             uint32_t sv[BK_SLAB];
             mbar_wait(s_full, parity);
             tc_fence_after();
             load_slab(BK_T_S, sv);
             tc_fence_before();
             mbar_arrive_warp(s_free);
-            p_math(sv, ii);
-            clear_unreal(jj);
+            p_math(dst, sv, ii);
+            clear_unreal(dst, jj);
         };
         // dS(pair) from P (registers) and dP in TMEM -> registers (and the dP buffer back to the tensor core)
         auto make_ds = [&](uint32_t parity, int jj, int ii) {
@@ -1137,19 +1141,24 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_warp(dp_free);
             ds_math(dv, ii);
-            clear_unreal(jj);
+            clear_unreal(pk, jj);
         };
 
         // ---- step -1: P(0)
-        make_p(0, 0, 0);
+        make_p(pk, 0, 0, 0);
         if (prof_thread) PROF(93);
         p_store();
         if (prof_thread) PROF(94);
-        // ---- steps 0 .. total-2: dS(p), then P(p+1);  pair p = (j, i), pair p+1 = (jn, in)
+        // ---- steps 0 .. total-2: dS(p) and P(p+1);  pair p = (j, i), pair p+1 = (jn, in).
+        // All warps wait on the same barriers, so they would run the FMA-bound dS half and the MUFU-bound P half in lock
+        // step (12,288 exponentials per step keep the MUFU busy for 768 clocks while the FMA pipe idles, and vice versa).
+        // Slabs 0, 1 therefore do dS first, slabs 2, 3 the exponentials first: the two pipes overlap across warps.
+        const bool p_first = slab >= 2;
         int j = 0, i = 0, jn = nqb > 1 ? 0 : 1, in = nqb > 1 ? 1 : 0;
 #pragma unroll 1
         for (int p = 0; p + 1 < total; ++p) {
             if (prof_thread && p < 8) PROF(100 + p * 4);
+            if (p_first) make_p(pn, (p + 1) & 1, jn, in);
             make_ds(p & 1, j, i);
             if (prof_thread && p < 8) PROF(101 + p * 4);
             // Key block j-1 is final: copy dK / dV out.  Here rather than at the top of the step: d(p-1) needs ~1,000 clocks
@@ -1161,7 +1170,12 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             }
             ds_store(p);
             if (prof_thread && p < 8) PROF(102 + p * 4);
-            make_p((p + 1) & 1, jn, in);
+            if (p_first) {
+#pragma unroll
+                for (int k = 0; k < BK_SLAB / 2; ++k) pk[k] = pn[k];
+            } else {
+                make_p(pk, (p + 1) & 1, jn, in);
+            }
             mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
             p_store();
             if (prof_thread && p < 8) PROF(103 + p * 4);
@@ -1408,7 +1422,7 @@ __global__ void __launch_bounds__(BK1_THREADS, 1) attn_bwd_v1_kernel(const __gri
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK_REGS_COMPUTE));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK1_REGS_COMPUTE));
         // ================================ compute warps ================================
         // 12 warps: warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and the 32 key columns
         // [32 slab, 32 slab + 32) of every 96-key block -- for the probabilities AND for dS, so P stays in registers

@@ -888,8 +888,11 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
     }
     // A-resident variant: the whole K extent of a row block fits in 6 K blocks and there are several N tiles to reuse it
     static const int force_ares = getenv("SVIT_GEMM_ARES") ? atoi(getenv("SVIT_GEMM_ARES")) : -1;
-    // (measured: -3 % for the plain store epilogue; the GELU / aux epilogues lose more from their halved staging rings)
-    bool ares = cg == 2 && d.K <= ARES_KB * BK && (d.N + BN - 1) / BN >= 3 && d.mode == EPI_STORE;
+    // (measured at M = 82176: plain store 69.7 -> 68.9 us (N = 1152); fc1 + GELU (+ derivative) 149.8 -> 143.1 us with the
+    // 64-byte-box epilogue, whose staging leaves room for the resident A block; the aux epilogues (residual, * gelu') LOSE
+    // 10-20 % with their rings cut to two boxes and keep the streaming schedule)
+    const bool heavy_mode = d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD || d.mode == EPI_GELU_ONLY;
+    bool ares = cg == 2 && d.K <= ARES_KB * BK && (d.N + BN - 1) / BN >= 3 && (d.mode == EPI_STORE || heavy_mode);
     if (force_ares == 0) ares = false;
     if (force_ares == 1 && d.K <= ARES_KB * BK && cg == 2) ares = true;
     if (cg == 2) return ares ? dispatch_tn<2, true>(d, a, num_sms, stream) : dispatch_tn<2, false>(d, a, num_sms, stream);
