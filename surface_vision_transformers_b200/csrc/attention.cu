@@ -417,290 +417,8 @@ __global__ void __launch_bounds__(384, 2) attn_fwd_kernel(const __grid_constant_
     }
 }
 
-// =================================================================================================
-// forward v1 (one CTA per SM; kept for A/B timing, SVIT_ATTN_FWD_V1=1)
-// =================================================================================================
-// One CTA per (sample, head); K and V (<= 384 keys) stay in shared memory, Q blocks of 128 rows stream through.
-// TMEM reads cost 64 B/clk/SM, as much as the exponentials themselves, so the scores are read ONCE: the softmax
-// shift is the row's score against key 0 (any shift is exact for softmax; the log-sum-exp is reported with the same
-// shift), and a guard on the row sum falls back to the classic max-shift pass in the (never observed) overflow case.
-// 8 softmax warps: warp (q, hf) owns TMEM lane quadrant q and one half of the key columns.
-// P never touches shared memory: the bf16 probabilities are written back into TMEM over the consumed scores
-// (tcgen05.st, two per 32-bit column) and feed the PV product as the A operand FROM TMEM -- no STS / proxy fence in the
-// softmax (LSU shared-memory traffic crawls while the tensor core streams operands) and no A fetch for the PV MMAs.
-// shared memory map (bytes):  sQ 16K | sK 48K | sV 48K | sO 16K | row sums / maxima | barriers   (~130 KB)
-constexpr int FW1_SQ = 0;
-constexpr int FW1_SK = FW1_SQ + TILE_BYTES;
-constexpr int FW1_SV = FW1_SK + 3 * TILE_BYTES;
-constexpr int FW1_SO = FW1_SV + 3 * TILE_BYTES;
-constexpr int FW1_RED = FW1_SO + TILE_BYTES;      // float [2][128]
-constexpr int FW1_BAR = FW1_RED + 2 * 128 * 4;
-constexpr int FW1_SMEM = 1024 + FW1_BAR + 128;
-constexpr int FW1_THREADS = 288;
-constexpr int FW1_TMEM_O = 384;  // O accumulator columns [384, 448)
-
-struct AttnFwdV1Args {
-    CUtensorMap tmQKV;  // (3*inner, T, B) bf16, box 64 x 128 x 1
-    CUtensorMap tmO;    // (inner, T, B) bf16, box 64 x 128 x 1
-    float* lse;
-    int B, H, T;
-    float scale, scale_log2e;
-    int debug;  // SVIT_ATTN_DEBUG: 8 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
-};
-
-// clock64 timeline of one CTA for scripts/prof_attn_*.py; costs nothing unless enabled
+// clock64 timeline of one CTA for scripts/prof_attn_bwd.py; costs nothing unless enabled (SVIT_ATTN_DEBUG=4)
 __device__ long long g_attn_prof[256];
-#define PROFF(slot) do { if ((args.debug & 8) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
-
-
-__global__ void __launch_bounds__(FW1_THREADS, 1) attn_fwd_v1_kernel(const __grid_constant__ AttnFwdV1Args args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem + FW1_SQ;
-    uint8_t* sK = smem + FW1_SK;
-    uint8_t* sV = smem + FW1_SV;
-    uint8_t* sO = smem + FW1_SO;
-    float* sRed = reinterpret_cast<float*>(smem + FW1_RED);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FW1_BAR);
-    uint64_t* bar_kv = bars + 0;
-    uint64_t* bar_q = bars + 1;
-    uint64_t* bar_s = bars + 2;
-    uint64_t* bar_p = bars + 3;
-    uint64_t* bar_o = bars + 4;
-    uint64_t* bar_of = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int T = args.T, H = args.H;
-    const int inner = H * 64;
-    const int b = blockIdx.x / H;
-    const int h = blockIdx.x % H;
-    const int tk = (T + 15) & ~15;       // keys padded to the UMMA K step
-    const int nkb = (T + 127) / 128;     // 128-row K/V boxes
-    const int nqb = (T + 127) / 128;     // query blocks
-    const int n1 = tk < 256 ? tk : 256;  // first S chunk (UMMA N <= 256)
-    const int n2 = tk - n1;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&args.tmQKV);
-        tma_prefetch_desc(&args.tmO);
-        mbar_init(bar_kv, 1);
-        mbar_init(bar_q, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_p, 8);
-        mbar_init(bar_o, 1);
-        mbar_init(bar_of, 8);
-        fence_mbar_init();
-    }
-    if (warp == 8) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 8) {
-        // ============================ control: TMA + MMA issue ============================
-        if (elect_one()) {
-            mbar_expect_tx(bar_kv, nkb * 2 * TILE_BYTES);
-            for (int r = 0; r < nkb; ++r) {
-                tma_load_3d(sK + r * TILE_BYTES, &args.tmQKV, bar_kv, inner + h * 64, r * 128, b);
-                tma_load_3d(sV + r * TILE_BYTES, &args.tmQKV, bar_kv, 2 * inner + h * 64, r * 128, b);
-            }
-            mbar_expect_tx(bar_q, TILE_BYTES);
-            tma_load_3d(sQ, &args.tmQKV, bar_q, h * 64, 0, b);
-            const uint32_t idesc_s1 = umma_idesc_bf16(128, n1, 0, 0);
-            const uint32_t idesc_s2 = umma_idesc_bf16(128, n2 > 0 ? n2 : 16, 0, 0);
-            const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            PROFF(0);
-            mbar_wait(bar_kv, 0);
-            PROFF(1);
-            for (int i = 0; i < nqb; ++i) {
-                const uint32_t ph = i & 1;
-                mbar_wait(bar_q, ph);
-                PROFF(10 + i * 10);
-                tc_fence_after();
-                // S = Q K^T  (K-major A and B)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, 1024);
-                    umma_ss(tmem_base, ad, umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s1, k != 0);
-                    if (n2 > 0)
-                        umma_ss(tmem_base + n1, ad, umma_smem_desc(k_addr + n1 * 128 + k * 32, 16, 1024), idesc_s2, k != 0);
-                }
-                umma_commit(bar_s);
-                mbar_wait(bar_s, ph);  // S done -> sQ reusable
-                PROFF(11 + i * 10);
-                if (i + 1 < nqb) {
-                    mbar_expect_tx(bar_q, TILE_BYTES);
-                    tma_load_3d(sQ, &args.tmQKV, bar_q, h * 64, (i + 1) * 128, b);
-                }
-                mbar_wait(bar_p, ph);  // P (bf16, in TMEM over the scores) complete
-                PROFF(12 + i * 10);
-                if (i > 0) mbar_wait(bar_of, (i - 1) & 1);  // previous O drained from TMEM
-                tc_fence_after();
-                // O = P V  (A = P from TMEM: lanes = query rows, 8 columns of packed bf16 pairs per 16-key step; B = V MN-major)
-                const int ksteps = tk / 16;
-                for (int s = 0; s < ksteps; ++s)
-                    umma_ts(tmem_base + FW1_TMEM_O, tmem_base + s * 8, umma_smem_desc(v_addr + s * 2048, 8192, 1024), idesc_pv,
-                            s != 0);
-                umma_commit(bar_o);
-                PROFF(13 + i * 10);
-            }
-        }
-    } else {
-        // ============================ softmax + epilogue warps ============================
-        const int q = warp & 3;    // TMEM lane quadrant
-        const int hf = warp >> 2;  // key-column half
-        const int row = q * 32 + lane;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const bool leader = threadIdx.x == 0;
-        const float c = args.scale_log2e;
-        // half 0: columns [0, split), half 1: [split, tk).  Rounded UP to a 32-column group: the last group of half 1 is the
-        // masked (slower) one, so half 1 gets the smaller share (T = 321: 6 full groups | 4 full + 1 masked)
-        const int split = min(tk, (tk / 2 + 31) & ~31);
-        const int col_lo = hf == 0 ? 0 : split;
-        const int col_hi = hf == 0 ? split : tk;
-
-        // exp2((s - shift) * c) of this thread's columns -> packed bf16 pairs in registers (up to 6 groups of 32
-        // columns per half); returns the partial row sum
-        uint32_t pk[96];
-        auto softmax_pass = [&](float shift_c) {
-            float sm0 = 0.0f, sm1 = 0.0f;
-#pragma unroll
-            for (int g6 = 0; g6 < 6; ++g6) {
-                const int c0 = col_lo + g6 * 32;
-                if (c0 < col_hi) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_row + c0, r);
-                    tmem_ld_wait();
-                    if (c0 + 32 <= T) {
-                        // all 32 keys real: no masking.  The row sum adds the fp32 probabilities (their bf16 rounding
-                        // in the PV product is unbiased; the difference is ~1e-4 relative, far below bf16 resolution)
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
-                            const float x1 = fmaf(__uint_as_float(r[e + 1]), c, -shift_c);
-                            const float p1 = ((e >> 1) & 1) ? fwd_ex2_poly(x1) : fwd_ex2(x1);  // every 4th on the FMA pipe
-                            pk[g6 * 16 + e / 2] = pack_bf16(p0, p1);
-                            sm0 += p0;
-                            sm1 += p1;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            float p0 = fwd_ex2(fmaf(__uint_as_float(r[e]), c, -shift_c));
-                            float p1 = fwd_ex2(fmaf(__uint_as_float(r[e + 1]), c, -shift_c));
-                            if (c0 + e >= T) p0 = 0.0f;
-                            if (c0 + e + 1 >= T) p1 = 0.0f;
-                            pk[g6 * 16 + e / 2] = pack_bf16(p0, p1);
-                            sm0 += p0;
-                            sm1 += p1;
-                        }
-                    }
-                }
-            }
-            return sm0 + sm1;
-        };
-        // packed P -> TMEM, in place over the scores: the pair (2k, 2k+1) of S columns lands in column k.  Called only
-        // after every warp of the CTA has finished reading S (the row-sum barriers below).
-        auto store_p = [&]() {
-#pragma unroll
-            for (int g6 = 0; g6 < 6; ++g6) {
-                const int c0 = col_lo + g6 * 32;
-                if (c0 < col_hi) tmem_st_32x16(t_row + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(&pk[g6 * 16]));
-            }
-            tmem_st_wait();
-        };
-
-        for (int i = 0; i < nqb; ++i) {
-            const uint32_t ph = i & 1;
-            mbar_wait(bar_s, ph);
-            tc_fence_after();
-            // ---- single pass with the score against key 0 as the softmax shift ----
-            float shift = __uint_as_float(tmem_ld_32x1(t_row));
-            tmem_ld_wait();
-            float part = softmax_pass(shift * c);
-            if (threadIdx.x == 0) PROFF(14 + i * 10);
-            sRed[hf * 128 + row] = part;
-            // One barrier publishes the partial sums and votes on the fallback.  The row sum cannot underflow (key 0
-            // contributes exp2(0) = 1), so "some partial sum is not < 1e30" (overflow, inf or NaN) is the whole test.
-            float total;
-            if (named_bar_or(1, 256, !(part < 1e30f))) {
-                // ---- fallback (uniform for the CTA): classic max-shifted softmax ----
-                float mx = -INFINITY;
-                for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_row + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < T && c0 + j < col_hi) mx = fmaxf(mx, __uint_as_float(r[j]));
-                }
-                sRed[hf * 128 + row] = mx;
-                named_bar_sync(1, 256);
-                shift = fmaxf(sRed[row], sRed[128 + row]);
-                named_bar_sync(2, 256);
-                part = softmax_pass(shift * c);
-                sRed[hf * 128 + row] = part;
-                named_bar_sync(1, 256);
-                total = sRed[row] + sRed[128 + row];
-                named_bar_sync(2, 256);
-            } else {
-                total = sRed[row] + sRed[128 + row];
-            }
-            if (threadIdx.x == 0) PROFF(15 + i * 10);
-            store_p();
-            tc_fence_before();
-            mbar_arrive_warp(bar_p);
-            if (threadIdx.x == 0) PROFF(16 + i * 10);
-            // ---- epilogue: O / sum -> bf16 -> staging -> TMA store (each half converts 32 of the 64 columns) ----
-            mbar_wait(bar_o, ph);
-            if (threadIdx.x == 0) PROFF(17 + i * 10);
-            tc_fence_after();
-            const float inv = 1.0f / total;
-            uint32_t o0[32];
-            tmem_ld_32x32(t_row + FW1_TMEM_O + hf * 32, o0);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive_warp(bar_of);
-            if (i > 0) {
-                if (leader) tma_store_wait_read<0>();  // previous O tile left the staging buffer
-                named_bar_sync(1, 256);
-            }
-            uint8_t* orow = sO + row * 128;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint32_t* src = &o0[g * 8];
-                uint4 o;
-                o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-                o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-                o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-                o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-                *reinterpret_cast<uint4*>(orow + (((hf * 4 + g) ^ (row & 7)) << 4)) = o;
-            }
-            const int t = i * 128 + row;
-            if (hf == 0 && t < T) args.lse[(static_cast<size_t>(b) * H + h) * T + t] = shift * args.scale + logf(total);
-            fence_proxy_async_smem();
-            named_bar_sync(2, 256);
-            if (leader) {
-                tma_store_3d(&args.tmO, sO, h * 64, i * 128, b);
-                tma_store_commit();
-            }
-        }
-        if (leader) tma_store_wait_all<0>();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
 
 // =================================================================================================
 // backward: one CTA per (sample, head), every operand loaded exactly once, no atomics
@@ -710,25 +428,29 @@ __global__ void __launch_bounds__(FW1_THREADS, 1) attn_fwd_v1_kernel(const __gri
 //   S [0,96)  dP [96,192)  dK_j [192,256)  dV_j [256,320)  dQ_0..2 [320,512)
 // so dQ accumulates on chip across the key blocks (no atomics, no fp32 scratch, no separate delta / convert kernels).
 //
-//   tensor core (two issuing warps X, Y)     12 compute warps: warp (q, slab) = TMEM lane quadrant q (one query row per
-//   a(p): S  = Q_i K_j^T          (X)         thread) x key columns [32 slab, 32 slab + 32) of the 96-key block
+//   tensor core (two issuing warps X, Y)     16 compute warps: warp (q, slab) = TMEM lane quadrant q (one query row per
+//   a(p): S  = Q_i K_j^T          (X)         thread) x key columns [24 slab, 24 slab + 24) of the 96-key block
 //   b(p): dP = dO_i V_j^T         (Y)           P  = exp2(S*scale*log2e - lse*log2e)    -> bf16 smem tile sP
 //   c(p): dV_j += P^T dO_i        (X)           dS = P * (dP*scale - delta*scale)       -> bf16 smem tile sdS
 //   d(p): dK_j += dS^T Q_i ; dQ_i += dS K_j (Y)
-// The compute warps are software-pipelined: step p computes dS(p) AND P(p+1) in one merged instruction stream (the
-// exponentials run on the MUFU while the dS arithmetic runs on the FMA pipe; P(p+1) stays in registers for dS(p+1), it
-// is never read back from shared memory).  S(p+1) and dP(p) were issued at the start of step p-1, as soon as their TMEM
-// buffers had been read out, so a step never waits for the tensor pipe; c and d of a step run underneath the next one.
+// Step p of the compute warps: dS(p) from dP(p) and the P(p) they kept in registers (packed bf16) since the previous step,
+// hand it to the tensor core, then P(p+1) from S(p+1).  S(p+1) and dP(p) were issued one step earlier, as soon as their
+// TMEM buffers had been read out, so a step never waits for the tensor pipe; c and d of a step run underneath the next.
 // Row masking costs nothing (lse = +inf for rows past T), column masking only touches the one slab that straddles T.
-// What the profile (SVIT_ATTN_DEBUG=4, scripts/prof_attn_bwd.py) taught, in clocks per CTA at T = 321 (63 k before):
+// What the profile (SVIT_ATTN_DEBUG=4, scripts/prof_attn_bwd.py) taught, in clocks per CTA at T = 321 (63 k at first):
 //   * delta = rowsum(dO * O): per-thread global loads of the O / dO rows took 11 k; O_i now arrives by TMA in the not yet
 //     used dS tiles and delta is read from shared memory (1.5 k);
 //   * dK_j / dV_j leave through the block's own K / V stage and two TMA stores (the stage is refilled one step later):
 //     per-thread row stores took 3 k per key block, and the LSU starves while the tensor core streams smem operands;
-//   * 4 P warps + 8 dS warps were unbalanced (the P warps needed 3.1 k per pair) and re-read P from shared memory;
-//   * registers: the two issuing warps give theirs up (setmaxnreg 56 / 152), the timeout printf of mbar_wait is gone
-//     (every inlined wait paid for a call site), the copy-out is a small rolled loop -- spills inside the pipelined
-//     loop are fatal (local-memory traffic crawls under the tensor core's shared-memory streaming).
+//   * the timeout printf of mbar_wait cost every inlined wait a call site; spills inside the step loop are fatal
+//     (with 227 KB of the unified L1 / shared memory taken, local memory is an L2 round trip);
+//   * round 2: 12 warps on 32-column slabs running dS(p) and P(p+1) as one hand-merged stream (152 registers via
+//     setmaxnreg) took 287 us; 16 warps on 24-column slabs doing dS then P (90 registers, four warps per sub-partition
+//     hide the TMEM-load / MUFU latencies) take 275 us.  A step is still ~2,300 clocks against ~1,500 of tensor work: the
+//     phases of a step (dP load + dS 650, dS hand-off 500, S load + exponentials + P hand-off 1,150) are latency chains
+//     through ONE P tile and ONE S / dP buffer each; letting half of the warps do the exponentials first (so that MUFU
+//     and FMA phases overlap across warps) did not shorten them (291 us).  The next step would be a second S / dP / P
+//     set, for which neither TMEM (512 columns used) nor shared memory (227 KB used) has room at 96-key blocks.
 // A [128 x 96] bf16 tile occupies one full 64-column swizzled tile plus half of a second one; the two dS buffers
 // share that second tile (buffer 1 lives in its columns 32..63, i.e. 64 bytes into every row).
 // smem: sQ[3] sdO[3] (16K each) | sK,sV x2 stages (12K each) | sP 32K | sdS 16K + 16K + 16K shared | barriers, delta (~227 KB)
@@ -747,9 +469,6 @@ constexpr int BK_COMPUTE_WARPS = 16;
 constexpr int BK_COMPUTE_THREADS = 32 * BK_COMPUTE_WARPS;
 constexpr int BK_THREADS = 128 + BK_COMPUTE_THREADS;  // warp group 0: MMA warps X and Y (+ 2 idle warps), then 16 compute warps
 constexpr int BK_SLAB = BK_KEYS / (BK_COMPUTE_WARPS / 4);  // 24 key columns per compute warp
-constexpr int BK1_THREADS = 512;
-constexpr int BK_REGS_MMA = 56, BK_REGS_COMPUTE = 104;    // setmaxnreg: 4 * 56 + 16 * 104 <= 20 * 96 (the launch-bound allocation)
-constexpr int BK1_REGS_COMPUTE = 152;                      // (v1) 4 * 56 + 12 * 152 = 16 * 128
 constexpr int BK_T_S = 0, BK_T_DP = 96, BK_T_DK = 192, BK_T_DV = 256, BK_T_DQ = 320;
 
 struct AttnBwdArgs {
@@ -859,7 +578,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     };
 
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BK_REGS_MMA));
       if (warp == 0) {
         // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
         if (elect_one()) {
@@ -962,7 +680,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK_REGS_COMPUTE));
         // ================================ compute warps ================================
         // 16 warps (four per SM sub-partition): warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and
         // the 24 key columns [24 slab, 24 slab + 24) of every 96-key block -- for the probabilities AND for dS, so P(p)
@@ -1065,12 +782,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         // block only) then clear those entries with integer masks, which also kills whatever stale TMEM contents (columns
         // beyond the MMA's N extent) may have produced.
         uint32_t pk[BK_SLAB / 2];  // P(p), then dS(p), of this thread's 24 columns, packed bf16 (exact zeros where masked)
-        uint32_t pn[BK_SLAB / 2];  // (P-first warps) P(p+1) while pk still holds P(p) / dS(p)
-        auto clear_unreal = [&](uint32_t (&dst)[BK_SLAB / 2], int jj) {
+        auto clear_unreal = [&](int jj) {
             const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns
             if (nv >= BK_SLAB) return;                            // warp-uniform
 #pragma unroll
-            for (int k = 0; k < BK_SLAB / 2; ++k) dst[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
+            for (int k = 0; k < BK_SLAB / 2; ++k) pk[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
         };
         auto load_slab = [&](uint32_t col, uint32_t (&v)[BK_SLAB]) {
 #pragma unroll
@@ -1078,11 +794,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
                 tmem_ld_32x8(t_row + col + c0 + g * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[g * 8]));
             tmem_ld_wait();
         };
-        auto p_math = [&](uint32_t (&dst)[BK_SLAB / 2], const uint32_t (&sv)[BK_SLAB], int ii) {
+        auto p_math = [&](const uint32_t (&sv)[BK_SLAB], int ii) {
             const float l2 = ii == 0 ? lse2[0] : (ii == 1 ? lse2[1] : lse2[2]);
 #pragma unroll
             for (int e = 0; e < BK_SLAB; e += 2)
-                dst[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
+                pk[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
                                       ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
         };
         auto ds_math = [&](const uint32_t (&dv)[BK_SLAB], int ii) {
@@ -1122,15 +838,15 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             mbar_arrive_warp(&ds_full[pp]);
         };
         // P(pair) from S in TMEM -> registers (and the S buffer back to the tensor core)
-        auto make_p = [&](uint32_t (&dst)[BK_SLAB / 2], uint32_t parity, int jj, int ii) {
+        auto make_p = [&](uint32_t parity, int jj, int ii) {
             uint32_t sv[BK_SLAB];
             mbar_wait(s_full, parity);
             tc_fence_after();
             load_slab(BK_T_S, sv);
             tc_fence_before();
             mbar_arrive_warp(s_free);
-            p_math(dst, sv, ii);
-            clear_unreal(dst, jj);
+            p_math(sv, ii);
+            clear_unreal(jj);
         };
         // dS(pair) from P (registers) and dP in TMEM -> registers (and the dP buffer back to the tensor core)
         auto make_ds = [&](uint32_t parity, int jj, int ii) {
@@ -1141,24 +857,19 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_warp(dp_free);
             ds_math(dv, ii);
-            clear_unreal(pk, jj);
+            clear_unreal(jj);
         };
 
         // ---- step -1: P(0)
-        make_p(pk, 0, 0, 0);
+        make_p(0, 0, 0);
         if (prof_thread) PROF(93);
         p_store();
         if (prof_thread) PROF(94);
-        // ---- steps 0 .. total-2: dS(p) and P(p+1);  pair p = (j, i), pair p+1 = (jn, in).
-        // All warps wait on the same barriers, so they would run the FMA-bound dS half and the MUFU-bound P half in lock
-        // step (12,288 exponentials per step keep the MUFU busy for 768 clocks while the FMA pipe idles, and vice versa).
-        // Slabs 0, 1 therefore do dS first, slabs 2, 3 the exponentials first: the two pipes overlap across warps.
-        const bool p_first = slab >= 2;
+        // ---- steps 0 .. total-2: dS(p), then P(p+1);  pair p = (j, i), pair p+1 = (jn, in)
         int j = 0, i = 0, jn = nqb > 1 ? 0 : 1, in = nqb > 1 ? 1 : 0;
 #pragma unroll 1
         for (int p = 0; p + 1 < total; ++p) {
             if (prof_thread && p < 8) PROF(100 + p * 4);
-            if (p_first) make_p(pn, (p + 1) & 1, jn, in);
             make_ds(p & 1, j, i);
             if (prof_thread && p < 8) PROF(101 + p * 4);
             // Key block j-1 is final: copy dK / dV out.  Here rather than at the top of the step: d(p-1) needs ~1,000 clocks
@@ -1170,12 +881,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             }
             ds_store(p);
             if (prof_thread && p < 8) PROF(102 + p * 4);
-            if (p_first) {
-#pragma unroll
-                for (int k = 0; k < BK_SLAB / 2; ++k) pk[k] = pn[k];
-            } else {
-                make_p(pk, (p + 1) & 1, jn, in);
-            }
+            make_p((p + 1) & 1, jn, in);
             mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
             p_store();
             if (prof_thread && p < 8) PROF(103 + p * 4);
@@ -1236,475 +942,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
 }
 
 
-// ---- previous schedule (12 compute warps, 32-column slabs, hand-merged dS / P streams): kept for A/B timing, SVIT_ATTN_BWD_V1=1 ----
-__global__ void __launch_bounds__(BK1_THREADS, 1) attn_bwd_v1_kernel(const __grid_constant__ AttnBwdArgs args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem + BK_SQ;
-    uint8_t* sdO = smem + BK_SDO;
-    uint8_t* sKV = smem + BK_SKV;
-    uint8_t* sP = smem + BK_SP;
-    uint8_t* sdS = smem + BK_SDS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BK_BAR);
-    uint64_t* q_full = bars + 0;     // [3] Q_i and dO_i landed (once per CTA)
-    uint64_t* kv_full = bars + 4;    // [2]
-    uint64_t* s_full = bars + 8;     // S in TMEM                      (MMA -> compute warps)
-    uint64_t* s_free = bars + 9;     // S copied to registers          (compute warps -> MMA)
-    uint64_t* dp_full = bars + 10;   // dP in TMEM                     (MMA -> compute warps)
-    uint64_t* dp_free = bars + 11;   // dP copied to registers         (compute warps -> MMA)
-    uint64_t* p_full = bars + 12;    // P tile written                 (compute warps -> MMA)
-    uint64_t* p_free = bars + 13;    // c(p) retired                   (MMA X -> compute warps)
-    uint64_t* ds_full = bars + 14;   // [2] dS tile p & 1 written      (compute warps -> MMA)
-    uint64_t* ds_free = bars + 16;   // [2] d(p) retired               (MMA -> compute warps)
-    uint64_t* dv_full = bars + 18;   // dV_j final (c(j, last) retired)  (MMA X -> compute warps)
-    uint64_t* dv_free = bars + 19;   // dV_j copied to registers         (compute warps -> MMA X)
-    uint64_t* dk_full = bars + 20;   // dK_j final (d(j, last) retired)  (MMA Y -> compute warps)
-    uint64_t* dk_free = bars + 21;   // dK_j copied to registers         (compute warps -> MMA Y)
-    uint64_t* dq_full = bars + 22;   // every MMA of the CTA retired     (MMA -> compute warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int T = args.T, H = args.H;
-    const int inner = H * 64;
-    const int nqb = (T + 127) / 128;
-    const int nkb = (T + BK_KEYS - 1) / BK_KEYS;
-    const int total = nqb * nkb;
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&args.tmQ);
-        tma_prefetch_desc(&args.tmDO);
-        tma_prefetch_desc(&args.tmKV);
-        tma_prefetch_desc(&args.tmDQ);
-        tma_prefetch_desc(&args.tmO);
-        tma_prefetch_desc(&args.tmDKV);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&kv_full[s], 1);
-            mbar_init(&ds_full[s], 12);
-            mbar_init(&ds_free[s], 1);
-        }
-        for (int i = 0; i < 3; ++i) mbar_init(&q_full[i], 1);
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 12);
-        mbar_init(dp_full, 1);
-        mbar_init(dp_free, 12);
-        mbar_init(p_full, 12);
-        mbar_init(p_free, 1);
-        mbar_init(dv_full, 1);
-        mbar_init(dv_free, 8);
-        mbar_init(dk_full, 1);
-        mbar_init(dk_free, 8);
-        mbar_init(dq_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    // The issuing warps need few registers, the compute warps many: move them (per warp group of 4 warps).  Each
-    // setmaxnreg sits at the top of the role branch it governs: ptxas allocates a region by the setmaxnreg that dominates
-    // it (after a common if / else it may fall back to the smaller limit).
-
-    auto load_kv = [&](int j) {  // K_j, V_j -> stage j & 1 (called by one thread)
-        const int s = j & 1;
-        uint8_t* dst = sKV + s * 2 * BK_KV_TILE;
-        mbar_expect_tx(&kv_full[s], 2 * BK_KV_TILE);
-        tma_load_3d(dst, &args.tmKV, &kv_full[s], inner + h * 64, j * BK_KEYS, b);
-        tma_load_3d(dst + BK_KV_TILE, &args.tmKV, &kv_full[s], 2 * inner + h * 64, j * BK_KEYS, b);
-    };
-
-    if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BK_REGS_MMA));
-      if (warp == 0) {
-        // ---- initial loads: all Q_i / dO_i and the first two K/V blocks ----
-        if (elect_one()) {
-            auto load_q = [&](int i) {
-                mbar_expect_tx(&q_full[i], 3 * TILE_BYTES);
-                tma_load_3d(sQ + i * TILE_BYTES, &args.tmQ, &q_full[i], h * 64, i * 128, b);
-                tma_load_3d(sdO + i * TILE_BYTES, &args.tmDO, &q_full[i], h * 64, i * 128, b);
-                tma_load_3d(sdS + i * TILE_BYTES, &args.tmO, &q_full[i], h * 64, i * 128, b);  // O_i: only for delta, before any dS
-            };
-            load_q(0);
-            load_kv(0);
-            for (int i = 1; i < nqb; ++i) load_q(i);
-            if (nkb > 1) load_kv(1);
-        }
-      }
-      if (warp < 2) {
-        // ================================ MMA issuers ================================
-        // warp 0 (X): a(p+1) = S, c(p) = dV.   warp 1 (Y): b(p+1) = dP, d(p) = dQ, dK.
-        // Descriptors are (lo, hi) 32-bit pairs; a K-step adds a constant to lo (see ptx.cuh).
-        if (elect_one()) {
-            const bool X = warp == 0;
-            constexpr uint32_t hi = umma_desc_hi(1024);
-            const uint32_t idesc_tn = umma_idesc_bf16(128, 64, 1, 1);   // dK / dV: A = P^T / dS^T (MN-major), B MN-major
-            const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ    : A = dS (K-major), B = K (MN-major)
-            // K-major operand tile (Q, dO, K, V): K-step = 32 B;  MN-major operand: K-step = 16 rows = 2048 B
-            const uint32_t kmaj0 = umma_desc_lo(smem_u32(X ? sQ : sdO), 16);          // A of a / b, + slot * TILE
-            const uint32_t kv0 = umma_desc_lo(smem_u32(sKV + (X ? 0 : BK_KV_TILE)), 16);  // B of a (K_j) / b (V_j), + stage
-            const uint32_t tr0 = umma_desc_lo(smem_u32(X ? sP : sdS), TILE_BYTES);    // A of c / dK: P^T / dS^T (+ dS buffer)
-            const uint32_t mn0 = umma_desc_lo(smem_u32(X ? sdO : sQ), 8192);          // B of c / dK: dO_i / Q_i, + slot * TILE
-            const uint32_t dsk0 = umma_desc_lo(smem_u32(sdS), 16);                    // A of dQ: dS, K-major (+ dS buffer)
-            const uint32_t kmn0 = umma_desc_lo(smem_u32(sKV), 8192);                  // B of dQ: K_j MN-major, + stage
-            auto keys_in = [&](int j) { return min(BK_KEYS, T - j * BK_KEYS); };
-            auto rows_in = [&](int i) { return min(128, T - i * 128); };
-            auto issue_ab = [&](int j, int i) {  // X: S = Q_i K_j^T      Y: dP = dO_i V_j^T
-                const uint32_t a_lo = kmaj0 + i * (TILE_BYTES >> 4);
-                const uint32_t b_lo = kv0 + (j & 1) * (2 * BK_KV_TILE >> 4);
-                const uint32_t idesc = umma_idesc_bf16(128, (keys_in(j) + 15) & ~15, 0, 0);
-                const uint32_t d = tmem_base + (X ? BK_T_S : BK_T_DP);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ss_lohi(d, a_lo + k * 2, b_lo + k * 2, hi, idesc, k != 0);
-                umma_commit(X ? s_full : dp_full);
-            };
-            if (X) PROF(0);
-            mbar_wait(&q_full[0], 0);
-            mbar_wait(&kv_full[0], 0);
-            if (X) PROF(1);
-            tc_fence_after();
-            issue_ab(0, 0);
-            int p = 0;
-            for (int j = 0; j < nkb; ++j) {
-                const int ks_k = (keys_in(j) + 15) >> 4;  // K steps over the keys of this block
-                for (int i = 0; i < nqb; ++i, ++p) {
-                    const uint32_t pp = p & 1;
-                    const bool has_next = p + 1 < total;
-                    const int jn = (i + 1 < nqb) ? j : j + 1;
-                    const int in = (i + 1 < nqb) ? i + 1 : 0;
-                    const int ks_q = (rows_in(i) + 15) >> 4;  // K steps over the queries of this block
-                    if (has_next) {
-                        mbar_wait(X ? s_free : dp_free, pp);
-                        if (in == 0) mbar_wait(&kv_full[jn & 1], (jn >> 1) & 1);
-                        mbar_wait(&q_full[in], 0);
-                        tc_fence_after();
-                        issue_ab(jn, in);
-                    }
-                    if (p < 8) PROF((X ? 10 : 12) + p * 4);
-                    if (X) mbar_wait(p_full, pp);
-                    else mbar_wait(&ds_full[pp], (p >> 1) & 1);
-                    if (p < 8) PROF((X ? 11 : 13) + p * 4);
-                    if (i == 0 && j > 0) mbar_wait(X ? dv_free : dk_free, (j - 1) & 1);  // dV_{j-1} / dK_{j-1} were copied out
-                    tc_fence_after();
-                    const uint32_t b_lo = mn0 + i * (TILE_BYTES >> 4);
-                    if (X) {
-                        // c(p): dV_j += P^T dO_i
-#pragma unroll
-                        for (int s = 0; s < 8; ++s)
-                            if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DV, tr0 + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
-                        umma_commit(p_free);
-                    } else {
-                        // d(p): dQ_i += dS K_j ; dK_j += dS^T Q_i
-                        const uint32_t k_lo = kmn0 + (j & 1) * (2 * BK_KV_TILE >> 4);
-#pragma unroll
-                        for (int s = 0; s < 6; ++s)
-                            if (s < ks_k)
-                                umma_ss_lohi(tmem_base + BK_T_DQ + i * 64,
-                                             (s < 4 ? dsk0 + pp * (TILE_BYTES >> 4) + s * 2
-                                                    : dsk0 + (2 * TILE_BYTES >> 4) + pp * 4 + (s - 4) * 2),
-                                             k_lo + s * 128, hi, idesc_dq, (j | s) != 0);
-                        // dS^T as MN-major A: keys 0..63 from tile pp, keys 64..127 from the shared tile (LBO spans the gap)
-                        const uint32_t dst_lo = umma_desc_lo(smem_u32(sdS) + pp * TILE_BYTES, (2 - pp) * TILE_BYTES + pp * 64);
-#pragma unroll
-                        for (int s = 0; s < 8; ++s)
-                            if (s < ks_q) umma_ss_lohi(tmem_base + BK_T_DK, dst_lo + s * 128, b_lo + s * 128, hi, idesc_tn, (i | s) != 0);
-                        umma_commit(&ds_free[pp]);
-                    }
-                    if (i == nqb - 1) umma_commit(X ? dv_full : dk_full);
-                }
-            }
-            if (!X) umma_commit(dq_full);
-            if (X) PROF(2);
-        }
-      }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BK1_REGS_COMPUTE));
-        // ================================ compute warps ================================
-        // 12 warps: warp (q, slab) owns TMEM lane quadrant q (one query row per thread) and the 32 key columns
-        // [32 slab, 32 slab + 32) of every 96-key block -- for the probabilities AND for dS, so P stays in registers
-        // between the two phases of a pair.
-        const int q = warp & 3;
-        const int slab = (warp - 4) >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int c0 = slab * 32;
-        const float c = args.scale_log2e;
-        const int sw = row & 7;
-        const bool prof_thread = threadIdx.x == 128;
-        // ---- prologue: delta * scale = rowsum(dO * O) * scale of query block `slab` -> smem, then everybody reads its rows.
-        // O_i arrives by TMA in the (still unused) dS tiles next to dO_i: per-thread global loads of these rows took
-        // 11,000 clocks here, the TMA tiles land in about 1,500.
-        float* sdl = reinterpret_cast<float*>(smem + BK_DELTA);
-        if (prof_thread) PROF(90);
-        if (slab < nqb) {
-            mbar_wait(&q_full[slab], 0);
-            const uint8_t* orow = sdS + slab * TILE_BYTES + row * 128;
-            const uint8_t* drow = sdO + slab * TILE_BYTES + row * 128;
-            float acc = 0.0f;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-                acc += dot8_bf16(*reinterpret_cast<const uint4*>(orow + ((g ^ sw) << 4)), *reinterpret_cast<const uint4*>(drow + ((g ^ sw) << 4)));
-            sdl[slab * 128 + row] = acc * args.scale;  // rows past T were zero-filled by the TMA
-        }
-        // Query rows past T: lse = +inf makes their probabilities exact zeros (S = 0 there: the TMA zero-fills Q), and with
-        // P = 0, dP = 0 (dO zero-filled) and delta = 0 their dS is an exact zero too -- no masking needed for rows.
-        float lse2[3], sdelta[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int t = i * 128 + row;
-            lse2[i] = (i < nqb && t < T) ? args.lse[(static_cast<size_t>(b) * H + h) * T + t] * 1.4426950408889634f : __int_as_float(0x7f800000);
-        }
-        if (prof_thread) PROF(91);
-        named_bar_sync(1, 384);
-        if (prof_thread) PROF(92);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) sdelta[i] = sdl[i * 128 + row];
-
-        // Key block jb is complete: dK | dV (TMEM columns [192, 320), lane = key, eight 16-column parts; three / three / two
-        // per slab) -> bf16 -> the block's own K / V stage (every MMA that read it has retired) -> two TMA stores; then
-        // the stage is refilled with block jb+2.  Per-thread global stores from here crawl (32 rows per request, and the
-        // LSU starves while the tensor core streams operands from shared memory).  A small rolled loop on purpose:
-        // unrolled, its register bursts made ptxas spill inside the software-pipelined loop below.
-        auto store_kv = [&](int jb) {
-            const bool key_warp = q * 32 < min(BK_KEYS, T - jb * BK_KEYS);
-            uint8_t* stage = sKV + (jb & 1) * 2 * BK_KV_TILE;
-            if (slab < 2) mbar_wait(dk_full, jb & 1);
-            if (slab > 0) mbar_wait(dv_full, jb & 1);
-            if (prof_thread && jb == 0) PROF(70);
-            tc_fence_after();
-            if (key_warp) {
-#pragma unroll 1
-                for (int a = slab * 3; a < min(8, slab * 3 + 3); ++a) {
-                    uint32_t o[16];
-                    tmem_ld_32x16(t_row + BK_T_DK + a * 16, o);
-                    tmem_ld_wait();
-                    uint8_t* trow = stage + (a >> 2) * BK_KV_TILE + row * 128;
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
-                        v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
-                        v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
-                        v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
-                        *reinterpret_cast<uint4*>(trow + ((((a & 3) * 2 + g) ^ sw) << 4)) = v;
-                    }
-                }
-            }
-            tc_fence_before();
-            if (slab < 2) mbar_arrive_warp(dk_free);
-            if (slab > 0) mbar_arrive_warp(dv_free);
-            if (prof_thread && jb == 0) PROF(71);
-            fence_proxy_async_smem();
-            named_bar_sync(2, 384);
-            if (prof_thread && jb == 0) PROF(72);
-            if (warp == 4 && lane == 0) {
-                tma_store_3d(&args.tmDKV, stage, inner + h * 64, jb * BK_KEYS, b);
-                tma_store_3d(&args.tmDKV, stage + BK_KV_TILE, 2 * inner + h * 64, jb * BK_KEYS, b);
-                tma_store_commit();
-            }
-        };
-        // one step later the stores have long read the stage: refill it with block jb+2 (waiting right away would stall
-        // this warp, and with it every hand-off of the step, for the ~1,500 clocks the TMA needs to drain 24 KB)
-        auto reload_kv = [&](int jb) {
-            if (warp == 4 && lane == 0 && jb + 2 < nkb) {
-                tma_store_wait_read<0>();
-                load_kv(jb + 2);
-            }
-        };
-
-        // Software pipeline: step p computes dS(p) and P(p+1).  S(p+1) and dP(p) were both issued at the beginning of
-        // step p-1 (when their TMEM buffers were read out), so neither wait below ever sees the tensor pipe's latency,
-        // and the S load is in flight while dS is computed and written.
-        // Both phases compute all 32 columns unconditionally; slabs that contain rows past T or keys past the block's
-        // end (a few warps of the last query / key block) then clear those entries with integer masks, which also
-        // kills whatever stale TMEM contents (columns beyond the MMA's N extent) may have produced.
-        uint32_t pk[16];  // P(p), then dS(p), of this thread's 32 columns, packed bf16 (exact zeros where masked)
-        uint32_t pn[16];  // P(p+1) while dS(p) is still in pk
-        // Keys past T exist only in the last key block: slabs entirely beyond them hold zeros, the one slab that straddles
-        // the end clears its invalid columns with integer masks (which also kills whatever the stale TMEM columns beyond
-        // the MMA's N extent produced).
-        auto clear_unreal = [&](uint32_t (&pk)[16], int jj) {
-            const int nv = min(BK_KEYS, T - jj * BK_KEYS) - c0;  // real keys among this slab's columns
-            if (nv >= 32) return;                                 // warp-uniform
-            if (nv <= 0) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) pk[k] = 0u;
-                return;
-            }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) pk[k] &= (2 * k + 1 < nv ? 0xffffffffu : (2 * k < nv ? 0x0000ffffu : 0u));
-        };
-        auto p_math = [&](const uint32_t (&sv)[32], int ii) {
-            const float l2 = ii == 0 ? lse2[0] : (ii == 1 ? lse2[1] : lse2[2]);
-#pragma unroll
-            for (int e = 0; e < 32; e += 2)
-                pk[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
-                                      ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
-        };
-        auto p_store = [&](const uint32_t (&pk)[16]) {
-            uint8_t* prow = sP + row * 128;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int gc = slab * 4 + g;
-                *reinterpret_cast<uint4*>(prow + (gc >> 3) * TILE_BYTES + (((gc & 7) ^ sw) << 4)) =
-                    make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive_warp(p_full);
-        };
-        auto ds_math = [&](const uint32_t (&dv)[32], int ii) {
-            const float sd = ii == 0 ? sdelta[0] : (ii == 1 ? sdelta[1] : sdelta[2]);
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                const uint32_t pa = pk[e / 2];
-                pk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(dv[e]), args.scale, -sd),
-                                      bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
-            }
-        };
-        auto ds_store = [&](int p) {
-            const uint32_t pp = p & 1;
-            if (p > 1) mbar_wait(&ds_free[pp], ((p >> 1) - 1) & 1);  // d(p-2) retired: this dS buffer is free
-            uint8_t* dsrow0 = sdS + pp * TILE_BYTES + row * 128;  // keys 0..63
-            uint8_t* dsrow1 = sdS + 2 * TILE_BYTES + row * 128;   // keys 64..95: chunks 4*pp .. 4*pp+3 of the shared tile
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int gc = slab * 4 + g;
-                const uint4 o = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                if (gc < 8) *reinterpret_cast<uint4*>(dsrow0 + ((gc ^ sw) << 4)) = o;
-                else *reinterpret_cast<uint4*>(dsrow1 + ((((gc - 8) + 4 * pp) ^ sw) << 4)) = o;
-            }
-            fence_proxy_async_smem();
-            mbar_arrive_warp(&ds_full[pp]);
-        };
-
-        // ---- step -1: P(0)
-        {
-            uint32_t sv[32];
-            mbar_wait(s_full, 0);
-            if (prof_thread) PROF(93);
-            tc_fence_after();
-            tmem_ld_32x32(t_row + BK_T_S + c0, sv);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive_warp(s_free);
-            p_math(sv, 0);
-            clear_unreal(pk, 0);
-            p_store(pk);
-            if (prof_thread) PROF(94);
-        }
-        // ---- steps 0 .. total-2: dS(p) and P(p+1);  pair p = (j, i), pair p+1 = (jn, in)
-        int j = 0, i = 0, jn = nqb > 1 ? 0 : 1, in = nqb > 1 ? 1 : 0;
-#pragma unroll 1
-        for (int p = 0; p + 1 < total; ++p) {
-            uint32_t dv[32], sv[32];
-            if (prof_thread && p < 8) PROF(100 + p * 4);
-            mbar_wait(dp_full, p & 1);
-            mbar_wait(s_full, (p + 1) & 1);
-            if (prof_thread && p < 8) PROF(101 + p * 4);
-            tc_fence_after();
-            tmem_ld_32x32(t_row + BK_T_DP + c0, dv);
-            tmem_ld_32x32(t_row + BK_T_S + c0, sv);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive_warp(dp_free);
-            mbar_arrive_warp(s_free);
-            // dS(p) (FMA pipe) and P(p+1) (MUFU) element by element in one instruction stream, so that the two pipes overlap
-            {
-                const float sd = i == 0 ? sdelta[0] : (i == 1 ? sdelta[1] : sdelta[2]);
-                const float l2 = in == 0 ? lse2[0] : (in == 1 ? lse2[1] : lse2[2]);
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const uint32_t pa = pk[e / 2];
-                    pn[e / 2] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sv[e]), c, -l2)),
-                                          ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -l2)));
-                    pk[e / 2] = pack_bf16(bf16_lo(pa) * fmaf(__uint_as_float(dv[e]), args.scale, -sd),
-                                          bf16_hi(pa) * fmaf(__uint_as_float(dv[e + 1]), args.scale, -sd));
-                }
-            }
-            // Key block j-1 is final: copy dK / dV out.  Here rather than at the top of the step: d(p-1) needs ~1,000 clocks
-            // after the previous step's dS hand-off to retire, and the arithmetic above has just covered them.
-            if (i == 0 && j > 0) {
-                if (prof_thread) PROF(80 + j * 2);
-                store_kv(j - 1);
-                if (prof_thread) PROF(81 + j * 2);
-            }
-            clear_unreal(pk, j);
-            ds_store(p);
-            if (prof_thread && p < 8) PROF(102 + p * 4);
-            clear_unreal(pn, jn);
-            mbar_wait(p_free, p & 1);  // c(p) retired: the P tile may be overwritten
-            p_store(pn);
-            if (prof_thread && p < 8) PROF(103 + p * 4);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) pk[k] = pn[k];
-            if (i == 0 && j > 0) reload_kv(j - 1);
-            j = jn, i = in;
-            if (++in == nqb) in = 0, ++jn;
-        }
-        // ---- last step: dS(total-1)
-        {
-            const int p = total - 1;
-            if (i == 0 && j > 0) store_kv(j - 1);
-            uint32_t dv[32];
-            mbar_wait(dp_full, p & 1);
-            tc_fence_after();
-            tmem_ld_32x32(t_row + BK_T_DP + c0, dv);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive_warp(dp_free);
-            ds_math(dv, i);
-            clear_unreal(pk, j);
-            ds_store(p);
-        }
-        if (prof_thread) PROF(95);
-        store_kv(nkb - 1);
-        if (prof_thread) PROF(96);
-        // ---- epilogue: slab i converts dQ_i -> bf16 -> staging (sP tiles, then dS buffer 0) -> TMA store ----
-        mbar_wait(dq_full, 0);
-        if (prof_thread) PROF(97);
-        tc_fence_after();
-        if (slab < nqb && slab * 128 + q * 32 < T) {  // rows past T are clipped by the store anyway
-            const int i = slab;
-            uint8_t* orow = (i < 2 ? sP + i * TILE_BYTES : sdS) + row * 128;
-#pragma unroll 1
-            for (int part = 0; part < 2; ++part) {
-                uint32_t o0[32];
-                tmem_ld_32x32(t_row + BK_T_DQ + i * 64 + part * 32, o0);
-                tmem_ld_wait();
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t* src = &o0[g * 8];
-                    uint4 o;
-                    o.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-                    o.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-                    o.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-                    o.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-                    *reinterpret_cast<uint4*>(orow + (((part * 4 + g) ^ sw) << 4)) = o;
-                }
-            }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 384);
-        if (warp == 4 && lane == 0) {
-            for (int i = 0; i < nqb; ++i)
-                tma_store_3d(&args.tmDQ, i < 2 ? sP + i * TILE_BYTES : sdS, h * 64, i * 128, b);
-            tma_store_commit();
-            tma_store_wait_all<0>();
-            PROF(3);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
 // =================================================================================================
 // host
 // =================================================================================================
@@ -1716,52 +953,8 @@ static int check_attn_shape(int B, int H, int T) {
     return 0;
 }
 
-static int launch_attn_fwd_v1(const AttnDesc& d, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW1_SMEM);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(attn_fwd_v1) failed: %s", cudaGetErrorString(e));
-            return -10;
-        }
-        configured = true;
-    }
-    const int inner = d.H * 64;
-    AttnFwdV1Args a;
-    memset(&a, 0, sizeof(a));
-    int rc = 0;
-    rc |= make_tmap_3d(&a.tmQKV, d.qkv, TmapDtype::BF16, 3 * inner, d.T, d.B, (uint64_t)3 * inner * 2,
-                       (uint64_t)d.T * 3 * inner * 2, 64, 128);
-    rc |= make_tmap_3d(&a.tmO, d.out, TmapDtype::BF16, inner, d.T, d.B, (uint64_t)inner * 2, (uint64_t)d.T * inner * 2, 64,
-                       128);
-    if (rc) {
-        set_error("attn_fwd: tensor map creation failed: %s", tmap_last_error());
-        return -3;
-    }
-    a.lse = d.lse;
-    a.B = d.B;
-    a.H = d.H;
-    a.T = d.T;
-    a.scale = d.scale;
-    a.scale_log2e = d.scale * 1.4426950408889634f;
-    {
-        static const char* dbg = getenv("SVIT_ATTN_DEBUG");
-        a.debug = dbg ? atoi(dbg) : 0;
-    }
-    attn_fwd_v1_kernel<<<d.B * d.H, FW1_THREADS, FW1_SMEM, stream>>>(a);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        set_error("attn_fwd launch failed: %s", cudaGetErrorString(e));
-        return -11;
-    }
-    return 0;
-}
-
 int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     if (check_attn_shape(d.B, d.H, d.T)) return -1;
-    static const bool use_v1 = getenv("SVIT_ATTN_FWD_V1") != nullptr && atoi(getenv("SVIT_ATTN_FWD_V1")) != 0;
-    if (use_v1) return launch_attn_fwd_v1(d, stream);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(ATT_MAX_T));
@@ -1815,7 +1008,6 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attn_bwd) failed: %s", cudaGetErrorString(e));
             return -10;
@@ -1847,9 +1039,7 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
         static const char* dbg = getenv("SVIT_ATTN_DEBUG");
         a.debug = dbg ? atoi(dbg) : 0;
     }
-    static const bool use_v1 = getenv("SVIT_ATTN_BWD_V1") != nullptr && atoi(getenv("SVIT_ATTN_BWD_V1")) != 0;
-    if (use_v1) attn_bwd_v1_kernel<<<d.B * d.H, BK1_THREADS, BK_SMEM, stream>>>(a);
-    else attn_bwd_kernel<<<d.B * d.H, BK_THREADS, BK_SMEM, stream>>>(a);
+    attn_bwd_kernel<<<d.B * d.H, BK_THREADS, BK_SMEM, stream>>>(a);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

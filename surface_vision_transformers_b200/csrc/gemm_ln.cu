@@ -12,7 +12,9 @@
 // per CTA -- SiT-small; other widths keep the separate kernels): an N = 256 and an N = 128 MMA per 16-wide K step.  Besides making the fusion possible the
 // wide tile reads A once instead of once per 192-column tile -- these GEMMs are bound by the L2 -> SM operand feed.
 // One accumulator stage (2 x 384 columns would not fit TMEM): the MMAs of the next tile wait for the epilogue, the
-// operand ring keeps prefetching meanwhile.
+// operand ring keeps prefetching meanwhile.  (Starting every other cluster half a tile period late, so that the HBM-bound
+// epilogues of one half of the chip run under the MMA phases of the other, was measured and does not help: 85.7 -> 87.9 us
+// for the out-projection shape, 139.7 -> 147.4 us for fc2 at M = 82176.)
 //
 // Epilogue, 8 warps = TMEM lane quadrant q (32 rows, one per thread) x column half p:
 //   pass 1  acc + bias + residual -> x (fp32): staged in place over the TMA-prefetched residual box, TMA-stored, and
@@ -71,7 +73,6 @@ struct LnArgs {
     float* rstd;
     int M, K;
     float eps;
-    unsigned stagger_ns;  // start delay of the odd clusters (see below)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -148,12 +149,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // With one accumulator stage a CTA alternates between an MMA phase (L2 operand traffic, hardly any HBM traffic) and an
-    // epilogue phase (10 bytes of HBM traffic per element, no MMA).  All clusters start together, so left alone the whole
-    // chip computes while HBM idles and then drains while the tensor cores idle; starting every other cluster half a
-    // tile period later keeps both busy.
-    if ((cluster_id & 1) && args.stagger_ns) __nanosleep(args.stagger_ns);
-
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
@@ -467,14 +462,6 @@ int launch_gemm_ln(const GemmLnDesc& d, int num_sms, cudaStream_t stream) {
     a.M = d.M;
     a.K = d.K;
     a.eps = d.eps;
-    {
-        // half a tile period of the odd clusters: ~ (epilogue 12 us + 0.4 us per 64-wide K block) / 2, only when every
-        // cluster has several tiles (SVIT_LN_STAGGER_NS overrides; 0 disables)
-        static const char* env = getenv("SVIT_LN_STAGGER_NS");
-        const int tiles = (d.M + 2 * LBM - 1) / (2 * LBM);
-        const unsigned auto_ns = tiles >= num_sms ? 5000u + 380u * static_cast<unsigned>((d.K + LBK - 1) / LBK) : 0u;
-        a.stagger_ns = env ? static_cast<unsigned>(atoi(env)) : auto_ns;
-    }
     return launch_ln_inst<384>(a, num_sms, stream);
 }
 
