@@ -76,7 +76,8 @@ def load():
     if _lib is not None:
         return _lib
     # a library that is stale relative to csrc/ or include/ is rebuilt, never loaded silently
-    path = _build.build(force=os.environ.get("SVIT_REBUILD") == "1")
+    # (SVIT_LIB=/path/to/other.so: developer override for A/B-ing a library built with other compile-time options)
+    path = os.environ.get("SVIT_LIB") or _build.build(force=os.environ.get("SVIT_REBUILD") == "1")
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly

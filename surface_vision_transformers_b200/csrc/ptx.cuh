@@ -76,11 +76,16 @@ __device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+#ifndef SVIT_WAIT_HINT_NS
+#define SVIT_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    // SVIT_WAIT_HINT_NS > 0: park the thread in hardware until the phase completes (or the hint expires) instead of
+    // polling -- a waiting warp then costs no issue slots
+    while (!(SVIT_WAIT_HINT_NS > 0 ? mbar_try_wait_suspend(bar, parity, SVIT_WAIT_HINT_NS) : mbar_try_wait(bar, parity))) {
 #ifdef SVIT_SPIN_SLEEP_NS
         __nanosleep(SVIT_SPIN_SLEEP_NS);
 #endif
