@@ -1,0 +1,31 @@
+#!/bin/bash
+# Round-end evidence batch (one GPU): tests, smoke, headline bench + reference arm, workload sweep, launch list of the
+# bench command, full ncu of the dominant kernels, section-level ncu of every kernel of the step.
+O=gpurun_out; T=${1:-r02}
+python -m pytest tests -m gpu -q -s 2>&1 | grep -v Warning | grep -E "passed|failed|FAILED|Error|worst|rel-L2" | tail -40 > $O/${T}_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.log 2>&1
+python bench.py --impl reference --steps 10 --warmup 3 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err
+python bench.py --steps 20 --warmup 5 > $O/${T}_bench.json 2> $O/${T}_bench.err
+python bench.py --sweep $O/${T}_workloads.json --steps 10 --warmup 3 > $O/${T}_sweep.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${T}_launches_sit_small_b256.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_ncu1.log 2>&1
+python scripts/ncu_top.py > $O/${T}_top_plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -o $O/${T}_top python scripts/ncu_top.py > $O/${T}_ncu2.log 2>&1
+python scripts/ncu_summary.py $O/${T}_top.ncu-rep -o $O/${T}_ncu_top_summary.json
+for k in attn_fwd attn_bwd gemm_ln gemm_wgrad ln_bwd; do python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 $k > $O/${T}_ncu_${k}.hot.txt 2>/dev/null; done
+python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 gemm_tn 1 > $O/${T}_ncu_gemm_fc1_gelu_grad.hot.txt 2>/dev/null
+python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 gemm_tn 2 > $O/${T}_ncu_gemm_dfc2_mul.hot.txt 2>/dev/null
+python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 gemm_tn 3 > $O/${T}_ncu_gemm_dfc1_store.hot.txt 2>/dev/null
+python scripts/ncu_all.py > $O/${T}_all_plain.log 2>&1 && timeout 900 ncu --section LaunchStats --section Occupancy --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section WarpStateStats --clock-control none --profile-from-start off -o $O/${T}_all python scripts/ncu_all.py > $O/${T}_ncu3.log 2>&1
+python scripts/ncu_summary.py $O/${T}_all.ncu-rep -o $O/${T}_ncu_all_summary.json && python scripts/ncu_table.py $O/${T}_ncu_all_summary.json > $O/${T}_ncu_all_table.txt
+ls -la $O/${T}_all.ncu-rep; rm -f $O/${T}_all.ncu-rep
+cat $O/${T}_tests.log | tail -4; cat $O/${T}_smoke.log | tail -2; cat $O/${T}_bench_reference.json | cut -c1-300
+python - $T <<'PY'
+import json,sys
+T=sys.argv[1]
+d=json.loads([x for x in open('gpurun_out/%s_bench.json'%T) if x.startswith('{')][-1])
+print('bench', round(d['value']), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), d['clocks'], 'launches', d['gpu_launches'])
+print(' roofline', d['roofline']['kernel'][:40], round(d['roofline']['us_per_launch'],1), round(d['roofline']['frac'],3), d['roofline'].get('traffic'))
+print(' cpu', d['cpu_baseline'])
+for r in json.load(open('gpurun_out/%s_workloads.json'%T)):
+    print(r['config']['workload'], r['config']['batch_per_gpu'], round(r['value']), round(r['ms_per_step'],2), round(r['roofline']['frac'],3))
+PY
+head -40 $O/${T}_ncu_all_table.txt

@@ -1,7 +1,9 @@
 """Lists the hottest SASS instructions (by warp-stall samples) of an ncu report's source page."""
 import csv, subprocess, sys
+# usage: ncu_hot.py report.ncu-rep [top N] [kernel regex] [invocation nr]   (the last two pick one launch of a multi-kernel report)
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["--kernel-id", f"::regex:{sys.argv[3]}:{sys.argv[4] if len(sys.argv) > 4 else 1}"] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]; ci = {h: i for i, h in enumerate(hdr)}
