@@ -14,7 +14,7 @@ for k in attn_fwd attn_bwd gemm_ln gemm_wgrad ln_bwd; do python scripts/ncu_hot.
 python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 gemm_tn 1 > $O/${T}_ncu_gemm_fc1_gelu_grad.hot.txt 2>/dev/null
 python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 gemm_tn 2 > $O/${T}_ncu_gemm_dfc2_mul.hot.txt 2>/dev/null
 python scripts/ncu_hot.py $O/${T}_top.ncu-rep 25 gemm_tn 3 > $O/${T}_ncu_gemm_dfc1_store.hot.txt 2>/dev/null
-python scripts/ncu_all.py > $O/${T}_all_plain.log 2>&1 && timeout 900 ncu --section LaunchStats --section Occupancy --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section WarpStateStats --clock-control none --profile-from-start off -o $O/${T}_all python scripts/ncu_all.py > $O/${T}_ncu3.log 2>&1
+python scripts/ncu_all.py > $O/${T}_all_plain.log 2>&1 && timeout 900 ncu --section LaunchStats --section Occupancy --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section WarpStateStats --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sass__inst_executed_local_loads,sass__inst_executed_local_stores --clock-control none --profile-from-start off -o $O/${T}_all python scripts/ncu_all.py > $O/${T}_ncu3.log 2>&1
 python scripts/ncu_summary.py $O/${T}_all.ncu-rep -o $O/${T}_ncu_all_summary.json && python scripts/ncu_table.py $O/${T}_ncu_all_summary.json > $O/${T}_ncu_all_table.txt
 ls -la $O/${T}_all.ncu-rep; rm -f $O/${T}_all.ncu-rep
 cat $O/${T}_tests.log | tail -4; cat $O/${T}_smoke.log | tail -2; cat $O/${T}_bench_reference.json | cut -c1-300

@@ -1,5 +1,6 @@
 #!/bin/bash
 O=gpurun_out
+for i in 1 2 3 4 5 6; do python -m pytest tests/test_gpu_model.py -q -s -k "bookkeeping" 2>&1 | grep -E "un-synchron|passed|failed"; done
 python -m pytest tests/test_gpu_kernels.py -q -x -k "gemm" 2>&1 | tail -2
 python scripts/bench_kernels.py gemm 2>&1 | grep -E "gemm_wide|gemm_tn  |dfc1|dqkv|gelu" > $O/r2k_kernels.log; cat $O/r2k_kernels.log
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/r2k_bench.log 2>&1

@@ -1,7 +1,9 @@
 """One launch of EVERY kernel of the training step at the benchmark shapes (SiT-small ico-2, per-GPU batch 256), for
 
     ncu --section LaunchStats --section Occupancy --section SpeedOfLight --section MemoryWorkloadAnalysis \
-        --section ComputeWorkloadAnalysis --section WarpStateStats --clock-control none --profile-from-start off \
+        --section ComputeWorkloadAnalysis --section WarpStateStats \
+        --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sass__inst_executed_local_loads,sass__inst_executed_local_stores \
+        --clock-control none --profile-from-start off \
         -o gpurun_out/r02_all python scripts/ncu_all.py
 
 (the sections that hold duration, DRAM bytes, pipe utilisation, occupancy and stall reasons: ~10 replay passes per launch
