@@ -50,6 +50,9 @@ WORKLOADS = {
                    num_classes=1, dim_head=64), kind="infer", gflop_per_sample=58.627),
 }
 DEFAULT_WORKLOAD = "sit_small_ico2_scan_age_train"
+# `ncu --set full` summary of the kernels of the current build (scripts/ncu_top.py + scripts/ncu_summary.py); re-captured
+# whenever a kernel changes -- roofline.traffic is read from it
+NCU_SUMMARY = "r02_ncu_top_summary.json"
 
 
 def load_peaks():
@@ -439,15 +442,15 @@ def main():
         # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/), same shape only
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
-                prof = json.load(f)["gemm_tn_fc1_gelu"]
+            with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as f:
+                prof = json.load(f)["gemm_tn_kernel<__nv_bfloat16, 5, 192, 2, 1>"]
             if kind != "infer" and (M, H4, D) == (82176, 1536, 384):
                 traffic = prof["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
         roof_gemm = dict(bound="tensor", kernel="gemm_tn_kernel<bf16,%s,192,cta_group::2> (fc1 + bias + exact GELU%s, M=%d N=%d K=%d)" % ("EPI_GELU_ONLY" if mode == 4 else "EPI_GELU_GRAD", "" if mode == 4 else " and its derivative", M, H4, D),
                     achieved=ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=ach / peaks["tflops_burst"],
-                    traffic=traffic, traffic_source="profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + "
+                    traffic=traffic, traffic_source="profiles/" + NCU_SUMMARY + " (dram__bytes_read.sum + "
                     "dram__bytes_write.sum, one ncu --set full launch)" if traffic else None,
                     algorithmic_bytes=2.0 * M * D + 2.0 * H4 * D + (2 if mode == 5 else 1) * 2.0 * M * H4,
                     peak_source=peaks["source"] + " (burst: kernel timed alone)",
@@ -490,8 +493,8 @@ def main():
         a_ach = a_flops / (a_ms * 1e-3) / 1e12
         a_traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
-                prof = json.load(f)[a_key]
+            with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as f:
+                prof = json.load(f)[a_key + "_kernel"]
             if (B, Hh, T) == (256, 6, 321):
                 a_traffic = prof["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
@@ -499,14 +502,14 @@ def main():
         roof = dict(bound="tensor", kernel="%s (one CTA per (sample, head); B=%d H=%d T=%d d=64; %s*T^2*64 flop per head at the "
                                           "unpadded T)" % (a_name, B, Hh, T, "4" if kind == "infer" else "10"),
                     achieved=a_ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=a_ach / peaks["tflops_burst"],
-                    traffic=a_traffic, traffic_source="profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + "
+                    traffic=a_traffic, traffic_source="profiles/" + NCU_SUMMARY + " (dram__bytes_read.sum + "
                     "dram__bytes_write.sum, one ncu --set full launch)" if a_traffic else None,
                     algorithmic_bytes=a_bytes, peak_source=peaks["source"] + " (burst: kernel timed alone)",
                     us_per_launch=a_ms * 1e3, flops_per_launch=a_flops,
                     share_of_step=a_ms * m["depth"] / ms_step,
                     note="fraction of the dense bf16 tensor peak at the algorithmic flop count; T=%d pads to 128x96 tiles "
-                         "(executed MMA work is 1.6x the algorithmic count at T=321) and the kernel is bound by the "
-                         "softmax / dS warps' issue slots and per-step hand-offs, not by the tensor pipe (DESIGN.md 3a)" % T,
+                         "(executed MMA work is 1.4x the algorithmic count at T=321) and the kernel is bound by the latency "
+                         "chain of its compute warps through one P tile per step, not by the tensor pipe (DESIGN.md 3, 3b)" % T,
                     step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
                     step_frac_of_nominal_2250=step_tf / 2250.0)
 

@@ -173,10 +173,6 @@ int svit_gemm_tn(const void* A, const void* B, void* out, void* out2, const void
 int svit_gemm_ln(const void* A, const void* W, const float* bias, const float* x_in, float* x_out, void* a_out,
                  const float* gamma, const float* beta, float* mean, float* rstd, int M, int D, int K, int lda, int ldb,
                  float eps, int num_sms, void* stream);
-/* out[M, 384] (bf16) = A[M, K] W[384, K]^T (+ bias) on the same full-row 256 x 384 CTA-pair tile: the input-gradient GEMMs
- * of the backward pass whose output is the model width (autograd of to_qkv / to_out / FeedForward.net[0]). */
-int svit_gemm_wide(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int lda, int ldb,
-                   int ldo, int num_sms, void* stream);
 int svit_gemm_wgrad(const void* dY, const void* X, float* dW, int M, int N, int K, int ldy, int ldx, int ldw,
                     int num_sms, void* stream);
 /* same, and dbias[N] += sum over the M rows of dY (bias gradient of the Linear, fused as one extra MMA) */

@@ -62,14 +62,6 @@ if "gemm" in which:
         by = M*K*2 + D*K*2 + M*D*4*2 + M*D*2
         timeit(f"gemm_ln {nm}  [M,{K}]x[384] resid f32 + LN", lambda: lib.svit_gemm_ln(ptr(A), ptr(W), ptr(bias), ptr(xin), ptr(xo), ptr(ao), ptr(g), ptr(bt), ptr(mean), ptr(rstd), M, D, K, K, K, 1e-5, SMS, st()),
                bytes_=by, flops=2.0*M*D*K)
-if "gemm" in which:
-    for (K, nm) in ((1536, "dfc1"), (1152, "dqkv"), (384, "dO")):
-        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16(); W = (torch.randn(D, K, device=dev) * 0.05).bfloat16()
-        o = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-        timeit(f"gemm_wide {nm} [M,{K}]x[384] store bf16 (256x384 tile)", lambda: lib.svit_gemm_wide(ptr(A), ptr(W), vp(0), ptr(o), M, D, K, K, K, D, SMS, st()),
-               bytes_=M*K*2 + D*K*2 + M*D*2, flops=2.0*M*D*K)
-        timeit(f"gemm_tn   {nm} [M,{K}]x[384] store bf16 (256x192 tile)", lambda: lib.svit_gemm_tn(ptr(A), ptr(W), ptr(o), vp(0), vp(0), vp(0), vp(0), 1, M, D, K, K, K, D, 0, 0, SMS, st()),
-               bytes_=M*K*2 + D*K*2 + M*D*2, flops=2.0*M*D*K)
 if "wgrad" in which:
     for (N, K) in [(1152, 384), (384, 384), (1536, 384), (384, 1536), (384, 640)]:
         dY = (torch.randn(M, N, device=dev) * 0.5).bfloat16(); X = (torch.randn(M, K, device=dev) * 0.5).bfloat16()

@@ -59,7 +59,6 @@ SIGNATURES = {
     "svit_regression_loss": (ci, [vp, vp, ci, ci, vp, vp, vp]),
     "svit_gemm_tn": (ci, [vp] * 7 + [ci] * 10 + [vp]),
     "svit_gemm_ln": (ci, [vp] * 10 + [ci] * 5 + [cf, ci, vp]),
-    "svit_gemm_wide": (ci, [vp] * 4 + [ci] * 7 + [vp]),
     "svit_gemm_wgrad": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),
     "svit_gemm_wgrad_bias": (ci, [vp, vp, vp, vp] + [ci] * 7 + [vp]),
     "svit_attn_fwd": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),

@@ -40,7 +40,6 @@ struct svit_engine {
     float drop_p, drop_emb_p;
     unsigned long long drop_seed, drop_offset;
     int no_fuse_ln;  // SVIT_NO_FUSE_LN=1: keep the stand-alone LayerNorm kernels (A/B timing)
-    int no_wide;     // SVIT_NO_WIDE=1: input-gradient GEMMs on the 256 x 192 tiles of gemm_tn (A/B timing)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -167,15 +166,6 @@ static int gemm(const svit_engine* e, cudaStream_t st, const void* A, int lda, c
                 void* out2 = nullptr, const float* rowtab = nullptr, int period = 1) {
     GemmTnDesc d{A, Bm, out, out2, aux, bias, rowtab, period, M, N, K, lda, ldb, ldo, mode, out_f32};
     return launch_gemm_tn(d, e->num_sms, st);
-}
-// out[M, N] (bf16) = A Bm^T: the 256 x 384 full-row tile when the output is 384 wide (gemm_ln.cu), else gemm_tn
-static int gemm_store(const svit_engine* e, cudaStream_t st, const void* A, int lda, const void* Bm, int ldb, void* out, int ldo,
-                      int M, int N, int K) {
-    if (gemm_ln_supported(N) && !e->no_wide && M >= 256 * (e->num_sms / 2)) {
-        GemmWideDesc d{A, Bm, nullptr, out, M, N, K, lda, ldb, ldo};
-        return launch_gemm_wide(d, e->num_sms, st);
-    }
-    return gemm(e, st, A, lda, Bm, ldb, out, ldo, M, N, K, EPI_STORE, 0);
 }
 static int wgrad(const svit_engine* e, cudaStream_t st, const void* dY, int ldy, const void* X, int ldx, float* dW, int ldw,
                  int M, int N, int K, float* dbias = nullptr) {
@@ -305,7 +295,8 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
                     0, nullptr, L.u));
         RET_IF(wgrad(e, st, gb, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp, drop ? gp(FC2_B) : nullptr));
         // da2 = du W1
-        RET_IF(gemm_store(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, M, D, mlp));
+        RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, M, D, mlp,
+                    EPI_STORE, 0));
         RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D, gp(FC1_B)));  // + d fc1_b = colsum(du)
         // g_mid = g + LN2'(da2) ; colsum(g_mid) = d out_b
         RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, w.g16, gp(LN2_W), gp(LN2_B),
@@ -316,11 +307,12 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
             RET_IF(launch_dropout_grad(w.g, w.da, nD, 1, drop_layer(e, l, DROP_SITE_TO_OUT), st));
             gb = w.da;
         }
-        RET_IF(gemm_store(e, st, gb, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D));
+        RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
         RET_IF(wgrad(e, st, gb, D, L.O, I, gp(OUT_W), I, M, D, I, drop ? gp(OUT_B) : nullptr));
         AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, scale};
         RET_IF(launch_attn_bwd(bd, st));
-        RET_IF(gemm_store(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I));
+        RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
+                    EPI_STORE, 0));
         RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
         // g_in = g_mid + LN1'(da1) ; colsum(g_in) = d fc2_b of the previous layer
         float* cs = (l > 0 && !drop) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
@@ -589,7 +581,6 @@ svit_engine* svit_create(const svit_config* cfg) {
     e->drop_p = e->drop_emb_p = 0.0f;
     e->drop_seed = e->drop_offset = 0;
     e->no_fuse_ln = getenv("SVIT_NO_FUSE_LN") != nullptr && atoi(getenv("SVIT_NO_FUSE_LN")) != 0;
-    e->no_wide = getenv("SVIT_NO_WIDE") != nullptr && atoi(getenv("SVIT_NO_WIDE")) != 0;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int sms = 0;
@@ -912,12 +903,6 @@ int svit_gemm_ln(const void* A, const void* W, const float* bias, const float* x
                  int num_sms, void* stream) {
     GemmLnDesc d{A, W, bias, x_in, x_out, a_out, gamma, beta, mean, rstd, M, D, K, lda, ldb, eps};
     return launch_gemm_ln(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int svit_gemm_wide(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int lda, int ldb, int ldo,
-                   int num_sms, void* stream) {
-    GemmWideDesc d{A, W, bias, out, M, N, K, lda, ldb, ldo};
-    return launch_gemm_wide(d, num_sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int svit_regression_loss(const float* out, const float* target, int n, int l1, float* loss, float* dout, void* stream) {

@@ -107,9 +107,9 @@ struct EpiTraits {
     static constexpr bool HAS_AUX = (MODE == EPI_RESID || MODE == EPI_DGELU || MODE == EPI_MUL);
     static constexpr bool TWO_OUT = (MODE == EPI_GELU || MODE == EPI_GELU_GRAD);
     static constexpr bool HEAVY = (MODE == EPI_GELU || MODE == EPI_GELU_GRAD || MODE == EPI_GELU_ONLY);
-    // 64-byte staging boxes: the GELU epilogues (16 warps), and the `* stored gelu'` epilogue of the MLP input gradient,
-    // whose three-box residual ring then fits next to a resident A block (ARES)
-    static constexpr bool SMALLBOX = HEAVY || MODE == EPI_MUL;
+    // 64-byte staging boxes for the GELU epilogues (16 warps).  (Measured and rejected: the `* stored gelu'` epilogue of
+    // the MLP input gradient on 64-byte boxes with a resident A block, 118.7 -> 137.8 us at M = 82176.)
+    static constexpr bool SMALLBOX = HEAVY;
     static constexpr int EW = HEAVY ? 16 : SVIT_EPI_WARPS;   // epilogue warps
     static constexpr int NP = EW / 4;                          // warps per TMEM lane quadrant
     static constexpr int BOXB = SMALLBOX ? 64 : 128;           // bytes per staging-box row (= TMA swizzle span)
@@ -880,7 +880,7 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
     const int osz = d.out_f32 ? 4 : 2;
     // staging-box row of the mode's epilogue (EpiTraits::BOXB): the GELU epilogues use 64-byte boxes
     const bool heavy = d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD || d.mode == EPI_GELU_ONLY;
-    const int box_cols = ((heavy || d.mode == EPI_MUL) ? 64 : 128) / osz;
+    const int box_cols = (heavy ? 64 : 128) / osz;
     rc |= make_tmap_2d(&a.tmOut, d.out, odt, d.N, d.M, (uint64_t)d.ldo * osz, box_cols, 32);
     if (d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD) rc |= make_tmap_2d(&a.tmOut2, d.out2, odt, d.N, d.M, (uint64_t)d.ldo * osz, box_cols, 32);
     if (d.mode == EPI_RESID || d.mode == EPI_DGELU || d.mode == EPI_MUL)
@@ -895,8 +895,7 @@ int launch_gemm_tn(const GemmTnDesc& d, int num_sms, cudaStream_t stream) {
     // 64-byte-box epilogue, whose staging leaves room for the resident A block; the aux epilogues (residual, * gelu') LOSE
     // 10-20 % with their rings cut to two boxes and keep the streaming schedule)
     const bool heavy_mode = d.mode == EPI_GELU || d.mode == EPI_GELU_GRAD || d.mode == EPI_GELU_ONLY;
-    bool ares = cg == 2 && d.K <= ARES_KB * BK && (d.N + BN - 1) / BN >= 3 &&
-                (d.mode == EPI_STORE || heavy_mode || d.mode == EPI_MUL);
+    bool ares = cg == 2 && d.K <= ARES_KB * BK && (d.N + BN - 1) / BN >= 3 && (d.mode == EPI_STORE || heavy_mode);
     if (force_ares == 0) ares = false;
     if (force_ares == 1 && d.K <= ARES_KB * BK && cg == 2) ares = true;
     if (cg == 2) return ares ? dispatch_tn<2, true>(d, a, num_sms, stream) : dispatch_tn<2, false>(d, a, num_sms, stream);

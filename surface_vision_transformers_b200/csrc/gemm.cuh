@@ -72,16 +72,6 @@ struct GemmLnDesc {
 bool gemm_ln_supported(int D);
 int launch_gemm_ln(const GemmLnDesc& d, int num_sms, cudaStream_t stream);
 
-// The same 256 x 384 full-row CTA-pair tile as a plain GEMM: out[M, 384] (bf16) = A[M, K] W[384, K]^T (+ bias)
-struct GemmWideDesc {
-    const void* A;      // bf16 [M, K], row pitch lda
-    const void* W;      // bf16 [N, K], row pitch ldb
-    const float* bias;  // [N] or nullptr
-    void* out;          // bf16 [M, N], row pitch ldo
-    int M, N, K, lda, ldb, ldo;
-};
-int launch_gemm_wide(const GemmWideDesc& d, int num_sms, cudaStream_t stream);
-
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);  // kernels launched through this library (svit_launch_count)
 

@@ -12,7 +12,9 @@
 // per CTA -- SiT-small; other widths keep the separate kernels): an N = 256 and an N = 128 MMA per 16-wide K step.  Besides making the fusion possible the
 // wide tile reads A once instead of once per 192-column tile -- these GEMMs are bound by the L2 -> SM operand feed.
 // One accumulator stage (2 x 384 columns would not fit TMEM): the MMAs of the next tile wait for the epilogue, the
-// operand ring keeps prefetching meanwhile.  (Starting every other cluster half a tile period late, so that the HBM-bound
+// operand ring keeps prefetching meanwhile.  (The same tile as a plain bf16-store GEMM for the 384-wide input-gradient
+// GEMMs was measured and is no faster than gemm_tn's double-buffered 256 x 192 tiles: d fc1 90.4 vs 88.1 us, d qkv 71.6 vs
+// 68.5 us -- what the wide tile saves in operand traffic it loses to the exposed epilogue and to 4.34 -> 5 waves.  Starting every other cluster half a tile period late, so that the HBM-bound
 // epilogues of one half of the chip run under the MMA phases of the other, was measured and does not help: 85.7 -> 87.9 us
 // for the out-projection shape, 139.7 -> 147.4 us for fc2 at M = 82176.)
 //
@@ -87,12 +89,7 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
-// LN = true : the fused residual Linear + LayerNorm described above.
-// LN = false: the same 256 x 384 full-row tile as a plain bf16 store, out = A W^T (+ bias) -- for the input-gradient GEMMs
-//             of the backward pass whose output is 384 wide (d fc1, d qkv, d to_out): A is read once instead of once per
-//             192-column tile, 41 KB of operands per CTA and K block feed 128 x 384 x 64 MACs (77 MAC/B against 55 for the
-//             256 x 192 tile of gemm_tn), which is what these TMA-feed-bound GEMMs need.
-template <int BN, bool LN>
+template <int BN>
 __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_constant__ LnArgs args) {
     using Cfg = LnCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -126,8 +123,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmA);
         tma_prefetch_desc(&args.tmB);
-        if (LN) tma_prefetch_desc(&args.tmX);
-        if (LN) tma_prefetch_desc(&args.tmAux);
+        tma_prefetch_desc(&args.tmX);
+        tma_prefetch_desc(&args.tmAux);
         tma_prefetch_desc(&args.tmAn);
         for (int i = 0; i < L_STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
@@ -143,10 +140,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
     }
     for (int i = threadIdx.x; i < BN; i += L_THREADS) {
         sBias[i] = args.bias != nullptr ? args.bias[i] : 0.0f;
-        if (LN) {
-            sGamma[i] = args.gamma[i];
-            sBeta[i] = args.beta[i];
-        }
+        sGamma[i] = args.gamma[i];
+        sBeta[i] = args.beta[i];
     }
     if (warp == 3) {
         tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
@@ -225,7 +220,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
         // ===================== residual loader =====================
         // Per epilogue warp and tile: U1 pass-1 jobs (residual box in, x out, in place) and U3 pass-3 jobs (bf16 out only);
         // job n of a warp uses box n % NBUF, and JOBS % NBUF == 0, so the pattern is the same for every tile.
-        if (LN && elect_one()) {
+        if (elect_one()) {
             uint32_t loads = 0;  // residual loads issued per warp so far (the same for all warps)
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = tile * 2 * LBM + row_off;
@@ -293,40 +288,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
             const int grow = m0 + lane;
             mbar_wait(tfull_bar, it & 1);
             tc_fence_after();
-            if constexpr (!LN) {
-                // ---------------- plain store: acc (+ bias) -> bf16 ----------------
-#pragma unroll 1
-                for (int u = 0; u < Cfg::U3; ++u) {
-                    const int slot = u % L_NBUF;  // U3 == NBUF: the same box for the same unit in every tile
-                    uint8_t* orow = wbuf + slot * L_BOX + lane * 128;
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(t_row + u * 64 + hh * 32, r);
-                        tmem_ld_wait();
-                        if (u == Cfg::U3 - 1 && hh == 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(tempty_bar, 0);
-                        }
-                        const float* bs = sBias + cbase + u * 64 + hh * 32;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint4 o;
-                            o.x = pack_bf16(__uint_as_float(r[c * 8 + 0]) + bs[c * 8 + 0], __uint_as_float(r[c * 8 + 1]) + bs[c * 8 + 1]);
-                            o.y = pack_bf16(__uint_as_float(r[c * 8 + 2]) + bs[c * 8 + 2], __uint_as_float(r[c * 8 + 3]) + bs[c * 8 + 3]);
-                            o.z = pack_bf16(__uint_as_float(r[c * 8 + 4]) + bs[c * 8 + 4], __uint_as_float(r[c * 8 + 5]) + bs[c * 8 + 5]);
-                            o.w = pack_bf16(__uint_as_float(r[c * 8 + 6]) + bs[c * 8 + 6], __uint_as_float(r[c * 8 + 7]) + bs[c * 8 + 7]);
-                            *reinterpret_cast<uint4*>(orow + (((hh * 4 + c) ^ sw) << 4)) = o;
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&args.tmAn, wbuf + slot * L_BOX, cbase + u * 64, m0);
-                    job_done(slot, false);
-                }
-                continue;
-            }
             // ---------------- pass 1: x = acc + bias + residual ----------------
             float s = 0.0f;
 #pragma unroll 1
@@ -432,10 +393,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
     }
 }
 
-template <int BN, bool LN>
+template <int BN>
 int launch_ln_inst(const LnArgs& a, int num_sms, cudaStream_t stream) {
     using Cfg = LnCfg<BN>;
-    auto kfn = gemm_ln_kernel<BN, LN>;
+    auto kfn = gemm_ln_kernel<BN>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -503,32 +464,7 @@ int launch_gemm_ln(const GemmLnDesc& d, int num_sms, cudaStream_t stream) {
     a.M = d.M;
     a.K = d.K;
     a.eps = d.eps;
-    return launch_ln_inst<384, true>(a, num_sms, stream);
-}
-
-int launch_gemm_wide(const GemmWideDesc& d, int num_sms, cudaStream_t stream) {
-    if (!gemm_ln_supported(d.N)) {
-        set_error("gemm_wide: the full-row tile is built for N = 384 (got %d)", d.N);
-        return -4;
-    }
-    if (d.M <= 0 || d.K <= 0 || (d.lda % 8) || (d.ldb % 8) || (d.ldo % 8)) {
-        set_error("gemm_wide: bad problem M=%d K=%d lda=%d ldb=%d ldo=%d", d.M, d.K, d.lda, d.ldb, d.ldo);
-        return -1;
-    }
-    LnArgs a;
-    memset(&a, 0, sizeof(a));
-    int rc = 0;
-    rc |= make_tmap_2d(&a.tmA, d.A, TmapDtype::BF16, d.K, d.M, (uint64_t)d.lda * 2, LBK, LBM);
-    rc |= make_tmap_2d(&a.tmB, d.W, TmapDtype::BF16, d.K, d.N, (uint64_t)d.ldb * 2, LBK, 32);
-    rc |= make_tmap_2d(&a.tmAn, d.out, TmapDtype::BF16, d.N, d.M, (uint64_t)d.ldo * 2, 64, 32);
-    if (rc != 0) {
-        set_error("gemm_wide: tensor map creation failed: %s", tmap_last_error());
-        return -3;
-    }
-    a.bias = d.bias;
-    a.M = d.M;
-    a.K = d.K;
-    return launch_ln_inst<384, false>(a, num_sms, stream);
+    return launch_ln_inst<384>(a, num_sms, stream);
 }
 
 }  // namespace svit

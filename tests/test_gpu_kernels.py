@@ -394,26 +394,3 @@ def test_gemm_ln_residual_linear_plus_layernorm(env, M, K):
     check(lib.svit_layernorm_fwd(ptr(x2), ptr(gamma), ptr(beta), ptr(a2), ptr(m2), ptr(r2), M, D, 1e-5, stream()), "ln")
     torch.cuda.synchronize()
     assert rel_l2(x_out, x2) < 1e-6 and rel_l2(a_out.float(), a2.float()) < 2e-3
-
-
-@pytest.mark.parametrize("M,K,bias", [(845, 1536, False), (5, 384, True), (20544, 1152, False), (82176, 1536, False)])
-def test_gemm_wide_full_row_store(env, M, K, bias):
-    """svit_gemm_wide: out[M, 384] = A W^T (+ bias) in bf16 on the 256 x 384 CTA-pair tile (the backward pass's dgrad GEMMs)
-    against fp32 torch on the same bf16 operands and against gemm_tn."""
-    dev, lib = env["dev"], env["lib"]
-    N = 384
-    torch.manual_seed(M + K)
-    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
-    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
-    b = torch.randn(N, device=dev) * 0.1 if bias else None
-    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
-    check(lib.svit_gemm_wide(ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, K, K, N, env["sms"], stream()), "gemm_wide")
-    torch.cuda.synchronize()
-    ref = A.float() @ W.float().t() + (b if bias else 0.0)
-    assert torch.isfinite(out.float()).all()
-    assert rel_l2(out.float(), ref) < 4e-3
-    o2 = torch.empty_like(out)
-    check(lib.svit_gemm_tn(ptr(A), ptr(W), ptr(o2), vp(0), vp(0), ptr(b), vp(0), 1, M, N, K, K, K, N, 0, 0, env["sms"], stream()),
-          "gemm_tn")
-    torch.cuda.synchronize()
-    assert rel_l2(out.float(), o2.float()) < 1e-3
