@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(384, 2) attn_fwd_kernel(const __grid_constant_
     const int nqb = (T + 127) / 128;                  // query blocks
     const int nch = (tk + FWD_CHUNK - 1) / FWD_CHUNK;  // key chunks (<= 4); chunk c lives in buffer c & 1, group c & 1
 
+    griddep_launch();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmQ);
         tma_prefetch_desc(&args.tmKV);
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(384, 2) attn_fwd_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
 
     if (warp == 8) {
         // ============================ control: TMA + MMA issue ============================
@@ -531,6 +533,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     const int total = nqb * nkb;
     const int b = blockIdx.x / H, h = blockIdx.x % H;
 
+    griddep_launch();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmQ);
         tma_prefetch_desc(&args.tmDO);
@@ -565,6 +568,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
     // The issuing warps need few registers, the compute warps many: move them (per warp group of 4 warps).  Each
     // setmaxnreg sits at the top of the role branch it governs: ptxas allocates a region by the setmaxnreg that dominates
     // it (after a common if / else it may fall back to the smaller limit).
@@ -993,7 +997,7 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     a.T = d.T;
     a.scale = d.scale;
     a.scale_log2e = d.scale * 1.4426950408889634f;
-    attn_fwd_kernel<<<d.B * d.H, FWD_THREADS, fwd_smem_bytes(tk), stream>>>(a);
+    launch_pdl(attn_fwd_kernel, dim3(d.B * d.H), dim3(FWD_THREADS), fwd_smem_bytes(tk), stream, a);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -1039,7 +1043,7 @@ int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
         static const char* dbg = getenv("SVIT_ATTN_DEBUG");
         a.debug = dbg ? atoi(dbg) : 0;
     }
-    attn_bwd_kernel<<<d.B * d.H, BK_THREADS, BK_SMEM, stream>>>(a);
+    launch_pdl(attn_bwd_kernel, dim3(d.B * d.H), dim3(BK_THREADS), BK_SMEM, stream, a);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -3,7 +3,8 @@
 
 #include <cuda_bf16.h>
 
-#include "gemm.cuh"  // set_error
+#include "gemm.cuh"  // set_error, launch_pdl
+#include "ptx.cuh"   // griddep_launch / griddep_wait
 
 namespace svit {
 
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
     const float inv_d = 1.0f / D;
+    griddep_launch();
+    griddep_wait();
     float4 g[NVEC], bb[NVEC];
 #pragma unroll
     for (int k = 0; k < NVEC; ++k) {
@@ -284,8 +287,8 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a
     int blocks = (M + wpb - 1) / wpb;
     if (blocks > 148 * 8) blocks = 148 * 8;
     const int nv = (D + 127) / 128;
-    SVIT_LN_DISPATCH(nv, (ln_fwd_kernel<NV><<<blocks, wpb * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(a_bf16),
-                                                                         mean, rstd, M, D, eps)));
+    SVIT_LN_DISPATCH(nv, (launch_pdl(ln_fwd_kernel<NV>, dim3(blocks), dim3(wpb * 32), 0, st, x, gamma, beta,
+                                     reinterpret_cast<__nv_bfloat16*>(a_bf16), mean, rstd, M, D, eps)));
     SVIT_CHECK_LAUNCH("ln_fwd");
     return 0;
 }
@@ -305,8 +308,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
     const float inv_d = 1.0f / D;
+    griddep_launch();
     for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.0f;
     __syncthreads();
+    griddep_wait();
     float4 acc_g[NVEC], acc_b[NVEC], acc_c[NVEC], gm[NVEC];
 #pragma unroll
     for (int k = 0; k < NVEC; ++k) {
@@ -409,9 +414,9 @@ int launch_ln_bwd(const void* da_bf16, const float* x, const float* mean, const 
     int blocks = (M + wpb - 1) / wpb;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const int nv = (D + 127) / 128;
-    SVIT_LN_DISPATCH(nv, (ln_bwd_kernel<NV><<<blocks, wpb * 32, 3 * D * sizeof(float), st>>>(
-                             reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
-                             reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D)));
+    SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV>, dim3(blocks), dim3(wpb * 32), 3 * D * sizeof(float), st,
+                                     reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
+                                     reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D)));
     SVIT_CHECK_LAUNCH("ln_bwd");
     return 0;
 }

@@ -26,6 +26,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_last_error; }
 // incremented from the forward and the autograd (backward) host threads
+bool pdl_enabled() {
+    static const bool on = !(getenv("SVIT_NO_PDL") != nullptr && atoi(getenv("SVIT_NO_PDL")) != 0);
+    return on;
+}
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__((EpiTraits<MODE, ARES>::THREADS), 1) gemm_tn_k
     const int tile_stride = ARES ? 1 : num_clusters;
     const int row_off = static_cast<int>(cta_rank) * BM;
 
+    griddep_launch();  // the next kernel of the stream may set itself up under this one (ptx.cuh)
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmA);
         tma_prefetch_desc(&args.tmB);
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__((EpiTraits<MODE, ARES>::THREADS), 1) gemm_tn_k
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // everything above overlapped the previous kernel; its results are visible from here on
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -664,6 +670,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
     const int kb_end = min(total_kb, kb_begin + args.kb_per_split);
     const int num_kb = kb_end - kb_begin;
 
+    griddep_launch();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmP);
         tma_prefetch_desc(&args.tmQ);
@@ -685,6 +692,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
 
     if (num_kb > 0) {
         if (warp == 0) {
@@ -815,13 +823,13 @@ static int launch_tn_inst(const TnArgs& a, int num_sms, cudaStream_t stream) {
     cfg.blockDim = dim3(EpiTraits<MODE, ARES>::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_attr(attr, 1);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, a);
     if (e != cudaSuccess) {
         set_error("gemm_tn launch failed: %s", cudaGetErrorString(e));
@@ -967,13 +975,13 @@ int launch_gemm_wgrad(const GemmWgradDesc& d, int num_sms, cudaStream_t stream) 
     cfg.blockDim = dim3(WG_THREADS);
     cfg.dynamicSmemBytes = WG_SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_attr(attr, 1);
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel, a);
     if (e != cudaSuccess) {
         set_error("gemm_wgrad launch failed: %s", cudaGetErrorString(e));

@@ -73,6 +73,29 @@ bool gemm_ln_supported(int D);
 int launch_gemm_ln(const GemmLnDesc& d, int num_sms, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
+
+// Programmatic dependent launch (ptx.cuh: griddep_launch / griddep_wait): the per-layer kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that the set-up of kernel n + 1 (barriers, TMEM, descriptors) runs
+// under the tail of kernel n.  SVIT_NO_PDL=1 turns the attribute off (A/B timing); the instructions are then no-ops.
+bool pdl_enabled();
+inline int pdl_attr(cudaLaunchAttribute* attr, int n) {  // appends the attribute, returns the new attribute count
+    if (!pdl_enabled()) return n;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    return n + 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr(attr, 0);
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 void count_launch(int n = 1);  // kernels launched through this library (svit_launch_count)
 
 }  // namespace svit

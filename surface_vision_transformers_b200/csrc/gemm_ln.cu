@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
     const int num_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
     const int row_off = static_cast<int>(cta_rank) * LBM;
 
+    griddep_launch();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&args.tmA);
         tma_prefetch_desc(&args.tmB);
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_ln_kernel(const __grid_cons
         }
         fence_mbar_init();
     }
+    griddep_wait();  // before the first global read (the parameters are written by the optimiser kernels)
     for (int i = threadIdx.x; i < BN; i += L_THREADS) {
         sBias[i] = args.bias != nullptr ? args.bias[i] : 0.0f;
         sGamma[i] = args.gamma[i];
@@ -415,13 +417,13 @@ int launch_ln_inst(const LnArgs& a, int num_sms, cudaStream_t stream) {
     cfg.blockDim = dim3(L_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_attr(attr, 1);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, a);
     if (e != cudaSuccess) {
         set_error("gemm_ln launch failed: %s", cudaGetErrorString(e));

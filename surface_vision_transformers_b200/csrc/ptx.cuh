@@ -29,6 +29,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running: griddep_launch() (top of every hot kernel) lets the NEXT kernel's CTAs be scheduled as soon as every CTA
+// of this grid has started, griddep_wait() blocks until all earlier grids have completed and their writes are visible.
+// Everything before the wait (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail; nothing
+// before it may touch global memory that an earlier kernel of the step writes.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

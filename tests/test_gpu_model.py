@@ -493,12 +493,26 @@ def test_adamw_step_bookkeeping_is_stream_ordered_and_restorable():
     """The AdamW step counters / bias corrections live on the device: (a) a host that enqueues many steps without ever
     synchronising gets the same parameters as one that synchronises after every step (staging them through a pinned
     buffer did not guarantee that: the host could rewrite it before the copy ran); (b) optimizer.state_dict() ->
-    load_state_dict() into a fresh optimizer continues the run (moments, step counts, device table)."""
+    load_state_dict() into a fresh optimizer continues the run (moments, step counts, device table).
+
+    The strict comparison runs in fp32 check mode.  On the bf16 path two runs of the SAME program end either 5e-9 or 3e-5
+    apart (scripts/probe_drift.py, probe_drift2.py; gpurun_out/r2l_drift*.log): the fp32 atomics of the weight-gradient
+    kernels make step-1 gradients differ by 5e-8, AdamW turns that into last-bit differences of a few parameters, and one
+    of them moves an activation of step 2 across a bf16 rounding boundary (forward output 7e-5, gradients 5e-5 apart).
+    Replaying step 2 from bit-identical parameters is deterministic (12 of 12), so this is rounding chaos, not a missed
+    hand-off; a wrong bias correction on one of the 8 steps would show as >= 5e-3, which the loose bound still catches."""
     cfg = dict(dim=128, depth=2, heads=2, mlp_dim=256, num_patches=20, num_vertices=15)
     torch.manual_seed(21)
     base = svit.SiT(**cfg).to(DEV)
     xs = [torch.randn(8, 4, 20, 15, device=DEV) for _ in range(8)]
     ys = [torch.rand(8, device=DEV) * 19 + 26 for _ in range(8)]
+
+    def fresh(check, state=None):
+        m = svit.SiT(**cfg)
+        m.load_state_dict(base.state_dict() if state is None else state)
+        m.to(DEV)
+        m.set_check_mode(check)
+        return m, svit.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
 
     def run(model, opt, lo, hi, sync):
         for k in range(lo, hi):
@@ -508,34 +522,29 @@ def test_adamw_step_bookkeeping_is_stream_ordered_and_restorable():
             if sync:
                 torch.cuda.synchronize()
 
-    models = []
-    for sync in (False, True):
-        m = svit.SiT(**cfg)
-        m.load_state_dict(base.state_dict())
-        m.to(DEV)
-        o = svit.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
-        run(m, o, 0, 8, sync)
-        models.append((m, o))
-    torch.cuda.synchronize()
-    # (at this learning rate two synchronised runs agree to 4e-9 -- fp32 atomics order; at 1e-2 the run is chaotic enough
-    # to amplify that to 1e-4, which says nothing about the optimizer)
-    drift = _param_rel(models[0][0], models[1][0])
-    print(f"un-synchronised vs synchronised host after 8 AdamW steps: parameter rel-L2 {drift:.2e}")
-    assert drift < 1e-6, drift
-    assert float(models[0][1].state[models[0][0].cls_token]["step"]) == 8.0
-    # (b) resume from a checkpoint taken after 4 steps
-    m1 = svit.SiT(**cfg); m1.load_state_dict(base.state_dict()); m1.to(DEV)
-    o1 = svit.FusedAdamW(m1.parameters(), lr=1e-3, weight_decay=0.0)
-    run(m1, o1, 0, 4, True)
-    ck_m = {k: v.clone() for k, v in m1.state_dict().items()}
-    ck_o = copy.deepcopy(o1.state_dict())
-    m2 = svit.SiT(**cfg); m2.load_state_dict(ck_m); m2.to(DEV)
-    o2 = svit.FusedAdamW(m2.parameters(), lr=1e-3, weight_decay=0.0)
-    o2.load_state_dict(ck_o)
-    run(m2, o2, 4, 8, True)
-    torch.cuda.synchronize()
-    assert _param_rel(m2, models[1][0]) < 1e-6
-    assert float(o2.state[m2.cls_token]["step"]) == 8.0
+    for check, bound in ((True, 1e-6), (False, 1e-3)):
+        models = []
+        for sync in (False, True):
+            m, o = fresh(check)
+            run(m, o, 0, 8, sync)
+            models.append((m, o))
+        torch.cuda.synchronize()
+        drift = _param_rel(models[0][0], models[1][0])
+        print(f"un-synchronised vs synchronised host after 8 AdamW steps ({'fp32 check mode' if check else 'bf16 path'}): "
+              f"parameter rel-L2 {drift:.2e}")
+        assert drift < bound, drift
+        assert float(models[0][1].state[models[0][0].cls_token]["step"]) == 8.0
+        # (b) resume from a checkpoint taken after 4 steps
+        m1, o1 = fresh(check)
+        run(m1, o1, 0, 4, True)
+        ck_m = {k: v.clone() for k, v in m1.state_dict().items()}
+        ck_o = copy.deepcopy(o1.state_dict())
+        m2, o2 = fresh(check, ck_m)
+        o2.load_state_dict(ck_o)
+        run(m2, o2, 4, 8, True)
+        torch.cuda.synchronize()
+        assert _param_rel(m2, models[1][0]) < bound
+        assert float(o2.state[m2.cls_token]["step"]) == 8.0
 
 
 def test_cuda_graph_capture_of_inference_and_training_step():
