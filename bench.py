@@ -55,6 +55,21 @@ DEFAULT_WORKLOAD = "sit_small_ico2_scan_age_train"
 NCU_SUMMARY = "r02_ncu_top_summary.json"
 
 
+def executed_gflop(wl):
+    """GFLOP per sample the engine actually owes the result.  SURVEY 8(d)'s figure (wl["gflop_per_sample"]) counts every
+    token row of every block; under cls pooling (models/sit.py:78, all SiT workloads here) the last block's attention,
+    to_out and FeedForward are only needed -- and only computed, engine.cu cls_last -- for token 0, so the T - 1 other
+    rows of that block are subtracted: forward 4 T 64 H + 2 I D + 4 D mlp flop per row, x 3.5 / 3 / 3 in training
+    (attention backward is 2.5 x its forward, a Linear's backward 2 x).  MPP decodes every token: nothing is dropped."""
+    m, kind = wl["model"], wl["kind"]
+    if kind == "mpp" or os.environ.get("SVIT_FULL_LAST_LAYER", "0") not in ("", "0"):
+        return wl["gflop_per_sample"]
+    T, D, I, mlp = m["num_patches"] + 1, m["dim"], m["heads"] * m["dim_head"], m["mlp_dim"]
+    attn, lin = 4.0 * T * 64 * m["heads"], 2.0 * I * D + 4.0 * D * mlp
+    dead = (T - 1) * ((3.5 * attn + 3.0 * lin) if kind == "train" else (attn + lin))
+    return wl["gflop_per_sample"] - dead / 1e9
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -244,14 +259,15 @@ def run_sweep(args):
         ms = e0.elapsed_time(e1) / args.steps
         clocks = sampler.stop()
         value = B / (ms * 1e-3)
-        tf = value * wl["gflop_per_sample"] / 1e3
+        tf = value * executed_gflop(wl) / 1e3
         rec = dict(metric="SiT train samples/sec" if kind != "infer" else "SiT inference samples/sec", value=value,
                    unit="samples/s", n_gpus=1, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, dtype="bf16",
                    data="synthetic", config=dict(workload=wl_name, batch_per_gpu=B, **m), clocks=clocks,
                    gpu_launches=int(lib.svit_launch_count() - l0),
                    roofline=dict(bound="tensor", scope="whole step", achieved=tf, unit="TFLOP/s",
                                  peak=peaks["tflops_sustained"], frac=tf / peaks["tflops_sustained"],
-                                 gflop_per_sample=wl["gflop_per_sample"], peak_source=peaks["source"] + " (sustained)"))
+                                 gflop_per_sample=executed_gflop(wl), gflop_per_sample_all_rows=wl["gflop_per_sample"],
+                                 peak_source=peaks["source"] + " (sustained)"))
         records.append(rec)
         print(json.dumps(rec), flush=True)
         del model, runner, opt, x, y
@@ -300,13 +316,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's kernels on a high-priority stream: at a communication window (ddp.py) its few CTAs are placed before the
+        # pending CTAs of the attention backward they share the chip with (SVIT_NCCL_HIGH_PRIO=0 for A/B)
+        opts = None
+        if os.environ.get("SVIT_NCCL_HIGH_PRIO", "1") != "0":
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     lib = _lib.load()
     peaks = load_peaks()
 
     m = wl["model"]
     kind = wl["kind"]
     B = args.batch
+    cls_only_last = executed_gflop(wl) != wl["gflop_per_sample"]
     torch.manual_seed(0)
     model = svit.SiT(dim=m["dim"], depth=m["depth"], heads=m["heads"], mlp_dim=m["mlp_dim"], num_patches=m["num_patches"],
                      num_classes=m["num_classes"], num_channels=m["num_channels"], num_vertices=m["num_vertices"],
@@ -438,7 +460,7 @@ def main():
         k_ms = e0.elapsed_time(e1) / n_it
         flops = 2.0 * M * H4 * D
         ach = flops / (k_ms * 1e-3) / 1e12
-        step_tf = value / world * wl["gflop_per_sample"] / 1e3
+        step_tf = value / world * executed_gflop(wl) / 1e3
         # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/), same shape only
         traffic = None
         try:
@@ -506,12 +528,17 @@ def main():
                     "dram__bytes_write.sum, one ncu --set full launch)" if a_traffic else None,
                     algorithmic_bytes=a_bytes, peak_source=peaks["source"] + " (burst: kernel timed alone)",
                     us_per_launch=a_ms * 1e3, flops_per_launch=a_flops,
-                    share_of_step=a_ms * m["depth"] / ms_step,
+                    share_of_step=a_ms * (m["depth"] - (1 if cls_only_last else 0)) / ms_step,
                     note="fraction of the dense bf16 tensor peak at the algorithmic flop count; T=%d pads to 128x96 tiles "
                          "(executed MMA work is 1.4x the algorithmic count at T=321) and the kernel is bound by the latency "
                          "chain of its compute warps through one P tile per step, not by the tensor pipe (DESIGN.md 3, 3b)" % T,
                     step_achieved_tflops=step_tf, step_frac_of_sustained=step_tf / peaks["tflops_sustained"],
-                    step_frac_of_nominal_2250=step_tf / 2250.0)
+                    step_frac_of_nominal_2250=step_tf / 2250.0,
+                    step_gflop_per_sample=executed_gflop(wl), step_gflop_per_sample_all_rows=wl["gflop_per_sample"],
+                    step_flop_note="whole-step TFLOP/s counts the flops the result needs: with cls pooling the last "
+                                   "block's attention / to_out / FeedForward run for token 0 only (exact, engine.cu "
+                                   "cls_last), so its other T-1 rows are not counted; SURVEY 8(d)'s all-rows figure is "
+                                   "step_gflop_per_sample_all_rows" if cls_only_last else None)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -527,7 +554,8 @@ def main():
                     config=dict(workload=wl_name, batch_per_gpu=B, global_batch=B * world,
                                 parallelism=f"dp{world}" if world > 1 else "single", optimizer="FusedAdamW",
                                 l2_policy="inputs and activations larger than L2 (batch %.0f MB, activations > 10 GB)" % (x_dev.numel() * 4 / 1e6),
-                                **m),
+                                last_block="token 0 only (cls pooling: the head reads x[:, 0]; same outputs and gradients)"
+                                if cls_only_last else "all rows", **m),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                             ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(launches), roofline=roof, roofline_gemm=roof_gemm if rank == 0 else None, cpu_baseline=cpu)

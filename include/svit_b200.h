@@ -104,7 +104,13 @@ int svit_forward(svit_engine* e, const float* params, const void* shadow, void* 
  * same workspace. */
 /* progress (may be NULL) is called on the host while the work is being enqueued: stage = depth after the head
  * gradients are final, stage = l after those of encoder layer l, stage = -1 after patch-embedding / pos / cls.
- * A data-parallel caller launches the all-reduce of that flat-buffer range from it (overlap with backward). */
+ * A data-parallel caller launches the all-reduce of that flat-buffer range from it (overlap with backward).
+ * stage = SVIT_STAGE_WINDOW + l announces a communication window: the kernel enqueued next (the attention backward of
+ * layer l, ~270 us at the benchmark shape) is not a persistent kernel -- its CTAs are handed to the SMs one by one, so a
+ * collective launched now shares the chip with it gracefully, whereas under a persistent GEMM (static tile schedule over
+ * all SMs) it stalls the CTAs whose SMs it holds.  The gradients that are final at that point are those of the stages
+ * reported so far (layers > l and the head). */
+#define SVIT_STAGE_WINDOW 1000
 typedef void (*svit_progress_fn)(int stage, void* user);
 int svit_backward(svit_engine* e, const float* params, const void* shadow, void* workspace, int batch,
                   const float* dout, float* grads, svit_progress_fn progress, void* user, void* stream);

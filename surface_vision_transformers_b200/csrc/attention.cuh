@@ -30,4 +30,23 @@ struct AttnBwdDesc {
 };
 int launch_attn_bwd(const AttnBwdDesc& d, cudaStream_t stream);
 
+// The same attention for the query row of token 0 only (attention_cls.cu): the last encoder block under cls pooling.
+struct AttnClsDesc {
+    const void* qkv;  // bf16 [B, T, 3*H*64]
+    void* out;        // bf16 [B, H*64]     attention output of token 0, head-merged
+    float* prob;      // fp32 [B, H, T]     softmax row of token 0 (saved for backward)
+    int B, H, T;
+    float scale;
+};
+int launch_attn_cls_fwd(const AttnClsDesc& d, cudaStream_t stream);
+struct AttnClsBwdDesc {
+    const void* qkv;    // bf16 [B, T, 3*H*64]
+    const float* prob;  // fp32 [B, H, T]
+    const void* dout;   // bf16 [B, H*64]
+    void* dqkv;         // bf16 [B, T, 3*H*64]: dk, dv of every key, dq of token 0, zeros in the other dq rows
+    int B, H, T;
+    float scale;
+};
+int launch_attn_cls_bwd(const AttnClsBwdDesc& d, cudaStream_t stream);
+
 }  // namespace svit

@@ -40,6 +40,7 @@ struct svit_engine {
     float drop_p, drop_emb_p;
     unsigned long long drop_seed, drop_offset;
     int no_fuse_ln;  // SVIT_NO_FUSE_LN=1: keep the stand-alone LayerNorm kernels (A/B timing)
+    int full_last;   // SVIT_FULL_LAST_LAYER=1: compute every row of the last block even under cls pooling (A/B timing)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -211,10 +212,40 @@ static int check_ws(const svit_engine* e, int B, int training, int mpp, int with
 }
 
 // ---------------------------------------------------------------------------------------------
+// cls pooling: the last block on B rows
+// ---------------------------------------------------------------------------------------------
+// With pool = 'cls' the head reads token 0 of the encoder output only (models/sit.py:78), and after the last block's key /
+// value projection everything is row-wise.  The other T - 1 query rows of the LAST block reach neither the prediction nor
+// any gradient (their gradient is exactly zero in the reference as well), so svit_forward / svit_backward run that block's
+// attention for the cls query alone (attention_cls.cu) and its to_out / LayerNorm / FeedForward on B rows.  The compact
+// [B, *] operands live at the start of the block's own (otherwise unused) activation buffers.  Not with dropout (the masks
+// are indexed by the position in the full tensors), not for the encoder-only / MPP entry points (they return every token).
+static inline bool cls_last(const svit_engine* e) {
+    return !e->cfg.pool_mean && !e->full_last && e->drop_p == 0.0f && e->T >= 4 && e->depth >= 1;
+}
+struct ClsWs {
+    float *xin, *xmid, *xout, *g, *mean2, *rstd2, *prob;
+    bf16 *a2, *g16, *O, *u, *h;
+};
+static inline ClsWs cls_views(const svit_engine* e, const LayerWs& L, int B) {
+    const size_t BD = static_cast<size_t>(B) * e->D;
+    return ClsWs{L.xmid, L.xmid + BD, L.xout, L.xmid + 2 * BD, L.mean2, L.rstd2, L.lse, L.a2, L.a2 + BD, L.O, L.u, L.h};
+}
+// rows b * T of a [B * T, D] fp32 matrix <-> a compact [B, D] matrix
+static int copy_cls_rows(float* dst, size_t dst_pitch, const float* src, size_t src_pitch, int B, int D, cudaStream_t st) {
+    if (cudaMemcpy2DAsync(dst, dst_pitch * sizeof(float), src, src_pitch * sizeof(float), D * sizeof(float), B,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("cls-row copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -12;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // encoder forward / backward over the workspace
 // ---------------------------------------------------------------------------------------------
 static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws& w, const float* x_in, cudaStream_t st,
-                       const float** x_final) {
+                       const float** x_final, bool cls = false) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
     const float scale = 0.125f;  // dim_head ** -0.5 with dim_head = 64
     const bool drop = e->drop_p > 0.0f;  // extra passes (dropout.cuh); the p = 0 launch sequence is unchanged
@@ -231,6 +262,33 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
         if (l == 0 || !fuse_ln) RET_IF(launch_ln_fwd(xin, pp(LN1_W), pp(LN1_B), L.a1, L.mean1, L.rstd1, M, D, 1e-5f, st));
         RET_IF(gemm(e, st, L.a1, D, shp(sh, e->sh_qkv) + static_cast<size_t>(l) * 3 * I * D, D, L.qkv, 3 * I, M, 3 * I, D,
                     EPI_STORE, 0));
+        if (cls && l == e->depth - 1) {
+            // ---- last block under cls pooling: token 0 only from here on (B rows, compact operands) ----
+            const ClsWs c = cls_views(e, L, w.B);
+            const int Mc = w.B;
+            AttnClsDesc cd{L.qkv, c.O, c.prob, w.B, e->H, e->T, scale};
+            RET_IF(launch_attn_cls_fwd(cd, st));
+            RET_IF(copy_cls_rows(c.xin, D, xin, static_cast<size_t>(e->T) * D, w.B, D, st));
+            if (fuse_ln) {
+                RET_IF(gemm_ln(e, st, c.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, pp(OUT_B), c.xin, c.xmid,
+                               pp(LN2_W), pp(LN2_B), c.a2, c.mean2, c.rstd2, Mc, I));
+            } else {
+                RET_IF(gemm(e, st, c.O, I, shp(sh, e->sh_o) + static_cast<size_t>(l) * D * I, I, c.xmid, D, Mc, D, I, EPI_RESID,
+                            1, pp(OUT_B), c.xin));
+                RET_IF(launch_ln_fwd(c.xmid, pp(LN2_W), pp(LN2_B), c.a2, c.mean2, c.rstd2, Mc, D, 1e-5f, st));
+            }
+            if (w.training) {
+                RET_IF(gemm(e, st, c.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, c.u, mlp, Mc, mlp, D,
+                            EPI_GELU_GRAD, 0, pp(FC1_B), nullptr, c.h));
+            } else {
+                RET_IF(gemm(e, st, c.a2, D, shp(sh, e->sh_w1) + static_cast<size_t>(l) * mlp * D, D, c.h, mlp, Mc, mlp, D,
+                            EPI_GELU_ONLY, 0, pp(FC1_B)));
+            }
+            RET_IF(gemm(e, st, c.h, mlp, shp(sh, e->sh_w2) + static_cast<size_t>(l) * D * mlp, mlp, c.xout, D, Mc, D, mlp,
+                        EPI_RESID, 1, pp(FC2_B), c.xmid));
+            xin = c.xout;  // [B, D]: the head pools it with T = 1
+            break;
+        }
         AttnDesc ad{L.qkv, L.O, L.lse, w.B, e->H, e->T, scale};
         RET_IF(launch_attn_fwd(ad, st));
         if (fuse_ln) {
@@ -274,7 +332,7 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
 // both points); the bias gradients of to_out / fc2 are then column sums of that masked copy, so they come from the
 // wgrad kernel's bias column instead of the LayerNorm-backward / head column sums (callers skip those too).
 static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws& w, const float* x_in, float* G,
-                       cudaStream_t st, svit_progress_fn progress = nullptr, void* user = nullptr) {
+                       cudaStream_t st, svit_progress_fn progress = nullptr, void* user = nullptr, bool cls = false) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
     const float scale = 0.125f;
     const bool drop = e->drop_p > 0.0f;
@@ -284,6 +342,37 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         const float* xin = (l == 0) ? x_in : w.L[l - 1].xout;
         auto pp = [&](int which) { return P + e->poff[pidx_layer(l, which)]; };
         auto gp = [&](int which) { return G + e->poff[pidx_layer(l, which)]; };
+        if (cls && l == e->depth - 1) {
+            // ---- last block under cls pooling: B rows; c.g / c.g16 hold dL/dx_final of token 0 (head backward) ----
+            const ClsWs c = cls_views(e, L, w.B);
+            const int Mc = w.B;
+            RET_IF(gemm(e, st, c.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, Mc, mlp, D,
+                        EPI_MUL, 0, nullptr, c.u));
+            RET_IF(wgrad(e, st, c.g16, D, c.h, mlp, gp(FC2_W), mlp, Mc, D, mlp));
+            RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, Mc, D, mlp,
+                        EPI_STORE, 0));
+            RET_IF(wgrad(e, st, w.du, mlp, c.a2, D, gp(FC1_W), D, Mc, mlp, D, gp(FC1_B)));
+            RET_IF(launch_ln_bwd(w.da, c.xmid, c.mean2, c.rstd2, pp(LN2_W), c.g, c.g, c.g16, gp(LN2_W), gp(LN2_B), gp(OUT_B), Mc,
+                                 D, st));
+            RET_IF(gemm(e, st, c.g16, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, Mc, I, D, EPI_STORE, 0));
+            RET_IF(wgrad(e, st, c.g16, D, c.O, I, gp(OUT_W), I, Mc, D, I));
+            if (progress != nullptr) progress(SVIT_STAGE_WINDOW + l, user);
+            AttnClsBwdDesc cb{L.qkv, c.prob, w.dO, w.dqkv, w.B, e->H, e->T, scale};
+            RET_IF(launch_attn_cls_bwd(cb, st));
+            RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D,
+                        3 * I, EPI_STORE, 0));
+            RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+            // the residual gradient entering LN1' is g_mid in the cls rows and zero elsewhere
+            if (cudaMemsetAsync(w.g, 0, nD * sizeof(float), st) != cudaSuccess) {
+                set_error("cls-row gradient clear failed");
+                return -12;
+            }
+            RET_IF(copy_cls_rows(w.g, static_cast<size_t>(e->T) * D, c.g, D, w.B, D, st));
+            float* cs0 = (l > 0) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
+            RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs0, M, D, st));
+            if (progress != nullptr) progress(l, user);
+            continue;
+        }
         // ---- FeedForward ----
         // du = (g W2) * gelu'(u)      (L.u holds gelu'(u), stored by the forward epilogue)
         const bf16* gb = w.g16;
@@ -310,6 +399,8 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
         RET_IF(wgrad(e, st, gb, D, L.O, I, gp(OUT_W), I, M, D, I, drop ? gp(OUT_B) : nullptr));
         AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, scale};
+        // communication window: the next kernel is long and hands SMs out CTA by CTA (svit_b200.h, SVIT_STAGE_WINDOW)
+        if (progress != nullptr) progress(SVIT_STAGE_WINDOW + l, user);
         RET_IF(launch_attn_bwd(bd, st));
         RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
                     EPI_STORE, 0));
@@ -486,6 +577,7 @@ static int ck_encoder_bwd(const svit_engine* e, const float* P, CkWs& w, const f
         RET_IF(ck::colsum(gs, gp(OUT_B), M, D, st));
         RET_IF(ck_dgrad(st, gs, pp(OUT_W), w.dO, M, D, I));
         RET_IF(ck_wgrad(st, gs, L.O, gp(OUT_W), M, D, I));
+        if (progress != nullptr) progress(SVIT_STAGE_WINDOW + l, user);  // same callback sequence as the tensor-core path
         RET_IF(ck::attn_bwd(L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, 0.125f, st));
         RET_IF(ck_dgrad(st, w.dqkv, pp(QKV_W), w.da, M, 3 * I, D));
         RET_IF(ck_wgrad(st, w.dqkv, L.a1, gp(QKV_W), M, 3 * I, D));
@@ -581,6 +673,7 @@ svit_engine* svit_create(const svit_config* cfg) {
     e->drop_p = e->drop_emb_p = 0.0f;
     e->drop_seed = e->drop_offset = 0;
     e->no_fuse_ln = getenv("SVIT_NO_FUSE_LN") != nullptr && atoi(getenv("SVIT_NO_FUSE_LN")) != 0;
+    e->full_last = getenv("SVIT_FULL_LAST_LAYER") != nullptr && atoi(getenv("SVIT_FULL_LAST_LAYER")) != 0;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int sms = 0;
@@ -719,9 +812,10 @@ int svit_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, s
     PackDesc pd{input, w.Apatch, B, e->C, e->N, e->V, e->Kp, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
     RET_IF(embed_fwd(e, sh, w, pd, st));
     const float* xf = nullptr;
-    RET_IF(encoder_fwd(e, P, sh, w, w.x0, st, &xf));
+    const bool cls = cls_last(e);  // then xf is the compact [B, D] encoder output of token 0
+    RET_IF(encoder_fwd(e, P, sh, w, w.x0, st, &xf, cls));
     return launch_head_fwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)],
-                           P + e->poff[pidx_head(e, 3)], out, B, e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st);
+                           P + e->poff[pidx_head(e, 3)], out, B, cls ? 1 : e->T, e->D, e->NC, e->cfg.pool_mean, 1e-5f, st);
 }
 
 int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, int B, const float* dout, float* G,
@@ -731,13 +825,15 @@ int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, 
     Ws w;
     RET_IF(check_ws(e, B, 1, 0, 1, ws_ptr, 0, &w));
     const float* xf = w.L[e->depth - 1].xout;
+    const bool cls = cls_last(e);  // xf, g and g16 are then the compact [B, D] token-0 tensors of the last block
+    const ClsWs c = cls_views(e, w.L[e->depth - 1], B);
     RET_IF(launch_head_bwd(xf, P + e->poff[pidx_head(e, 0)], P + e->poff[pidx_head(e, 1)], P + e->poff[pidx_head(e, 2)], dout,
-                           w.g, w.g16, G + e->poff[pidx_head(e, 0)], G + e->poff[pidx_head(e, 1)],
+                           cls ? c.g : w.g, cls ? c.g16 : w.g16, G + e->poff[pidx_head(e, 0)], G + e->poff[pidx_head(e, 1)],
                            G + e->poff[pidx_head(e, 2)], G + e->poff[pidx_head(e, 3)],
-                           e->drop_p > 0.0f ? nullptr : G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, e->T, e->D, e->NC,
-                           e->cfg.pool_mean, 1e-5f, st));
+                           e->drop_p > 0.0f ? nullptr : G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, cls ? 1 : e->T, e->D,
+                           e->NC, e->cfg.pool_mean, 1e-5f, st));
     if (progress != nullptr) progress(e->depth, user);
-    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user));
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, cls));
     RET_IF(embed_bwd(e, w, G, st));
     if (progress != nullptr) progress(-1, user);
     return 0;

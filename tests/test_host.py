@@ -210,6 +210,30 @@ for start, n in [(700, 300), (300, 400), (0, 300)]:      # reverse-layer order, 
 r.finish()
 expect = torch.arange(1000, dtype=torch.float32) * 1.5    # mean of 1x and 2x
 assert torch.allclose(G, expect), (G[:5], expect[:5])
+# DataParallel's three schedules, driven by the engine's callback sequence (head, then per layer: window, layer final; patch
+# embedding; "fully enqueued"): every element is averaged exactly once, and the windowed mode issues depth collectives
+import surface_vision_transformers_b200 as svit
+from surface_vision_transformers_b200.ddp import DataParallel, STAGE_WINDOW
+torch.manual_seed(0)
+sit = svit.SiT(dim=128, depth=3, heads=2, mlp_dim=128, num_patches=4, num_vertices=5)
+for mode, calls in (("window", 3), ("none", 1), ("range", 5)):
+    dp = DataParallel(sit, overlap=mode)
+    dp.min_window_numel = 1000
+    n = sit._flat.numel()
+    G = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    issued = []
+    orig = dp.reducer.reduce_range
+    dp.reducer.reduce_range = lambda G_, a, k: (issued.append((a, k)), orig(G_, a, k))
+    dp._on_stage(sit, sit.depth, G)
+    for l in range(sit.depth - 1, -1, -1):
+        dp._on_stage(sit, STAGE_WINDOW + l, G)
+        dp._on_stage(sit, l, G)
+    dp._on_stage(sit, -1, G)
+    dp._on_stage(sit, None, G)
+    assert torch.allclose(G, torch.arange(n, dtype=torch.float32) * 1.5), mode
+    assert len(issued) == calls and sum(k for _, k in issued) == n, (mode, issued)
+    if mode == "window":   # head + last layer first (at the window of layer depth-2), layer 0 + patch embedding last
+        assert issued[0][0] + issued[0][1] == n and issued[-1][0] == 0, issued
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
