@@ -188,6 +188,13 @@ int svit_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int T, f
 /* (rowsum(dout * out) is computed inside the kernel and dQ accumulates on chip: no scratch arguments) */
 int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H, int T,
                   float scale, void* stream);
+/* The same attention for the query row of token 0 only -- what the last block needs under `pool = 'cls'`
+ * (models/sit.py:78: the head reads x[:, 0]); svit_forward / svit_backward use it there and run the block's row-wise
+ * rest on B rows.  out [B, H*64] bf16, prob [B, H, T] fp32 (softmax row of token 0, kept for the backward);
+ * dout [B, H*64] bf16 -> dqkv [B, T, 3*H*64] bf16 (dk, dv of every key, dq of token 0, zeros in the other dq rows). */
+int svit_attn_cls_fwd(const void* qkv, void* out, float* prob, int B, int H, int T, float scale, void* stream);
+int svit_attn_cls_bwd(const void* qkv, const float* prob, const void* dout, void* dqkv, int B, int H, int T, float scale,
+                      void* stream);
 int svit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd,
                        int M, int D, float eps, void* stream);
 int svit_layernorm_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,

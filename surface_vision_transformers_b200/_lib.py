@@ -62,6 +62,8 @@ SIGNATURES = {
     "svit_gemm_wgrad": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),
     "svit_gemm_wgrad_bias": (ci, [vp, vp, vp, vp] + [ci] * 7 + [vp]),
     "svit_attn_fwd": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
+    "svit_attn_cls_fwd": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
+    "svit_attn_cls_bwd": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, vp]),
     "svit_attn_bwd": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, cf, vp]),
     "svit_layernorm_fwd": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, cf, vp]),
     "svit_layernorm_bwd": (ci, [vp] * 11 + [ci, ci, vp]),

@@ -1030,6 +1030,15 @@ int svit_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
     AttnBwdDesc d{qkv, out, dout, lse, dqkv, B, H, T, scale};
     return launch_attn_bwd(d, reinterpret_cast<cudaStream_t>(stream));
 }
+int svit_attn_cls_fwd(const void* qkv, void* out, float* prob, int B, int H, int T, float scale, void* stream) {
+    AttnClsDesc d{qkv, out, prob, B, H, T, scale};
+    return launch_attn_cls_fwd(d, reinterpret_cast<cudaStream_t>(stream));
+}
+int svit_attn_cls_bwd(const void* qkv, const float* prob, const void* dout, void* dqkv, int B, int H, int T, float scale,
+                      void* stream) {
+    AttnClsBwdDesc d{qkv, prob, dout, dqkv, B, H, T, scale};
+    return launch_attn_cls_bwd(d, reinterpret_cast<cudaStream_t>(stream));
+}
 int svit_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd, int M,
                        int D, float eps, void* stream) {
     return launch_ln_fwd(x, gamma, beta, a_bf16, mean, rstd, M, D, eps, reinterpret_cast<cudaStream_t>(stream));

@@ -166,6 +166,39 @@ def test_attention_fwd_bwd(env, B, H, T):
             assert rel_l2(got, want) < 2 * TOL
 
 
+@pytest.mark.parametrize("B,H,T", [(1, 1, 1), (2, 3, 21), (3, 6, 321), (2, 12, 321), (2, 2, 384), (1, 2, 257)])
+def test_attention_cls_row_fwd_bwd(env, B, H, T):
+    """svit_attn_cls_fwd / _bwd (the last block under cls pooling): attention of the query row of token 0 against every
+    key, and its backward -- dk, dv of all keys, dq of token 0, exact zeros in the other dq rows -- against fp32 torch on
+    the same bf16 inputs."""
+    dev, lib = env["dev"], env["lib"]
+    torch.manual_seed(B * 1000 + H * 10 + T)
+    inner = H * 64
+    scale = 64 ** -0.5
+    qkv = torch.randn(B, T, 3 * inner, device=dev).bfloat16()
+    out = torch.full((B, inner), float("nan"), device=dev, dtype=torch.bfloat16)
+    prob = torch.full((B, H, T), float("nan"), device=dev)
+    check(lib.svit_attn_cls_fwd(ptr(qkv), ptr(out), ptr(prob), B, H, T, scale, stream()), "attn_cls_fwd")
+    q, k, v = [t.reshape(B, T, H, 64).permute(0, 2, 1, 3).float().requires_grad_(True) for t in qkv.chunk(3, dim=-1)]
+    p_ref = (q[:, :, :1] @ k.transpose(-1, -2) * scale).softmax(-1)            # (B, H, 1, T)
+    ref = (p_ref @ v).permute(0, 2, 1, 3).reshape(B, inner)
+    torch.cuda.synchronize()
+    assert rel_l2(prob, p_ref.squeeze(2)) < 1e-4 and rel_l2(out, ref) < 4e-3
+    dout = torch.randn(B, inner, device=dev).bfloat16()
+    dqkv = torch.full((B, T, 3 * inner), float("nan"), device=dev, dtype=torch.bfloat16)
+    check(lib.svit_attn_cls_bwd(ptr(qkv), ptr(prob), ptr(dout), ptr(dqkv), B, H, T, scale, stream()), "attn_cls_bwd")
+    ref.backward(dout.float())
+    torch.cuda.synchronize()
+    dref = torch.cat([g.permute(0, 2, 1, 3).reshape(B, T, inner) for g in (q.grad, k.grad, v.grad)], dim=-1)
+    assert torch.isfinite(dqkv.float()).all()
+    assert (dqkv[:, 1:, :inner] == 0).all()                                    # rows that were never queries
+    if T > 1:
+        for i in range(3):
+            assert rel_l2(dqkv[..., i * inner:(i + 1) * inner].float(), dref[..., i * inner:(i + 1) * inner]) < 5e-3, i
+    else:
+        assert dqkv[..., :2 * inner].float().abs().max() < 1e-5 and rel_l2(dqkv[..., 2 * inner:].float(), dref[..., 2 * inner:]) < 5e-3
+
+
 @pytest.mark.parametrize("T", [2, 31, 33, 95, 96, 97, 112, 127, 129, 191, 192, 193, 255, 256, 257, 287, 288, 289, 320, 322, 383])
 def test_attention_boundary_lengths(env, T):
     """Every tile boundary of the fused kernels (96-key blocks x 32-column slabs and 128-query blocks in the backward,
