@@ -52,7 +52,7 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "sit_small_ico2_scan_age_train"
 # `ncu --set full` summary of the kernels of the current build (scripts/ncu_top.py + scripts/ncu_summary.py); re-captured
 # whenever a kernel changes -- roofline.traffic is read from it
-NCU_SUMMARY = "r02_ncu_top_summary.json"
+NCU_SUMMARY = "r02b_ncu_top_summary.json"
 
 
 def executed_gflop(wl):
