@@ -99,17 +99,34 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const __nv_bf
         pout[j] = p;
     }
     __syncthreads();
-    // o = sum_j p_j v_j: warp w takes keys j = w (mod 8), lane owns two of the 64 dims
+    // o = sum_j p_j v_j: a warp load covers four key rows (8 lanes x 16 bytes each); lane (g, c) owns dims [8 c, 8 c + 8)
+    // of the keys j = 4 (warp + 8 it) + g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int j = warp; j < T; j += CLS_THREADS / 32) {
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + j * pitch + 2 * inner) + lane);
-        const float p = sp[j];
-        a0 = fmaf(p, bf16_lo(v), a0);
-        a1 = fmaf(p, bf16_hi(v), a1);
+    const int g = lane >> 3, c = lane & 7;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+#pragma unroll 4
+    for (int jb = warp * 4; jb < T; jb += 4 * (CLS_THREADS / 32)) {
+        const int j = jb + g;
+        if (j < T) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + j * pitch + 2 * inner) + c);
+            const float p = sp[j];
+            acc[0] = fmaf(p, bf16_lo(v.x), acc[0]); acc[1] = fmaf(p, bf16_hi(v.x), acc[1]);
+            acc[2] = fmaf(p, bf16_lo(v.y), acc[2]); acc[3] = fmaf(p, bf16_hi(v.y), acc[3]);
+            acc[4] = fmaf(p, bf16_lo(v.z), acc[4]); acc[5] = fmaf(p, bf16_hi(v.z), acc[5]);
+            acc[6] = fmaf(p, bf16_lo(v.w), acc[6]); acc[7] = fmaf(p, bf16_hi(v.w), acc[7]);
+        }
     }
-    sacc[warp][2 * lane] = a0;
-    sacc[warp][2 * lane + 1] = a1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    }
+    if (g == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sacc[warp][c * 8 + k] = acc[k];
+    }
     __syncthreads();
     if (threadIdx.x < 64) {
         float o = 0.0f;
@@ -153,21 +170,46 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const __nv_bf
     const float delta = block_reduce<false>(part, red);
     for (int j = threadIdx.x; j < T; j += CLS_THREADS) sds[j] = scale * sp[j] * (sds[j] - delta);
     __syncthreads();
-    // warp w takes keys j = w (mod 8); lane owns dims 2 lane, 2 lane + 1: dk_j, dv_j rows out, dq0 accumulated
+    // a warp access covers four key rows (8 lanes x 16 bytes each); lane (g, c) owns dims [8 c, 8 c + 8) of the keys
+    // j = 4 (warp + 8 it) + g: dk_j, dv_j (and the zero dq_j) rows out, dq0 accumulated
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float q0 = sq[2 * lane], q1 = sq[2 * lane + 1], g0 = sdo[2 * lane], g1 = sdo[2 * lane + 1];
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int j = warp; j < T; j += CLS_THREADS / 32) {
-        const float ds = sds[j], p = sp[j];
-        const uint32_t k = __ldg(reinterpret_cast<const uint32_t*>(base + j * pitch + inner) + lane);
-        a0 = fmaf(ds, bf16_lo(k), a0);
-        a1 = fmaf(ds, bf16_hi(k), a1);
-        reinterpret_cast<uint32_t*>(dbase + j * pitch + inner)[lane] = pack_bf16(ds * q0, ds * q1);
-        reinterpret_cast<uint32_t*>(dbase + j * pitch + 2 * inner)[lane] = pack_bf16(p * g0, p * g1);
-        if (j > 0) reinterpret_cast<uint32_t*>(dbase + j * pitch)[lane] = 0u;  // dq of the rows that were never queries
+    const int g = lane >> 3, c = lane & 7;
+    float q8[8], g8[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        q8[k] = sq[c * 8 + k];
+        g8[k] = sdo[c * 8 + k];
+        acc[k] = 0.0f;
     }
-    sacc[warp][2 * lane] = a0;
-    sacc[warp][2 * lane + 1] = a1;
+#pragma unroll 2
+    for (int jb = warp * 4; jb < T; jb += 4 * (CLS_THREADS / 32)) {
+        const int j = jb + g;
+        if (j < T) {
+            const float ds = sds[j], p = sp[j];
+            const uint4 kk = __ldg(reinterpret_cast<const uint4*>(base + j * pitch + inner) + c);
+            acc[0] = fmaf(ds, bf16_lo(kk.x), acc[0]); acc[1] = fmaf(ds, bf16_hi(kk.x), acc[1]);
+            acc[2] = fmaf(ds, bf16_lo(kk.y), acc[2]); acc[3] = fmaf(ds, bf16_hi(kk.y), acc[3]);
+            acc[4] = fmaf(ds, bf16_lo(kk.z), acc[4]); acc[5] = fmaf(ds, bf16_hi(kk.z), acc[5]);
+            acc[6] = fmaf(ds, bf16_lo(kk.w), acc[6]); acc[7] = fmaf(ds, bf16_hi(kk.w), acc[7]);
+            uint4 o;
+            o.x = pack_bf16(ds * q8[0], ds * q8[1]); o.y = pack_bf16(ds * q8[2], ds * q8[3]);
+            o.z = pack_bf16(ds * q8[4], ds * q8[5]); o.w = pack_bf16(ds * q8[6], ds * q8[7]);
+            reinterpret_cast<uint4*>(dbase + j * pitch + inner)[c] = o;
+            o.x = pack_bf16(p * g8[0], p * g8[1]); o.y = pack_bf16(p * g8[2], p * g8[3]);
+            o.z = pack_bf16(p * g8[4], p * g8[5]); o.w = pack_bf16(p * g8[6], p * g8[7]);
+            reinterpret_cast<uint4*>(dbase + j * pitch + 2 * inner)[c] = o;
+            if (j > 0) reinterpret_cast<uint4*>(dbase + j * pitch)[c] = make_uint4(0u, 0u, 0u, 0u);  // rows that were never queries
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    }
+    if (g == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sacc[warp][c * 8 + k] = acc[k];
+    }
     __syncthreads();
     if (threadIdx.x < 64) {
         float o = 0.0f;
