@@ -22,7 +22,7 @@
 namespace svit {
 namespace {
 
-constexpr int CLS_THREADS = 256;
+constexpr int CLS_THREADS = 128;  // small CTAs: all B * H of them resident at once (11 per SM at the benchmark shape)
 constexpr int CLS_MAX_T = 384;
 
 __device__ __forceinline__ float warp_sum_f(float v) {

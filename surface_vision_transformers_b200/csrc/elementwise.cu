@@ -384,13 +384,13 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a
 // =================================================================================================
 // LayerNorm backward + residual-gradient add + column reductions
 // =================================================================================================
-template <int NVEC>
+template <int NVEC, bool CLSG = false>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* g_in, float* g_out,
                                                      __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, float* __restrict__ colsum_out, int M,
-                                                     int D) {
+                                                     int D, int period) {
     extern __shared__ float red[];  // [3][D] block-level partial column sums
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -413,7 +413,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
         const float mu = mean[row], rs = rstd[row];
         const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
         const uint2* dar = reinterpret_cast<const uint2*>(da + static_cast<size_t>(row) * D);
-        const float4* gir = reinterpret_cast<const float4*>(g_in + static_cast<size_t>(row) * D);
+        // CLSG: the incoming gradient exists for rows 0, period, 2 period, ... only (compact matrix), zero elsewhere
+        const bool has_g = !CLSG || (row % period) == 0;
+        const float4* gir = reinterpret_cast<const float4*>(g_in + static_cast<size_t>(CLSG ? row / period : row) * D);
         float4 xh[NVEC], dy[NVEC], gi[NVEC];
         float s1 = 0.0f, s2 = 0.0f;
         // issue every load of the row first (memory-level parallelism), then reduce
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
             if (i < nvec) {
                 xh[k] = __ldcs(xr + i);
                 dv[k] = __ldcs(dar + i);
-                gi[k] = __ldcs(gir + i);
+                gi[k] = has_g ? __ldcs(gir + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
         }
 #pragma unroll
@@ -495,16 +497,28 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
 
 int launch_ln_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta, float* colsum_out,
-                  int M, int D, cudaStream_t st) {
+                  int M, int D, cudaStream_t st, int g_in_period) {
     if (M <= 0) return 0;
     if (!ln_shape_ok(D)) return -2;
     const int wpb = 8;
     int blocks = (M + wpb - 1) / wpb;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const int nv = (D + 127) / 128;
+    if (g_in_period > 0) {
+        if (g_in == g_out) {
+            set_error("ln_bwd: a compact incoming gradient cannot alias the full-size output");
+            return -2;
+        }
+        SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV, true>, dim3(blocks), dim3(wpb * 32), 3 * D * sizeof(float), st,
+                                         reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
+                                         reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D,
+                                         g_in_period)));
+        SVIT_CHECK_LAUNCH("ln_bwd");
+        return 0;
+    }
     SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV>, dim3(blocks), dim3(wpb * 32), 3 * D * sizeof(float), st,
                                      reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
-                                     reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D)));
+                                     reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D, 0)));
     SVIT_CHECK_LAUNCH("ln_bwd");
     return 0;
 }

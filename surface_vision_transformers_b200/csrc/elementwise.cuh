@@ -41,7 +41,9 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a
 //   dgamma += sum_rows da * xhat ; dbeta += sum_rows da ; colsum_out += sum_rows g_out   (fp32 atomics)
 int launch_ln_bwd(const void* da_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta, float* colsum_out,
-                  int M, int D, cudaStream_t st);
+                  int M, int D, cudaStream_t st, int g_in_period = 0);
+// g_in_period = T > 0: g_in is a compact [M / T, D] matrix that holds the incoming gradient of rows 0, T, 2T, ... only; every
+// other row's incoming gradient is zero (the last block under cls pooling, engine.cu) -- no zero-filled [M, D] buffer.
 
 // ---- a5: pooling + mlp_head (LayerNorm + Linear(D, C)) forward:  out[b,c]
 int launch_head_fwd(const float* x, const float* gamma, const float* beta, const float* W, const float* bias, float* out,

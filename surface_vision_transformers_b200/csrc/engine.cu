@@ -362,14 +362,10 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
             RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D,
                         3 * I, EPI_STORE, 0));
             RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
-            // the residual gradient entering LN1' is g_mid in the cls rows and zero elsewhere
-            if (cudaMemsetAsync(w.g, 0, nD * sizeof(float), st) != cudaSuccess) {
-                set_error("cls-row gradient clear failed");
-                return -12;
-            }
-            RET_IF(copy_cls_rows(w.g, static_cast<size_t>(e->T) * D, c.g, D, w.B, D, st));
+            // the residual gradient entering LN1' is g_mid in the cls rows (compact c.g) and zero elsewhere
             float* cs0 = (l > 0) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
-            RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs0, M, D, st));
+            RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), c.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs0, M, D, st,
+                                 e->T));
             if (progress != nullptr) progress(l, user);
             continue;
         }
