@@ -52,7 +52,7 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "sit_small_ico2_scan_age_train"
 # `ncu --set full` summary of the kernels of the current build (scripts/ncu_top.py + scripts/ncu_summary.py); re-captured
 # whenever a kernel changes -- roofline.traffic is read from it
-NCU_SUMMARY = "r02b_ncu_top_summary.json"
+NCU_SUMMARY = "r02c_ncu_top_summary.json"
 
 
 def executed_gflop(wl):
@@ -287,6 +287,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-input", default="bf16", choices=["bf16", "fp32"],
+                    help="dtype of the pinned host batches of the e2e leg: bf16 (rounded once on the host; the patch-embedding "
+                         "GEMM consumes bf16 either way, results are bit-identical) or fp32 (what the reference's loader yields)")
     ap.add_argument("--sweep", metavar="OUT.json", default=None,
                     help="instead of the headline line: time the other BASELINE.json configs (C1 tiny / C3 ico-1 / C4 MPP "
                          "training at the per-GPU batch, C5 SiT-base inference at batch 64..4096) and write one record per "
@@ -348,7 +351,9 @@ def main():
     g.manual_seed(1234 + rank)
     x_dev = torch.randn(B, m["num_channels"], m["num_patches"], m["num_vertices"], device=dev, generator=g)
     y_dev = torch.rand(B, device=dev, generator=g) * 19 + 26
-    x_host = x_dev.cpu().pin_memory()
+    # e2e batches: pinned host memory; bf16 staging halves the H2D bytes (MPP keeps fp32: its loss compares with the input)
+    e2e_bf16 = args.e2e_input == "bf16" and kind != "mpp"
+    x_host = (x_dev.bfloat16() if e2e_bf16 else x_dev).cpu().pin_memory()
     y_host = y_dev.cpu().pin_memory()
 
     def step(x, y):
@@ -427,7 +432,7 @@ def main():
     ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     assert len(losses) == args.steps
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d = x_host.numel() * 4 + y_host.numel() * 4
+    h2d = x_host.numel() * x_host.element_size() + y_host.numel() * 4
     d2h = 4
 
     # ---- dominant kernel (MLP up-projection GEMM + bias + GELU epilogue) timed alone ----
@@ -557,7 +562,12 @@ def main():
                                 last_block="token 0 only (cls pooling: the head reads x[:, 0]; same outputs and gradients)"
                                 if cls_only_last else "all rows", **m),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                                            ms_per_step=ms_e2e / args.steps),
+                                            ms_per_step=ms_e2e / args.steps,
+                                            input="pinned host batch as %s%s" % (
+                                                "bf16" if e2e_bf16 else "fp32",
+                                                " (rounded once on the host: bit-identical results, the embedding GEMM "
+                                                "consumes bf16 either way; --e2e-input fp32 for the reference loader's dtype)"
+                                                if e2e_bf16 else "")),
                     gpu_launches=int(launches), roofline=roof, roofline_gemm=roof_gemm if rank == 0 else None, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -100,6 +100,12 @@ int svit_mpp_prepare_weights(svit_engine* e, const float* to_original_w /* (C*V,
 int svit_forward(svit_engine* e, const float* params, const void* shadow, void* workspace, size_t workspace_bytes,
                  const float* input, int batch, const int32_t* table, int n_mesh, const float* ch_mean,
                  const float* ch_std, float* out, int training, void* stream);
+/* The same with the input given as bf16 (input_bf16 = 1; same layout).  The patch-embedding GEMM consumes bf16 either way
+ * (the packing kernel rounds fp32 input to bf16), so a batch rounded once on the host -- `inputs.to(device)` of
+ * tools/train.py:281-283 with a pinned bf16 tensor -- gives bit-identical results at half the host-to-device bytes. */
+int svit_forward_ex(svit_engine* e, const float* params, const void* shadow, void* workspace, size_t workspace_bytes,
+                    const void* input, int input_bf16, int batch, const int32_t* table, int n_mesh, const float* ch_mean,
+                    const float* ch_std, float* out, int training, void* stream);
 /* dout (B,num_classes) -> grads (flat, ACCUMULATED: caller zeroes). Must follow svit_forward(training=1) on the
  * same workspace. */
 /* progress (may be NULL) is called on the host while the work is being enqueued: stage = depth after the head

@@ -47,6 +47,7 @@ SIGNATURES = {
     "svit_prepare_weights": (ci, [vp, vp, vp, vp]),
     "svit_mpp_prepare_weights": (ci, [vp, vp, vp, vp]),
     "svit_forward": (ci, [vp, vp, vp, vp, csz, vp, ci, vp, ci, vp, vp, vp, ci, vp]),
+    "svit_forward_ex": (ci, [vp, vp, vp, vp, csz, vp, ci, ci, vp, ci, vp, vp, vp, ci, vp]),
     "svit_backward": (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "svit_encoder_forward": (ci, [vp, vp, vp, vp, csz, vp, ci, vp, ci, vp]),
     "svit_encoder_backward": (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),

@@ -190,6 +190,11 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 // One thread per 8 consecutive output elements (one 16-byte store); the operand row is channel-major (k = c * V + v),
 // so the 8 inputs of a thread are consecutive floats of one channel (or straddle one channel boundary).
 // IdxT = uint32_t whenever the vector count fits (always, in practice): the two divisions per thread are 32-bit then.
+// input element `off`: fp32, or bf16 when the caller staged the batch as bf16 (the operand is rounded to bf16 here
+// anyway, so a batch rounded once on the host gives bit-identical results at half the host-to-device bytes)
+__device__ __forceinline__ float pack_ldx(const PackDesc& d, size_t off) {
+    return d.x_bf16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(d.x) + off)) : __ldg(d.x + off);
+}
 template <typename IdxT>
 __global__ void __launch_bounds__(256) pack_patches_kernel(const PackDesc d) {
     const int T = d.N + 1;
@@ -215,11 +220,11 @@ __global__ void __launch_bounds__(256) pack_patches_kernel(const PackDesc d) {
         int c = k0 / d.V, v = k0 - c * d.V;
         if (!replace && d.table == nullptr && k0 + 8 <= CV) {
             // plain pre-patched input, no padding column in this vector: 8 consecutive (c, v) of one patch
-            const float* src = d.x + ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v;
+            size_t src = ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v;
             const size_t cstep = static_cast<size_t>(d.N - 1) * d.V;  // extra offset once the channel wraps
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                val[e] = __ldg(src + e);
+                val[e] = pack_ldx(d, src + e);
                 if (++v == d.V) {
                     v = 0;
                     src += cstep;
@@ -240,10 +245,10 @@ __global__ void __launch_bounds__(256) pack_patches_kernel(const PackDesc d) {
                 if (replace) {
                     x = d.mask_token[v * d.C + c];
                 } else if (d.table != nullptr) {
-                    x = __ldg(d.x + (static_cast<size_t>(b) * d.C + c) * d.n_mesh + d.table[static_cast<size_t>(v) * d.N + n]);
+                    x = pack_ldx(d, (static_cast<size_t>(b) * d.C + c) * d.n_mesh + d.table[static_cast<size_t>(v) * d.N + n]);
                     if (d.ch_mean != nullptr) x = (x - d.ch_mean[c]) / d.ch_std[c];
                 } else {
-                    x = __ldg(d.x + ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v);
+                    x = pack_ldx(d, ((static_cast<size_t>(b) * d.C + c) * d.N + n) * d.V + v);
                 }
             }
             val[e] = x;

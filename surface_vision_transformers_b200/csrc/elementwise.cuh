@@ -29,6 +29,7 @@ struct PackDesc {
     int n_mesh;
     const float* ch_mean;        // (C) or nullptr
     const float* ch_std;         // (C) or nullptr
+    int x_bf16;                  // 1: x points to bf16 data of the same layout (inputs staged as bf16 on the host)
 };
 int launch_pack_patches(const PackDesc& d, cudaStream_t st);
 

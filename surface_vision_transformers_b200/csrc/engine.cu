@@ -798,14 +798,26 @@ int svit_mpp_prepare_weights(svit_engine* e, const float* Wdec, void* mpp_shadow
 int svit_forward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, size_t ws_bytes, const float* input, int B,
                  const int32_t* table, int n_mesh, const float* ch_mean, const float* ch_std, float* out, int training,
                  void* stream) {
+    return svit_forward_ex(e, P, sh, ws_ptr, ws_bytes, input, 0, B, table, n_mesh, ch_mean, ch_std, out, training, stream);
+}
+
+int svit_forward_ex(svit_engine* e, const float* P, const void* sh, void* ws_ptr, size_t ws_bytes, const void* input,
+                    int input_bf16, int B, const int32_t* table, int n_mesh, const float* ch_mean, const float* ch_std,
+                    float* out, int training, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const float* in_f = reinterpret_cast<const float*>(input);
     if (e->check) {
-        PackDesc cpd{input, nullptr, B, e->C, e->N, e->V, e->K, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
+        if (input_bf16) {
+            set_error("fp32 check mode takes fp32 input");
+            return -1;
+        }
+        PackDesc cpd{in_f, nullptr, B, e->C, e->N, e->V, e->K, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
         return ck_forward(e, P, ws_ptr, ws_bytes, cpd, B, out, st);
     }
     Ws w;
     RET_IF(check_ws(e, B, training, 0, 1, ws_ptr, ws_bytes, &w));
-    PackDesc pd{input, w.Apatch, B, e->C, e->N, e->V, e->Kp, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std};
+    PackDesc pd{in_f, w.Apatch, B, e->C, e->N, e->V, e->Kp, nullptr, nullptr, nullptr, nullptr, table, n_mesh, ch_mean, ch_std,
+                input_bf16 ? 1 : 0};
     RET_IF(embed_fwd(e, sh, w, pd, st));
     const float* xf = nullptr;
     const bool cls = cls_last(e);  // then xf is the compact [B, D] encoder output of token 0

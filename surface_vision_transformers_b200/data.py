@@ -44,12 +44,17 @@ def preprocess_meshes(hemis, means, stds, table):
 class PatchedNpyDataset:
     """``{split}_data.npy`` + ``{split}_labels.npy`` of the reference, pinned in host memory as float32."""
 
-    def __init__(self, data_path, split, pin=True):
+    def __init__(self, data_path, split, pin=True, stage_dtype=torch.float32):
+        """``stage_dtype=torch.bfloat16`` keeps the (pinned) samples as bf16: the B200 ``SiT`` takes bf16 batches as they
+        are and gives bit-identical results (its patch-embedding GEMM consumes bf16 either way), at half the
+        host-to-device bytes per step.  Not for ``masked_patch_pretraining``, whose loss compares with the fp32 input."""
+        if stage_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("stage_dtype must be torch.float32 or torch.bfloat16")
         data = np.load(os.path.join(data_path, f"{split}_data.npy"))
         labels = np.load(os.path.join(data_path, f"{split}_labels.npy"))
         if data.ndim != 4 or labels.shape[0] != data.shape[0]:
             raise ValueError(f"unexpected shapes {data.shape} / {labels.shape} (want (2S, C, N, V) and (2S,))")
-        self.data = torch.from_numpy(data).float()
+        self.data = torch.from_numpy(data).float().to(stage_dtype)
         self.labels = torch.from_numpy(labels).float()
         if pin and torch.cuda.is_available():
             self.data = self.data.pin_memory()
@@ -81,7 +86,7 @@ class PatchedNpyDataset:
             if not shuffle and world == 1:
                 yield self.data[i:i + idx.numel()], self.labels[i:i + idx.numel()]   # contiguous views stay pinned
                 continue
-            x = torch.empty((idx.numel(),) + self.data.shape[1:], dtype=torch.float32, pin_memory=pinned)
+            x = torch.empty((idx.numel(),) + self.data.shape[1:], dtype=self.data.dtype, pin_memory=pinned)
             y = torch.empty((idx.numel(),), dtype=torch.float32, pin_memory=pinned)
             torch.index_select(self.data, 0, idx, out=x)
             torch.index_select(self.labels, 0, idx, out=y)

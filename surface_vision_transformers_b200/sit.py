@@ -99,8 +99,9 @@ class _SiTFunction(torch.autograd.Function):
         ctx.drop = model._next_dropout_state()
         model._apply_dropout_state(ctx.drop)
         table, n_mesh, ch_mean, ch_std = mesh_args if mesh_args is not None else (None, 0, None, None)
-        check(lib.svit_forward(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(img), B,
-                               ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std), ptr(out), 1, _stream(dev)), "svit_forward")
+        check(lib.svit_forward_ex(model._engine, ptr(model._flat), ptr(model._shadow), ptr(ws), nbytes, ptr(img),
+                                  1 if img.dtype == torch.bfloat16 else 0, B, ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std),
+                                  ptr(out), 1, _stream(dev)), "svit_forward")
         ctx.model = model
         ctx.ws = ws
         ctx.B = B
@@ -379,6 +380,10 @@ class SiT(nn.Module):
                              f"got {tuple(img.shape)}")
         if not img.is_cuda:
             raise RuntimeError("SiT (B200) needs a CUDA input: there is no CPU fallback")
+        # bf16 batches (staged as bf16 on the host: half the host-to-device bytes) are consumed as they are -- the patch
+        # packing kernel rounds fp32 input to bf16 anyway, so the results are bit-identical; anything else becomes fp32
+        if img.dtype == torch.bfloat16 and not _lib.load().svit_get_check_mode(self._engine):
+            return img.contiguous()
         return img.contiguous().float()
 
     def forward(self, img):
@@ -400,8 +405,9 @@ class SiT(nn.Module):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(B, self.num_classes, dtype=torch.float32, device=dev)
         self._apply_dropout_state(self._next_dropout_state())   # .train() under no_grad still drops, as nn.Dropout does
-        check(lib.svit_forward(self._engine, ptr(self._flat), ptr(self._shadow), ptr(ws), nbytes, ptr(img), B,
-                               ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std), ptr(out), 0, _stream(dev)), "svit_forward")
+        check(lib.svit_forward_ex(self._engine, ptr(self._flat), ptr(self._shadow), ptr(ws), nbytes, ptr(img),
+                                  1 if img.dtype == torch.bfloat16 else 0, B, ptr(table), n_mesh, ptr(ch_mean), ptr(ch_std),
+                                  ptr(out), 0, _stream(dev)), "svit_forward")
         return out
 
     def forward_mesh(self, mesh, table, ch_mean=None, ch_std=None):

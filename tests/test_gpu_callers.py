@@ -402,6 +402,41 @@ def test_training_from_raw_meshes_vs_oracle():
 
 
 @pytest.mark.parametrize("l1", [False, True])
+def test_bf16_staged_batches_give_bit_identical_results(tmp_path):
+    """svit_forward_ex(input_bf16=1): a batch rounded to bf16 on the host (PatchedNpyDataset(stage_dtype=bfloat16), half
+    the host-to-device bytes of tools/train.py:281-283) gives the SAME bits as its fp32 copy -- prediction, loss and every
+    gradient -- because the packing kernel rounds fp32 input to bf16 with the same round-to-nearest-even."""
+    import numpy as np
+    cfg = dict(dim=192, depth=2, heads=3, mlp_dim=768, num_patches=80, num_vertices=45)
+    torch.manual_seed(3)
+    model = svit.SiT(**cfg).to(DEV)
+    x = torch.randn(6, 4, 80, 45, device=DEV)
+    y = torch.rand(6, device=DEV) * 19 + 26
+    xb = x.bfloat16()
+    res = []
+    for inp in (xb, xb.float(), x):
+        model.zero_grad(set_to_none=True)
+        out = model(inp)
+        torch.nn.functional.mse_loss(out.squeeze(), y).backward()
+        res.append((out.detach().clone(), model.to_patch_embedding[1].weight.grad.clone(), model.pos_embedding.grad.clone()))
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)                                  # bf16 batch == its fp32 copy, bit for bit
+    for a, b in zip(res[0][:1], res[2][:1]):
+        assert torch.equal(a, b)                                  # ... and == the original fp32 batch (same rounding in the kernel)
+    with torch.no_grad():
+        assert torch.equal(model.eval()(xb), model(xb.float()))
+    # the reader hands out pinned bf16 batches
+    np.save(tmp_path / "train_data.npy", x.double().cpu().numpy())
+    np.save(tmp_path / "train_labels.npy", y.double().cpu().numpy())
+    ds = svit.PatchedNpyDataset(str(tmp_path), "train", stage_dtype=torch.bfloat16)
+    bx, by = next(iter(ds.batches(6)))
+    assert bx.dtype == torch.bfloat16 and by.dtype == torch.float32 and torch.equal(bx.to(DEV), xb)
+    # fp32 check mode has no bf16 operand: the module converts
+    model.set_check_mode(True)
+    with torch.no_grad():
+        assert torch.equal(model(xb), model(xb.float()))
+
+
 def test_fused_regression_loss_matches_torch_criterion(l1):
     """svit.regression_loss == nn.MSELoss(reduction='mean') / nn.L1Loss() on outputs.squeeze() (train.py:245-248, 288):
     value and gradient, incl. an exact zero residual (sign(0) = 0 for L1) and an upstream scale."""
