@@ -401,7 +401,6 @@ def test_training_from_raw_meshes_vs_oracle():
     assert w[0] < TOL, w
 
 
-@pytest.mark.parametrize("l1", [False, True])
 def test_bf16_staged_batches_give_bit_identical_results(tmp_path):
     """svit_forward_ex(input_bf16=1): a batch rounded to bf16 on the host (PatchedNpyDataset(stage_dtype=bfloat16), half
     the host-to-device bytes of tools/train.py:281-283) gives the SAME bits as its fp32 copy -- prediction, loss and every
@@ -437,6 +436,7 @@ def test_bf16_staged_batches_give_bit_identical_results(tmp_path):
         assert torch.equal(model(xb), model(xb.float()))
 
 
+@pytest.mark.parametrize("l1", [False, True])
 def test_fused_regression_loss_matches_torch_criterion(l1):
     """svit.regression_loss == nn.MSELoss(reduction='mean') / nn.L1Loss() on outputs.squeeze() (train.py:245-248, 288):
     value and gradient, incl. an exact zero residual (sign(0) = 0 for L1) and an upstream scale."""
