@@ -418,10 +418,10 @@ def test_bf16_staged_batches_give_bit_identical_results(tmp_path):
         out = model(inp)
         torch.nn.functional.mse_loss(out.squeeze(), y).backward()
         res.append((out.detach().clone(), model.to_patch_embedding[1].weight.grad.clone(), model.pos_embedding.grad.clone()))
-    for a, b in zip(res[0], res[1]):
-        assert torch.equal(a, b)                                  # bf16 batch == its fp32 copy, bit for bit
-    for a, b in zip(res[0][:1], res[2][:1]):
-        assert torch.equal(a, b)                                  # ... and == the original fp32 batch (same rounding in the kernel)
+    assert torch.equal(res[0][0], res[1][0])                      # bf16 batch == its fp32 copy, bit for bit (the forward has no atomics)
+    assert torch.equal(res[0][0], res[2][0])                      # ... and == the original fp32 batch (same rounding in the kernel)
+    for k in (1, 2):                                              # gradients: equal up to the fp32 atomics order of the weight-gradient kernels
+        assert rel_l2(res[0][k], res[1][k]) < 1e-6 and rel_l2(res[0][k], res[2][k]) < 1e-6
     with torch.no_grad():
         assert torch.equal(model.eval()(xb), model(xb.float()))
     # the reader hands out pinned bf16 batches
