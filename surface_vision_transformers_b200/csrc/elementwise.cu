@@ -707,12 +707,39 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
         dst[i] = __float2bfloat16(src[i]);
 }
+// 8 elements per thread and step: two 16-byte loads, one 16-byte store, two steps in flight (n8 = n / 8 vectors)
+__global__ void __launch_bounds__(256) cast_bf16_vec_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, size_t n8) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + stride < n8; i += 2 * stride) {
+        const float4 a0 = __ldcs(src + 2 * i), a1 = __ldcs(src + 2 * i + 1);
+        const float4 b0 = __ldcs(src + 2 * (i + stride)), b1 = __ldcs(src + 2 * (i + stride) + 1);
+        dst[i] = make_uint4(pack2_bf16(a0.x, a0.y), pack2_bf16(a0.z, a0.w), pack2_bf16(a1.x, a1.y), pack2_bf16(a1.z, a1.w));
+        dst[i + stride] = make_uint4(pack2_bf16(b0.x, b0.y), pack2_bf16(b0.z, b0.w), pack2_bf16(b1.x, b1.y), pack2_bf16(b1.z, b1.w));
+    }
+    for (; i < n8; i += stride) {
+        const float4 a0 = __ldcs(src + 2 * i), a1 = __ldcs(src + 2 * i + 1);
+        dst[i] = make_uint4(pack2_bf16(a0.x, a0.y), pack2_bf16(a0.z, a0.w), pack2_bf16(a1.x, a1.y), pack2_bf16(a1.z, a1.w));
+    }
+}
 int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
-    size_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    cast_bf16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
-    SVIT_CHECK_LAUNCH("cast_bf16");
+    const size_t n8 = ((reinterpret_cast<uintptr_t>(src) % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0) ? n / 8 : 0;
+    if (n8 > 0) {
+        size_t blocks = (n8 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cast_bf16_vec_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(src),
+                                                                      reinterpret_cast<uint4*>(dst), n8);
+        SVIT_CHECK_LAUNCH("cast_bf16");
+    }
+    const size_t done = n8 * 8;
+    if (done < n) {   // tail (or everything, for unaligned pointers)
+        const size_t rest = n - done;
+        size_t blocks = (rest + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        cast_bf16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(src + done, reinterpret_cast<__nv_bfloat16*>(dst) + done, rest);
+        SVIT_CHECK_LAUNCH("cast_bf16");
+    }
     return 0;
 }
 
@@ -860,32 +887,66 @@ int launch_unpermute_patch_wgrad(const float* dWp, float* dW, int D, int C, int 
 // =================================================================================================
 // a9: MPP loss
 // =================================================================================================
-__global__ void mpp_loss_fwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ x,
-                                    const uint8_t* __restrict__ mask, float* __restrict__ loss_sum, int C, int N, int V) {
+// A block of 128 threads per group of patch rows (grid-stride; unmasked rows cost one byte): the 612 elements of a row are
+// spread over the block (every load of the row in flight at once), one block reduction and ONE atomic per block at the
+// end.  (89 us for 217 MB, like round 1's block per row with 40,960 atomics on one address, 92 us: the 612-byte runs of x and
+// the 2,448-byte rows of y at random positions bound it, not the block structure.  A warp per row, 19 dependent steps per
+// lane, was slower: 165 us.)
+constexpr int MPP_LOSS_MAXIT = 8;   // C * V <= 128 * 8 takes the unrolled path
+__global__ void __launch_bounds__(128) mpp_loss_fwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ x,
+                                                           const uint8_t* __restrict__ mask, float* __restrict__ loss_sum,
+                                                           int BN, int C, int N, int V) {
     __shared__ float scratch[32];
-    const int bn = blockIdx.x;
-    if (mask[bn] == 0) return;
-    const int b = bn / N, n = bn % N;
     const int T = N + 1;
-    const float* yr = y + (static_cast<size_t>(b) * T + 1 + n) * ldy;
+    const int CV = C * V;
     float s = 0.0f;
-    for (int k = threadIdx.x; k < C * V; k += blockDim.x) {
-        const int v = k / C, c = k - v * C;
-        const float t = x[((static_cast<size_t>(b) * C + c) * N + n) * V + v];
-        const float dlt = yr[k] - t;
-        s += dlt * dlt;
+    for (int bn = blockIdx.x; bn < BN; bn += gridDim.x) {
+        if (mask[bn] == 0) continue;
+        const int b = bn / N, n = bn - b * N;
+        const float* yr = y + (static_cast<size_t>(b) * T + 1 + n) * ldy;
+        const float* xb = x + (static_cast<size_t>(b) * C * N + n) * V;   // + c * N * V + v
+        if (CV <= 128 * MPP_LOSS_MAXIT) {
+            float yv[MPP_LOSS_MAXIT], xv[MPP_LOSS_MAXIT];
+#pragma unroll
+            for (int i = 0; i < MPP_LOSS_MAXIT; ++i) {
+                const int k = threadIdx.x + i * 128;
+                yv[i] = 0.0f;
+                xv[i] = 0.0f;
+                if (k < CV) {
+                    const int v = k / C, c = k - v * C;
+                    yv[i] = __ldcs(yr + k);
+                    xv[i] = __ldg(xb + static_cast<size_t>(c) * N * V + v);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MPP_LOSS_MAXIT; ++i) {
+                const float dlt = yv[i] - xv[i];
+                s = fmaf(dlt, dlt, s);
+            }
+        } else {
+            for (int k = threadIdx.x; k < CV; k += 128) {
+                const int v = k / C, c = k - v * C;
+                const float dlt = yr[k] - xb[static_cast<size_t>(c) * N * V + v];
+                s = fmaf(dlt, dlt, s);
+            }
+        }
     }
     s = block_sum(s, scratch);
-    if (threadIdx.x == 0) atomicAdd(loss_sum, s);
+    if (threadIdx.x == 0 && s != 0.0f) atomicAdd(loss_sum, s);
 }
 int launch_mpp_loss_fwd(const float* y, int ldy, const float* x, const uint8_t* mask, float* loss_sum, int B, int C, int N,
                         int V, cudaStream_t st) {
     if (B <= 0) return 0;
-    mpp_loss_fwd_kernel<<<B * N, 128, 0, st>>>(y, ldy, x, mask, loss_sum, C, N, V);
+    const int BN = B * N;
+    int blocks = BN < 148 * 16 ? BN : 148 * 16;
+    mpp_loss_fwd_kernel<<<blocks, 128, 0, st>>>(y, ldy, x, mask, loss_sum, BN, C, N, V);
     SVIT_CHECK_LAUNCH("mpp_loss_fwd");
     return 0;
 }
 
+// dy[row, :] = coef * (y - x) for masked patch rows, zeros elsewhere (cls rows, unmasked rows, pad columns), bf16: a block per
+// row, a thread writes 8 consecutive outputs as one 16-byte store (113 -> 95 us at the benchmark shape; a grid-stride variant
+// with several rows per block was slower, 132 us).
 __global__ void mpp_loss_bwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ x,
                                     const uint8_t* __restrict__ mask, const float* __restrict__ coef_dev,
                                     __nv_bfloat16* __restrict__ dy, int lddy, int C, int N, int V) {
@@ -897,6 +958,27 @@ __global__ void mpp_loss_bwd_kernel(const float* __restrict__ y, int ldy, const 
     const float coef = *coef_dev;
     const int n = t - 1;
     const float* yr = y + static_cast<size_t>(row) * ldy;
+    if ((lddy & 7) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+        for (int k0 = threadIdx.x * 8; k0 < lddy; k0 += blockDim.x * 8) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (on && k0 < C * V) {
+                float val[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k = k0 + e;
+                    val[e] = 0.0f;
+                    if (k < C * V) {
+                        const int v = k / C, c = k - v * C;
+                        val[e] = coef * (__ldcs(yr + k) - __ldg(x + ((static_cast<size_t>(b) * C + c) * N + n) * V + v));
+                    }
+                }
+                o = make_uint4(pack2_bf16(val[0], val[1]), pack2_bf16(val[2], val[3]), pack2_bf16(val[4], val[5]),
+                               pack2_bf16(val[6], val[7]));
+            }
+            *reinterpret_cast<uint4*>(dr + k0) = o;
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < lddy; k += blockDim.x) {
         float val = 0.0f;
         if (on && k < C * V) {
@@ -915,37 +997,74 @@ int launch_mpp_loss_bwd(const float* y, int ldy, const float* x, const uint8_t* 
     return 0;
 }
 
-__global__ void masked_rowsum_kernel(const float* __restrict__ g0, const uint8_t* __restrict__ sel, float* __restrict__ r,
-                                     int B, int T, int D, int rows_per_block) {
+// r[d] += sum over the selected patch rows of g0: a warp per row (the selection byte is read first, unselected rows
+// cost nothing), the whole row in flight per warp, block-level partial sums in shared memory, one atomic per column and
+// block.  blockDim = 256 (8 warps), dynamic shared memory D floats.
+__global__ void __launch_bounds__(256) masked_rowsum_kernel(const float* __restrict__ g0, const uint8_t* __restrict__ sel,
+                                                            float* __restrict__ r, int B, int T, int D, int rows_per_block) {
+    extern __shared__ float mr_red[];  // [D]
     const int N = T - 1;
     const int i0 = blockIdx.x * rows_per_block;
     const int i1 = min(B * N, i0 + rows_per_block);
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float s = 0.0f;
-        for (int i = i0; i < i1; ++i) {
-            if (sel[i]) {
-                const int b = i / N, n = i - b * N;
-                s += g0[(static_cast<size_t>(b) * T + 1 + n) * D + d];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) mr_red[d] = 0.0f;
+    __syncthreads();
+    for (int d0 = 0; d0 < D; d0 += 32 * 4 * 4) {   // 512 columns per pass: 4 float4 per lane
+        float4 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int i = i0 + warp; i < i1; i += 8) {
+            if (!sel[i]) continue;
+            const int b = i / N, n = i - b * N;
+            const float4* row = reinterpret_cast<const float4*>(g0 + (static_cast<size_t>(b) * T + 1 + n) * D + d0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = (k * 32 + lane) * 4;
+                if (d0 + c < D) {
+                    const float4 v = __ldcs(row + k * 32 + lane);
+                    acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+                }
             }
         }
-        atomicAdd(&r[d], s);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = d0 + (k * 32 + lane) * 4;
+            if (c < D) {
+                atomicAdd(&mr_red[c], acc[k].x); atomicAdd(&mr_red[c + 1], acc[k].y);
+                atomicAdd(&mr_red[c + 2], acc[k].z); atomicAdd(&mr_red[c + 3], acc[k].w);
+            }
+        }
     }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(&r[d], mr_red[d]);
 }
+// dmt[k] += sum_d r[d] W[d, k]: grid (K / 128, slices of d), partial sums added atomically
 __global__ void mask_token_gemv_kernel(const float* __restrict__ r, const float* __restrict__ W, float* __restrict__ dmt,
                                        int D, int K) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
-    float s = 0.0f;
-    for (int d = 0; d < D; ++d) s += r[d] * W[static_cast<size_t>(d) * K + k];
-    dmt[k] += s;
+    const int per = (D + gridDim.y - 1) / gridDim.y;
+    const int da = blockIdx.y * per, db = min(D, da + per);
+    float s0 = 0.0f, s1 = 0.0f;
+    int d = da;
+    for (; d + 2 <= db; d += 2) {
+        s0 = fmaf(r[d], W[static_cast<size_t>(d) * K + k], s0);
+        s1 = fmaf(r[d + 1], W[static_cast<size_t>(d + 1) * K + k], s1);
+    }
+    if (d < db) s0 = fmaf(r[d], W[static_cast<size_t>(d) * K + k], s0);
+    atomicAdd(&dmt[k], s0 + s1);
 }
 int launch_mask_token_grad(const float* g0, const uint8_t* replace_sel, const float* W, float* scratch_r, float* dmt,
                            int B, int T, int D, int K, cudaStream_t st) {
     if (B <= 0) return 0;
     cudaMemsetAsync(scratch_r, 0, D * sizeof(float), st);
     const int rpb = 64;
-    masked_rowsum_kernel<<<(B * (T - 1) + rpb - 1) / rpb, 128, 0, st>>>(g0, replace_sel, scratch_r, B, T, D, rpb);
-    mask_token_gemv_kernel<<<(K + 127) / 128, 128, 0, st>>>(scratch_r, W, dmt, D, K);
+    if ((D % 4) != 0) {
+        set_error("mask_token_grad: D=%d must be a multiple of 4", D);
+        return -2;
+    }
+    masked_rowsum_kernel<<<(B * (T - 1) + rpb - 1) / rpb, 256, D * sizeof(float), st>>>(g0, replace_sel, scratch_r, B, T, D, rpb);
+    mask_token_gemv_kernel<<<dim3((K + 127) / 128, 16), 128, 0, st>>>(scratch_r, W, dmt, D, K);
     count_launch();
     SVIT_CHECK_LAUNCH("mask_token_grad");
     return 0;
