@@ -113,6 +113,8 @@ class DataParallel(torch.nn.Module):
             return
         if self.overlap == "none":
             return
+        if stage == sit.depth:
+            self._ready = None                  # first callback of a backward: nothing can be left over from a failed one
         if stage >= STAGE_WINDOW:
             # (the head's 1.2 k gradients alone are not worth a collective: they ride with the last layer's range)
             if self.overlap == "window" and self._ready is not None and self._ready[1] - self._ready[0] >= self.min_window_numel:
