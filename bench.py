@@ -82,18 +82,47 @@ def load_peaks():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs.
+
+    NVML in-process (the library nvidia-smi itself reads: clocks.sm = NVML_CLOCK_SM, clocks_event_reasons.* = the bits of
+    nvmlDeviceGetCurrentClocksEventReasons) every 10 ms, so that a 0.4 s timed region yields tens of samples; the
+    `nvidia-smi -lms 100` subprocess of the profiling recipe is the fallback (its first line arrives after ~0.3 s)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []      # (sm_mhz, set(reasons))
+        self.max_mhz = None
         self.proc = None
         self.thread = None
+        self.source = None
+        self._stop = threading.Event()
+        self._nvml = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # the torch device may be remapped by CUDA_VISIBLE_DEVICES: find it by UUID
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        return pynvml, h
 
     def start(self):
+        try:
+            self._nvml = self._nvml_handle()
+            self.source = "nvml, 10 ms period"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -101,36 +130,53 @@ class ClockSampler:
         except OSError:
             self.proc = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.source = "nvidia-smi -lms 100"
+        self.thread = threading.Thread(target=self._read_smi, daemon=True)
         self.thread.start()
 
-    def _read(self):
+    def _poll_nvml(self):
+        pynvml, h = self._nvml
+        bits = ((pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while not self._stop.is_set():
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((mhz, {n for b, n in bits if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.010)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
-                self.samples.append(parts)
+                try:
+                    mhz = float(parts[0])
+                    self.max_mhz = float(parts[1])
+                except ValueError:
+                    continue
+                self.samples.append((mhz, {n for n, v in zip(self.NAMES, parts[3:7]) if v.lower().startswith("active")}))
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for p in self.samples:
+        if self.thread is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"])
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(p[0]))
-                mx = float(p[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.thread.join(timeout=5)
+        sm = sorted(s[0] for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            reasons |= s[1]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=self.max_mhz, reasons=sorted(reasons),
+                    samples=len(sm), source=self.source)
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm

@@ -483,7 +483,8 @@ struct AttnBwdArgs {
     const float* lse;
     int B, H, T;
     float scale, scale_log2e;
-    int debug;  // SVIT_ATTN_DEBUG: 4 = record a clock64 timeline of one CTA (svit_debug_attn_prof)
+    int debug;  // SVIT_ATTN_DEBUG: 4 = record a clock64 timeline of one CTA (svit_debug_attn_prof); 8 = dead warps do the full
+                // arithmetic like round 1 (A/B of the dead-pair shortcut)
 };
 
 #define PROF(slot) do { if ((args.debug & 4) && blockIdx.x == 148 * 3) g_attn_prof[slot] = clock64(); } while (0)
@@ -842,9 +843,25 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
             mbar_arrive_warp(&ds_full[pp]);
         };
         // P(pair) from S in TMEM -> registers (and the S buffer back to the tensor core)
+        // A (warp, pair) is DEAD when none of its 32 x 24 entries is real: the slab lies past the last key of the block
+        // (T = 321: slabs 2 and 3 of the fourth key block) or the lane quadrant past the last query (quadrant 3 of the third
+        // query block).  Its P and dS are exact zeros either way; a dead warp keeps the barrier protocol (and stores the
+        // zeros) but skips the TMEM loads and the arithmetic, which leaves its sub-partition's issue slots to the live slabs.
+        auto dead_pair = [&](int jj, int ii) {
+            return (min(BK_KEYS, T - jj * BK_KEYS) <= c0 || ii * 128 + q * 32 >= T) && !(args.debug & 8);   // warp-uniform
+        };
+        auto zero_pk = [&]() {
+#pragma unroll
+            for (int k = 0; k < BK_SLAB / 2; ++k) pk[k] = 0u;
+        };
         auto make_p = [&](uint32_t parity, int jj, int ii) {
             uint32_t sv[BK_SLAB];
             mbar_wait(s_full, parity);
+            if (dead_pair(jj, ii)) {
+                mbar_arrive_warp(s_free);
+                zero_pk();
+                return;
+            }
             tc_fence_after();
             load_slab(BK_T_S, sv);
             tc_fence_before();
@@ -856,6 +873,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) attn_bwd_kernel(const __grid_co
         auto make_ds = [&](uint32_t parity, int jj, int ii) {
             uint32_t dv[BK_SLAB];
             mbar_wait(dp_full, parity);
+            if (dead_pair(jj, ii)) {   // pk already holds the zeros of P(pair)
+                mbar_arrive_warp(dp_free);
+                return;
+            }
             tc_fence_after();
             load_slab(BK_T_DP, dv);
             tc_fence_before();
