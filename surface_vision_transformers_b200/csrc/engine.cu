@@ -41,7 +41,46 @@ struct svit_engine {
     unsigned long long drop_seed, drop_offset;
     int no_fuse_ln;  // SVIT_NO_FUSE_LN=1: keep the stand-alone LayerNorm kernels (A/B timing)
     int full_last;   // SVIT_FULL_LAST_LAYER=1: compute every row of the last block even under cls pooling (A/B timing)
+    // Weight-gradient GEMMs on a second stream, next to the LayerNorm backward kernels (encoder_bwd).  SVIT_WGRAD_OVERLAP:
+    // 0 = everything on the caller's stream, 1 = only the wgrad that directly precedes a LayerNorm backward, 2 (default) =
+    // both wgrads of a sub-layer (needs the second bf16 gradient buffer Ws::g16b).
+    int wgrad_overlap;
+    int side_dev;
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join[2];
 };
+
+// The side stream and its events, created on first use for the device the engine is called on.
+static bool ensure_side(svit_engine* e) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (e->side != nullptr && e->side_dev == dev) return true;
+    if (e->side != nullptr) return false;  // created for another device: this call runs on the caller's stream only
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3; ++i)
+        if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < i; ++j) cudaEventDestroy(ev[j]);
+            cudaStreamDestroy(s);
+            return false;
+        }
+    e->side = s;
+    e->side_dev = dev;
+    e->ev_fork = ev[0];
+    e->ev_join[0] = ev[1];
+    e->ev_join[1] = ev[2];
+    return true;
+}
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -65,7 +104,7 @@ struct Ws {
     std::vector<LayerWs> L;
     // backward temporaries
     float *g, *dWp, *rvec;
-    bf16 *g16, *du, *da, *dO, *dqkv;
+    bf16 *g16, *g16b, *du, *da, *dO, *dqkv;
     // mpp
     bf16 *xL16, *dy;
     size_t total;
@@ -113,6 +152,7 @@ static void carve(const svit_engine* e, int B, int training, int mpp, int with_e
         }
         w->g = bp.take<float>(M * e->D);
         w->g16 = bp.take<bf16>(M * e->D);
+        w->g16b = bp.take<bf16>(M * e->D);  // LN2' writes its bf16 gradient here while the side stream still reads g16
         w->du = bp.take<bf16>(M * e->mlp);
         w->da = bp.take<bf16>(M * e->D);
         w->dO = bp.take<bf16>(M * e->I);
@@ -141,7 +181,7 @@ static void carve(const svit_engine* e, int B, int training, int mpp, int with_e
             w->L[l].xout = (l & 1) ? xb : xa;
         }
         w->g = nullptr;
-        w->g16 = w->du = w->da = w->dO = w->dqkv = nullptr;
+        w->g16 = w->g16b = w->du = w->da = w->dO = w->dqkv = nullptr;
         w->dWp = w->rvec = nullptr;
     }
     if (mpp) {
@@ -331,12 +371,47 @@ static int encoder_fwd(const svit_engine* e, const float* P, const void* sh, Ws&
 // With dropout the gradient that enters a dropped branch is g * m / (1-p) (a bf16 copy in w.da, which is free at
 // both points); the bias gradients of to_out / fc2 are then column sums of that masked copy, so they come from the
 // wgrad kernel's bias column instead of the LayerNorm-backward / head column sums (callers skip those too).
+//
+// Side stream (use_side, set by the C-ABI entry points after ensure_side): the weight-gradient GEMMs leave the critical path.
+// LayerNorm backward is HBM-bound and leaves the tensor cores idle (76 us per launch, 10 % of the step), the weight-gradient
+// GEMMs are tensor / L2-bound and touch little HBM, and one CTA of each fits an SM together (wgrad: 205 KB shared memory,
+// 20 k registers, TMEM; ln_bwd: 5 KB, 32 k registers).  So the wgrads of a sub-layer are enqueued on a high-priority second
+// stream at the moment the LayerNorm backward of that sub-layer is enqueued on the caller's stream:
+//     main:  dfc2, dfc1 | LN2' (writes the bf16 gradient to g16b)  dto_out, attn', dqkv GEMM | LN1' (writes g16)
+//     side:             | wgrad fc2 (reads g16), wgrad fc1 (du)    .........................  | wgrad to_out (g16b), wgrad qkv
+// Buffers: a side kernel reads g16 / g16b / du / dqkv; the main stream waits for the side stream (join) before the kernel
+// that overwrites the first of them -- LN1' for the FeedForward pair (g16), the next layer's LN2' for the attention pair
+// (g16b; its attn' overwrites dqkv later) -- and before every progress callback (gradients of a stage must be final in
+// the caller's stream order).  Mode 1 moves only the wgrad that directly precedes a LayerNorm backward and needs no second
+// buffer.  Not with dropout (masked gradient copies live in w.da) and not for the B-row last block under cls pooling.
 static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws& w, const float* x_in, float* G,
-                       cudaStream_t st, svit_progress_fn progress = nullptr, void* user = nullptr, bool cls = false) {
+                       cudaStream_t st, svit_progress_fn progress = nullptr, void* user = nullptr, bool cls = false,
+                       bool use_side = false) {
     const int M = w.M, D = e->D, I = e->I, mlp = e->mlp;
     const float scale = 0.125f;
     const bool drop = e->drop_p > 0.0f;
     const size_t nD = static_cast<size_t>(M) * D;
+    const int ov = (use_side && !drop && e->side != nullptr) ? e->wgrad_overlap : 0;
+    cudaStream_t ss = e->side;
+    bool pending[2] = {false, false};
+    auto fork = [&]() {   // the side stream continues from this point of the caller's stream
+        cudaEventRecord(e->ev_fork, st);
+        cudaStreamWaitEvent(ss, e->ev_fork, 0);
+    };
+    auto mark = [&](int k) {   // ... and this is where the caller's stream will pick it up again
+        cudaEventRecord(e->ev_join[k], ss);
+        pending[k] = true;
+    };
+    auto join = [&](int k) {
+        if (pending[k]) {
+            cudaStreamWaitEvent(st, e->ev_join[k], 0);
+            pending[k] = false;
+        }
+    };
+    struct Joiner {   // every exit path leaves the side stream joined (stream capture requires it, and so do the callers)
+        decltype(join)& j;
+        ~Joiner() { j(0), j(1); }
+    } joiner{join};
     for (int l = e->depth - 1; l >= 0; --l) {
         LayerWs& L = w.L[l];
         const float* xin = (l == 0) ? x_in : w.L[l - 1].xout;
@@ -372,38 +447,57 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
         // ---- FeedForward ----
         // du = (g W2) * gelu'(u)      (L.u holds gelu'(u), stored by the forward epilogue)
         const bf16* gb = w.g16;
+        bf16* g16_mid = ov == 2 ? w.g16b : w.g16;   // bf16 gradient of the residual stream between the two sub-layers
         if (drop) {
             RET_IF(launch_dropout_grad(w.g, w.da, nD, 1, drop_layer(e, l, DROP_SITE_FF_OUT), st));
             gb = w.da;
         }
         RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, M, mlp, D, EPI_MUL,
                     0, nullptr, L.u));
-        RET_IF(wgrad(e, st, gb, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp, drop ? gp(FC2_B) : nullptr));
+        if (ov != 2) RET_IF(wgrad(e, st, gb, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp, drop ? gp(FC2_B) : nullptr));
         // da2 = du W1
         RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, M, D, mlp,
                     EPI_STORE, 0));
-        RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D, gp(FC1_B)));  // + d fc1_b = colsum(du)
+        if (ov) {
+            join(1);   // the attention pair of the layer above has read g16b (LN2' below overwrites it) and dqkv
+            fork();
+            if (ov == 2) RET_IF(wgrad(e, ss, gb, D, L.h, mlp, gp(FC2_W), mlp, M, D, mlp));
+            RET_IF(wgrad(e, ss, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D, gp(FC1_B)));
+            mark(0);
+        } else {
+            RET_IF(wgrad(e, st, w.du, mlp, L.a2, D, gp(FC1_W), D, M, mlp, D, gp(FC1_B)));  // + d fc1_b = colsum(du)
+        }
         // g_mid = g + LN2'(da2) ; colsum(g_mid) = d out_b
-        RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, w.g16, gp(LN2_W), gp(LN2_B),
+        RET_IF(launch_ln_bwd(w.da, L.xmid, L.mean2, L.rstd2, pp(LN2_W), w.g, w.g, g16_mid, gp(LN2_W), gp(LN2_B),
                              drop ? nullptr : gp(OUT_B), M, D, st));
+        if (ov == 1) join(0);
         // ---- Attention ----
-        gb = w.g16;
+        gb = g16_mid;
         if (drop) {
             RET_IF(launch_dropout_grad(w.g, w.da, nD, 1, drop_layer(e, l, DROP_SITE_TO_OUT), st));
             gb = w.da;
         }
         RET_IF(gemm(e, st, gb, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, M, I, D, EPI_STORE, 0));
-        RET_IF(wgrad(e, st, gb, D, L.O, I, gp(OUT_W), I, M, D, I, drop ? gp(OUT_B) : nullptr));
+        if (ov != 2) RET_IF(wgrad(e, st, gb, D, L.O, I, gp(OUT_W), I, M, D, I, drop ? gp(OUT_B) : nullptr));
         AttnBwdDesc bd{L.qkv, L.O, w.dO, L.lse, w.dqkv, w.B, e->H, e->T, scale};
         // communication window: the next kernel is long and hands SMs out CTA by CTA (svit_b200.h, SVIT_STAGE_WINDOW)
         if (progress != nullptr) progress(SVIT_STAGE_WINDOW + l, user);
         RET_IF(launch_attn_bwd(bd, st));
         RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D, 3 * I,
                     EPI_STORE, 0));
-        RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+        if (ov) {
+            join(0);   // the FeedForward pair has read g16 (LN1' below overwrites it) and du
+            fork();
+            if (ov == 2) RET_IF(wgrad(e, ss, gb, D, L.O, I, gp(OUT_W), I, M, D, I));
+            RET_IF(wgrad(e, ss, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+            mark(1);
+        } else {
+            RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+        }
         // g_in = g_mid + LN1'(da1) ; colsum(g_in) = d fc2_b of the previous layer
         float* cs = (l > 0 && !drop) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
         RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), w.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs, M, D, st));
+        if (ov == 1 || progress != nullptr) join(1);
         // every gradient of layer l is final now (d fc2_b[l] was added by the layer above / the head)
         if (progress != nullptr) progress(l, user);
     }
@@ -670,6 +764,11 @@ svit_engine* svit_create(const svit_config* cfg) {
     e->drop_seed = e->drop_offset = 0;
     e->no_fuse_ln = getenv("SVIT_NO_FUSE_LN") != nullptr && atoi(getenv("SVIT_NO_FUSE_LN")) != 0;
     e->full_last = getenv("SVIT_FULL_LAST_LAYER") != nullptr && atoi(getenv("SVIT_FULL_LAST_LAYER")) != 0;
+    e->wgrad_overlap = getenv("SVIT_WGRAD_OVERLAP") != nullptr ? atoi(getenv("SVIT_WGRAD_OVERLAP")) : 2;
+    if (e->wgrad_overlap < 0 || e->wgrad_overlap > 2) e->wgrad_overlap = 2;
+    e->side = nullptr;
+    e->side_dev = -1;
+    e->ev_fork = e->ev_join[0] = e->ev_join[1] = nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int sms = 0;
@@ -726,7 +825,17 @@ svit_engine* svit_create(const svit_config* cfg) {
     return e;
 }
 
-void svit_destroy(svit_engine* e) { delete e; }
+void svit_destroy(svit_engine* e) {
+    if (e == nullptr) return;
+    if (e->side != nullptr) {   // best effort: the context may already be gone at interpreter exit
+        cudaEventDestroy(e->ev_fork);
+        cudaEventDestroy(e->ev_join[0]);
+        cudaEventDestroy(e->ev_join[1]);
+        cudaStreamDestroy(e->side);
+        cudaGetLastError();
+    }
+    delete e;
+}
 int svit_num_params(const svit_engine* e) { return static_cast<int>(e->poff.size()); }
 long long svit_param_offset(const svit_engine* e, int i) { return (i >= 0 && i < (int)e->poff.size()) ? e->poff[i] : -1; }
 long long svit_param_numel(const svit_engine* e, int i) { return (i >= 0 && i < (int)e->pnum.size()) ? e->pnum[i] : -1; }
@@ -841,7 +950,7 @@ int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, 
                            e->drop_p > 0.0f ? nullptr : G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, cls ? 1 : e->T, e->D,
                            e->NC, e->cfg.pool_mean, 1e-5f, st));
     if (progress != nullptr) progress(e->depth, user);
-    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, cls));
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, cls, e->wgrad_overlap != 0 && ensure_side(e)));
     RET_IF(embed_bwd(e, w, G, st));
     if (progress != nullptr) progress(-1, user);
     return 0;
@@ -892,7 +1001,7 @@ int svit_encoder_backward(svit_engine* e, const float* P, const void* sh, void* 
     cudaMemcpyAsync(w.g, dy, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     RET_IF(launch_cast_bf16(dy, w.g16, n, st));
     if (!(e->drop_p > 0.0f)) RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], w.M, e->D, e->D, st));
-    RET_IF(encoder_bwd(e, P, sh, w, x, G, st));
+    RET_IF(encoder_bwd(e, P, sh, w, x, G, st, nullptr, nullptr, false, e->wgrad_overlap != 0 && ensure_side(e)));
     if (dx != nullptr) cudaMemcpyAsync(dx, w.g, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     return 0;
 }
@@ -972,7 +1081,7 @@ int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void
     RET_IF(gemm(e, st, w.dy, Kd, shp(msh, e->msh_wdecT), Kd, w.g, D, M, D, K, EPI_STORE, 1));
     RET_IF(launch_cast_bf16(w.g, w.g16, static_cast<size_t>(M) * D, st));
     if (!(e->drop_p > 0.0f)) RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], M, D, D, st));
-    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user));
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, false, e->wgrad_overlap != 0 && ensure_side(e)));
     RET_IF(embed_bwd(e, w, G, st));
     if (progress != nullptr) progress(-1, user);
     if (replace_sel != nullptr)
