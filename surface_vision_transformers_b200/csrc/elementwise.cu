@@ -389,30 +389,33 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* a
 // =================================================================================================
 // LayerNorm backward + residual-gradient add + column reductions
 // =================================================================================================
+// Register budget: 112 per thread, so that THREE 128-thread CTAs (12 warps) fit an SM next to a resident weight-gradient
+// GEMM CTA (20 k of the 64 k registers; engine.cu runs those GEMMs on a side stream under this kernel) and four when the
+// kernel has the SM to itself.  gamma therefore lives in shared memory, not in registers.
 template <int NVEC, bool CLSG = false>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ x,
+__global__ void __maxnreg__(NVEC <= 3 ? 112 : 232) ln_bwd_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* g_in, float* g_out,
                                                      __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, float* __restrict__ colsum_out, int M,
                                                      int D, int period) {
-    extern __shared__ float red[];  // [3][D] block-level partial column sums
+    extern __shared__ float red[];  // [3][D] block-level partial column sums, then [D] gamma
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
     const float inv_d = 1.0f / D;
+    const float4* sgm = reinterpret_cast<const float4*>(red + 3 * D);
     griddep_launch();
     for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.0f;
-    __syncthreads();
     griddep_wait();
-    float4 acc_g[NVEC], acc_b[NVEC], acc_c[NVEC], gm[NVEC];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) red[3 * D + i] = gamma[i];
+    __syncthreads();
+    float4 acc_g[NVEC], acc_b[NVEC], acc_c[NVEC];
 #pragma unroll
     for (int k = 0; k < NVEC; ++k) {
         acc_g[k] = make_float4(0, 0, 0, 0);
         acc_b[k] = make_float4(0, 0, 0, 0);
         acc_c[k] = make_float4(0, 0, 0, 0);
-        const int i = lane + k * 32;
-        gm[k] = (i < nvec) ? reinterpret_cast<const float4*>(gamma)[i] : make_float4(0, 0, 0, 0);
     }
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
         const float mu = mean[row], rs = rstd[row];
@@ -445,7 +448,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                 xh[k] = make_float4((xh[k].x - mu) * rs, (xh[k].y - mu) * rs, (xh[k].z - mu) * rs, (xh[k].w - mu) * rs);
                 acc_g[k].x += d.x * xh[k].x; acc_g[k].y += d.y * xh[k].y; acc_g[k].z += d.z * xh[k].z; acc_g[k].w += d.w * xh[k].w;
                 acc_b[k].x += d.x; acc_b[k].y += d.y; acc_b[k].z += d.z; acc_b[k].w += d.w;
-                dy[k] = make_float4(d.x * gm[k].x, d.y * gm[k].y, d.z * gm[k].z, d.w * gm[k].w);
+                const float4 gm = sgm[i];
+                dy[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
                 s1 += dy[k].x + dy[k].y + dy[k].z + dy[k].w;
                 s2 += dy[k].x * xh[k].x + dy[k].y * xh[k].y + dy[k].z * xh[k].z + dy[k].w * xh[k].w;
             }
@@ -505,23 +509,26 @@ int launch_ln_bwd(const void* da_bf16, const float* x, const float* mean, const 
                   int M, int D, cudaStream_t st, int g_in_period) {
     if (M <= 0) return 0;
     if (!ln_shape_ok(D)) return -2;
-    const int wpb = 8;
+    // 128-thread CTAs: three of them fit next to a weight-gradient GEMM CTA (see the kernel); SVIT_LN_BWD_WARPS=8 brings the
+    // former 256-thread CTAs back for A/B timing.  The same number of warps (and rows per warp) either way.
+    static const int wpb_env = getenv("SVIT_LN_BWD_WARPS") != nullptr ? atoi(getenv("SVIT_LN_BWD_WARPS")) : 4;
+    const int wpb = (wpb_env == 8) ? 8 : 4;
     int blocks = (M + wpb - 1) / wpb;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 32 / wpb) blocks = 148 * 32 / wpb;
     const int nv = (D + 127) / 128;
     if (g_in_period > 0) {
         if (g_in == g_out) {
             set_error("ln_bwd: a compact incoming gradient cannot alias the full-size output");
             return -2;
         }
-        SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV, true>, dim3(blocks), dim3(wpb * 32), 3 * D * sizeof(float), st,
+        SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV, true>, dim3(blocks), dim3(wpb * 32), 4 * D * sizeof(float), st,
                                          reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
                                          reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D,
                                          g_in_period)));
         SVIT_CHECK_LAUNCH("ln_bwd");
         return 0;
     }
-    SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV>, dim3(blocks), dim3(wpb * 32), 3 * D * sizeof(float), st,
+    SVIT_LN_DISPATCH(nv, (launch_pdl(ln_bwd_kernel<NV>, dim3(blocks), dim3(wpb * 32), 4 * D * sizeof(float), st,
                                      reinterpret_cast<const __nv_bfloat16*>(da_bf16), x, mean, rstd, gamma, g_in, g_out,
                                      reinterpret_cast<__nv_bfloat16*>(g_out_bf16), dgamma, dbeta, colsum_out, M, D, 0)));
     SVIT_CHECK_LAUNCH("ln_bwd");

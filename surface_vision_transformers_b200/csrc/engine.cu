@@ -515,15 +515,27 @@ static int embed_fwd(const svit_engine* e, const void* sh, Ws& w, const PackDesc
 }
 
 // g / g16 hold dL/dx0
-static int embed_bwd(const svit_engine* e, Ws& w, float* G, cudaStream_t st) {
+// use_side: the weight-gradient GEMM runs on the side stream under the HBM-bound position / cls / bias reduction (see encoder_bwd)
+static int embed_bwd(const svit_engine* e, Ws& w, float* G, cudaStream_t st, bool use_side = false) {
     if (e->drop_emb_p > 0.0f) {
         const size_t n = static_cast<size_t>(w.M) * e->D;
         RET_IF(launch_dropout_scale(w.g, nullptr, n, 0, drop_emb(e), st));
         RET_IF(launch_cast_bf16(w.g, w.g16, n, st));
     }
-    RET_IF(launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], w.B, e->T, e->D, st));
     cudaMemsetAsync(w.dWp, 0, static_cast<size_t>(e->D) * e->Kp * sizeof(float), st);
-    RET_IF(wgrad(e, st, w.g16, e->D, w.Apatch, e->Kp, w.dWp, e->Kp, w.M, e->D, e->Kp));
+    if (use_side && e->side != nullptr && e->wgrad_overlap != 0) {
+        cudaEventRecord(e->ev_fork, st);
+        cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+        int rc = wgrad(e, e->side, w.g16, e->D, w.Apatch, e->Kp, w.dWp, e->Kp, w.M, e->D, e->Kp);
+        cudaEventRecord(e->ev_join[0], e->side);
+        int rc2 = launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], w.B, e->T, e->D, st);
+        cudaStreamWaitEvent(st, e->ev_join[0], 0);   // joined on every path
+        RET_IF(rc);
+        RET_IF(rc2);
+    } else {
+        RET_IF(launch_embed_bwd(w.g, G + e->poff[P_POS], G + e->poff[P_CLS], G + e->poff[P_PE_B], w.B, e->T, e->D, st));
+        RET_IF(wgrad(e, st, w.g16, e->D, w.Apatch, e->Kp, w.dWp, e->Kp, w.M, e->D, e->Kp));
+    }
     return launch_unpermute_patch_wgrad(w.dWp, G + e->poff[P_PE_W], e->D, e->C, e->V, e->Kp, st);
 }
 
@@ -950,8 +962,9 @@ int svit_backward(svit_engine* e, const float* P, const void* sh, void* ws_ptr, 
                            e->drop_p > 0.0f ? nullptr : G + e->poff[pidx_layer(e->depth - 1, FC2_B)], B, cls ? 1 : e->T, e->D,
                            e->NC, e->cfg.pool_mean, 1e-5f, st));
     if (progress != nullptr) progress(e->depth, user);
-    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, cls, e->wgrad_overlap != 0 && ensure_side(e)));
-    RET_IF(embed_bwd(e, w, G, st));
+    const bool side = e->wgrad_overlap != 0 && ensure_side(e);
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, cls, side));
+    RET_IF(embed_bwd(e, w, G, st, side));
     if (progress != nullptr) progress(-1, user);
     return 0;
 }
@@ -1081,8 +1094,9 @@ int svit_mpp_backward(svit_engine* e, const float* P, const void* sh, const void
     RET_IF(gemm(e, st, w.dy, Kd, shp(msh, e->msh_wdecT), Kd, w.g, D, M, D, K, EPI_STORE, 1));
     RET_IF(launch_cast_bf16(w.g, w.g16, static_cast<size_t>(M) * D, st));
     if (!(e->drop_p > 0.0f)) RET_IF(launch_colsum_bf16(w.g16, G + e->poff[pidx_layer(e->depth - 1, FC2_B)], M, D, D, st));
-    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, false, e->wgrad_overlap != 0 && ensure_side(e)));
-    RET_IF(embed_bwd(e, w, G, st));
+    const bool side = e->wgrad_overlap != 0 && ensure_side(e);
+    RET_IF(encoder_bwd(e, P, sh, w, w.x0, G, st, progress, user, false, side));
+    RET_IF(embed_bwd(e, w, G, st, side));
     if (progress != nullptr) progress(-1, user);
     if (replace_sel != nullptr)
         RET_IF(launch_mask_token_grad(w.g, replace_sel, P + e->poff[P_PE_W], w.rvec, gmt, B, e->T, D, K, st));
