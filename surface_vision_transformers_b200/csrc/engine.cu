@@ -62,7 +62,9 @@ static bool ensure_side(svit_engine* e) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     cudaStream_t s = nullptr;
-    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) {
+    // high priority: the weight-gradient CTAs claim their SM before the LayerNorm CTAs fill it (SVIT_SIDE_PRIO=0: lowest, A/B)
+    const bool low = getenv("SVIT_SIDE_PRIO") != nullptr && atoi(getenv("SVIT_SIDE_PRIO")) == 0;
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, low ? lo : hi) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
@@ -421,26 +423,37 @@ static int encoder_bwd(const svit_engine* e, const float* P, const void* sh, Ws&
             // ---- last block under cls pooling: B rows; c.g / c.g16 hold dL/dx_final of token 0 (head backward) ----
             const ClsWs c = cls_views(e, L, w.B);
             const int Mc = w.B;
+            // (side stream: the B-row weight-gradient GEMMs are one-tile kernels that would otherwise each hold the whole
+            // stream for ~15 us; the full-size QKV one runs under the LayerNorm backward like in the other layers)
+            bf16* c_g16mid = ov ? w.g16b : c.g16;   // compact [B, D]: LN2' must not overwrite what wgrad fc2 still reads
             RET_IF(gemm(e, st, c.g16, D, shp(sh, e->sh_w2T) + static_cast<size_t>(l) * mlp * D, D, w.du, mlp, Mc, mlp, D,
                         EPI_MUL, 0, nullptr, c.u));
-            RET_IF(wgrad(e, st, c.g16, D, c.h, mlp, gp(FC2_W), mlp, Mc, D, mlp));
+            cudaStream_t sw = ov ? ss : st;
+            if (ov) fork();
+            RET_IF(wgrad(e, sw, c.g16, D, c.h, mlp, gp(FC2_W), mlp, Mc, D, mlp));
+            RET_IF(wgrad(e, sw, w.du, mlp, c.a2, D, gp(FC1_W), D, Mc, mlp, D, gp(FC1_B)));
+            if (ov) mark(1);   // (re-recorded after every group: the side stream is in order, the last record covers all)
             RET_IF(gemm(e, st, w.du, mlp, shp(sh, e->sh_w1T) + static_cast<size_t>(l) * D * mlp, mlp, w.da, D, Mc, D, mlp,
                         EPI_STORE, 0));
-            RET_IF(wgrad(e, st, w.du, mlp, c.a2, D, gp(FC1_W), D, Mc, mlp, D, gp(FC1_B)));
-            RET_IF(launch_ln_bwd(w.da, c.xmid, c.mean2, c.rstd2, pp(LN2_W), c.g, c.g, c.g16, gp(LN2_W), gp(LN2_B), gp(OUT_B), Mc,
+            RET_IF(launch_ln_bwd(w.da, c.xmid, c.mean2, c.rstd2, pp(LN2_W), c.g, c.g, c_g16mid, gp(LN2_W), gp(LN2_B), gp(OUT_B), Mc,
                                  D, st));
-            RET_IF(gemm(e, st, c.g16, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, Mc, I, D, EPI_STORE, 0));
-            RET_IF(wgrad(e, st, c.g16, D, c.O, I, gp(OUT_W), I, Mc, D, I));
+            RET_IF(gemm(e, st, c_g16mid, D, shp(sh, e->sh_oT) + static_cast<size_t>(l) * I * D, D, w.dO, I, Mc, I, D, EPI_STORE, 0));
+            if (ov) fork();
+            RET_IF(wgrad(e, sw, c_g16mid, D, c.O, I, gp(OUT_W), I, Mc, D, I));
+            if (ov) mark(1);
             if (progress != nullptr) progress(SVIT_STAGE_WINDOW + l, user);
             AttnClsBwdDesc cb{L.qkv, c.prob, w.dO, w.dqkv, w.B, e->H, e->T, scale};
             RET_IF(launch_attn_cls_bwd(cb, st));
             RET_IF(gemm(e, st, w.dqkv, 3 * I, shp(sh, e->sh_qkvT) + static_cast<size_t>(l) * D * 3 * I, 3 * I, w.da, D, M, D,
                         3 * I, EPI_STORE, 0));
-            RET_IF(wgrad(e, st, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+            if (ov) fork();
+            RET_IF(wgrad(e, sw, w.dqkv, 3 * I, L.a1, D, gp(QKV_W), D, M, 3 * I, D));
+            if (ov) mark(1);
             // the residual gradient entering LN1' is g_mid in the cls rows (compact c.g) and zero elsewhere
             float* cs0 = (l > 0) ? G + e->poff[pidx_layer(l - 1, FC2_B)] : nullptr;
             RET_IF(launch_ln_bwd(w.da, xin, L.mean1, L.rstd1, pp(LN1_W), c.g, w.g, w.g16, gp(LN1_W), gp(LN1_B), cs0, M, D, st,
                                  e->T));
+            join(1);   // the layer below overwrites du / dqkv / g16b, and the stage is reported final next
             if (progress != nullptr) progress(l, user);
             continue;
         }
