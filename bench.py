@@ -53,6 +53,7 @@ DEFAULT_WORKLOAD = "sit_small_ico2_scan_age_train"
 # `ncu --set full` summary of the kernels of the current build (scripts/ncu_top.py + scripts/ncu_summary.py); re-captured
 # whenever a kernel changes -- roofline.traffic is read from it
 NCU_SUMMARY = "r02c_ncu_top_summary.json"
+NCU_SUMMARY_ATTN_BWD = "r02i_ncu_attn_bwd_summary.json"   # attention backward re-captured after the dead-pair shortcut
 
 
 def executed_gflop(wl):
@@ -567,16 +568,18 @@ def main():
         a_ach = a_flops / (a_ms * 1e-3) / 1e12
         a_traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as f:
+            a_src = NCU_SUMMARY_ATTN_BWD if (a_key == "attn_bwd" and os.path.exists(
+                os.path.join(ROOT, "profiles", NCU_SUMMARY_ATTN_BWD))) else NCU_SUMMARY
+            with open(os.path.join(ROOT, "profiles", a_src)) as f:
                 prof = json.load(f)[a_key + "_kernel"]
             if (B, Hh, T) == (256, 6, 321):
                 a_traffic = prof["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
-            pass
+            a_src = NCU_SUMMARY
         roof = dict(bound="tensor", kernel="%s (one CTA per (sample, head); B=%d H=%d T=%d d=64; %s*T^2*64 flop per head at the "
                                           "unpadded T)" % (a_name, B, Hh, T, "4" if kind == "infer" else "10"),
                     achieved=a_ach, peak=peaks["tflops_burst"], unit="TFLOP/s", frac=a_ach / peaks["tflops_burst"],
-                    traffic=a_traffic, traffic_source="profiles/" + NCU_SUMMARY + " (dram__bytes_read.sum + "
+                    traffic=a_traffic, traffic_source="profiles/" + a_src + " (dram__bytes_read.sum + "
                     "dram__bytes_write.sum, one ncu --set full launch)" if a_traffic else None,
                     algorithmic_bytes=a_bytes, peak_source=peaks["source"] + " (burst: kernel timed alone)",
                     us_per_launch=a_ms * 1e3, flops_per_launch=a_flops,
