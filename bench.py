@@ -500,6 +500,24 @@ def main():
         def gemm():
             _lib.check(lib.svit_gemm_tn(_lib.ptr(A), _lib.ptr(W), _lib.ptr(o1), _lib.ptr(o2), _lib.vp(0), _lib.ptr(bias),
                                         _lib.vp(0), 1, M, H4, D, D, D, H4, mode, 0, sms, st), "gemm")
+        # `peak` below is the BURST figure of MEASURED_PEAKS.json (a kernel timed alone), so the kernel is timed in burst
+        # conditions too: one idle second first -- right after the long power-capped step the SM clock is still at its
+        # sustained value (~1.7 GHz) and a 20-launch loop (3-6 ms) is over before it recovers.  The clock is sampled
+        # through NVML right after the loop and reported next to the duration.
+        def sm_clock_now():
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)).encode())
+                except Exception:
+                    h = pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)
+                return float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                return None
+
+        torch.cuda.synchronize()
+        time.sleep(1.0)
         for _ in range(3):
             gemm()
         torch.cuda.synchronize()
@@ -509,6 +527,7 @@ def main():
         for _ in range(n_it):
             gemm()
         e1.record()
+        k_mhz = sm_clock_now()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / n_it
         flops = 2.0 * M * H4 * D
@@ -529,7 +548,7 @@ def main():
                     "dram__bytes_write.sum, one ncu --set full launch)" if traffic else None,
                     algorithmic_bytes=2.0 * M * D + 2.0 * H4 * D + (2 if mode == 5 else 1) * 2.0 * M * H4,
                     peak_source=peaks["source"] + " (burst: kernel timed alone)",
-                    us_per_launch=k_ms * 1e3, flops_per_launch=flops)
+                    us_per_launch=k_ms * 1e3, flops_per_launch=flops, sm_mhz_during_launches=k_mhz)
         roof_gemm["hbm_view"] = dict(achieved=roof_gemm["algorithmic_bytes"] / (k_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
                                      unit="GB/s", frac=roof_gemm["algorithmic_bytes"] / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                      note="arithmetic intensity %.0f flop/B is below the machine balance: by the roofline "
@@ -556,6 +575,8 @@ def main():
                 _lib.check(lib.svit_attn_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse), _lib.ptr(dqkv), B, Hh, T, scale, st), "attn_bwd")
             a_flops, a_name, a_key = 10.0 * T * T * 64 * B * Hh, "attn_bwd_kernel", "attn_bwd"
             a_bytes = 2.0 * B * T * (3 * inner + inner + inner + 3 * inner) + 4.0 * B * Hh * T
+        torch.cuda.synchronize()
+        time.sleep(1.0)
         for _ in range(3):
             attn()
         torch.cuda.synchronize()
@@ -563,6 +584,7 @@ def main():
         for _ in range(n_it):
             attn()
         e1.record()
+        a_mhz = sm_clock_now()
         torch.cuda.synchronize()
         a_ms = e0.elapsed_time(e1) / n_it
         a_ach = a_flops / (a_ms * 1e-3) / 1e12
@@ -582,7 +604,7 @@ def main():
                     traffic=a_traffic, traffic_source="profiles/" + a_src + " (dram__bytes_read.sum + "
                     "dram__bytes_write.sum, one ncu --set full launch)" if a_traffic else None,
                     algorithmic_bytes=a_bytes, peak_source=peaks["source"] + " (burst: kernel timed alone)",
-                    us_per_launch=a_ms * 1e3, flops_per_launch=a_flops,
+                    us_per_launch=a_ms * 1e3, flops_per_launch=a_flops, sm_mhz_during_launches=a_mhz,
                     share_of_step=a_ms * (m["depth"] - (1 if cls_only_last else 0)) / ms_step,
                     note="fraction of the dense bf16 tensor peak at the algorithmic flop count; T=%d pads to 128x96 tiles "
                          "(executed MMA work is 1.4x the algorithmic count at T=321) and the kernel is bound by the latency "

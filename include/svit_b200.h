@@ -115,7 +115,14 @@ int svit_forward_ex(svit_engine* e, const float* params, const void* shadow, voi
  * layer l, ~270 us at the benchmark shape) is not a persistent kernel -- its CTAs are handed to the SMs one by one, so a
  * collective launched now shares the chip with it gracefully, whereas under a persistent GEMM (static tile schedule over
  * all SMs) it stalls the CTAs whose SMs it holds.  The gradients that are final at that point are those of the stages
- * reported so far (layers > l and the head). */
+ * reported so far (layers > l and the head).
+ *
+ * Streams: everything the caller may observe is ordered on `stream`.  Internally the backward entry points (svit_backward,
+ * svit_encoder_backward, svit_mpp_backward) enqueue the weight-gradient GEMMs on one engine-owned high-priority side stream
+ * that forks from and joins `stream` through events, so that they run next to the HBM-bound LayerNorm backward kernels
+ * (engine.cu, encoder_bwd).  The side stream is joined before every progress callback (the gradients of a reported stage are
+ * final in `stream` order) and before the entry point returns; it takes part in CUDA-graph capture of `stream` like any forked
+ * stream.  SVIT_WGRAD_OVERLAP=0 keeps every kernel on `stream`. */
 #define SVIT_STAGE_WINDOW 1000
 typedef void (*svit_progress_fn)(int stage, void* user);
 int svit_backward(svit_engine* e, const float* params, const void* shadow, void* workspace, int batch,
