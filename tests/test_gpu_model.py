@@ -272,6 +272,70 @@ def test_cls_pooling_last_block_on_token_zero_only(cfg, B, monkeypatch):
         assert torch.isfinite(res["cls"][1][n]).all() and (res["cls"][1][n].abs().sum() > 0) == (go[n].abs().sum() > 0), n
 
 
+@pytest.mark.parametrize("cfg,B,pool", [
+    (dict(dim=384, depth=3, heads=6, mlp_dim=1536, num_patches=320, num_vertices=153), 6, "cls"),   # B-row last block + two full layers
+    (dict(dim=384, depth=2, heads=6, mlp_dim=1536, num_patches=320, num_vertices=153), 4, "mean"),  # every layer full size
+    (dict(dim=192, depth=3, heads=3, mlp_dim=768, num_patches=80, num_vertices=45), 9, "cls"),      # stand-alone LayerNorm kernels
+])
+def test_side_stream_weight_gradients_equal_single_stream(cfg, B, pool, monkeypatch):
+    """engine.cu runs the weight-gradient GEMMs on a side stream next to the LayerNorm backward kernels (DESIGN 3d;
+    SVIT_WGRAD_OVERLAP, read at svit_create: 0 = one stream, 1 = the adjacent wgrad only, 2 = default).  The kernels and their
+    operands are the same in every mode, so every gradient must agree with the one-stream engine up to the order of the fp32
+    reductions (red.global.add / atomicAdd) -- a missing event dependency would show up as a stale or half-written operand.
+    Repeated backward passes (the scratch buffers are reused from layer to layer and from pass to pass) must agree as well."""
+    torch.manual_seed(11)
+    oracle = OracleSiT(pool=pool, **cfg).to(DEV)
+    x = torch.randn(B, 4, cfg["num_patches"], cfg["num_vertices"], device=DEV)
+    y = torch.rand(B, device=DEV) * 19 + 26
+    grads = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("SVIT_WGRAD_OVERLAP", mode)
+        m = svit.SiT(pool=pool, **cfg)
+        m.load_state_dict(oracle.state_dict())
+        m.to(DEV)
+        runs = []
+        for _ in range(3):
+            m.zero_grad(set_to_none=True)
+            torch.nn.functional.mse_loss(m(x).squeeze(), y).backward()
+            runs.append({n: p.grad.clone() for n, p in m.named_parameters()})
+        torch.cuda.synchronize()
+        for r in runs[1:]:
+            for n in r:
+                assert rel_l2(r[n], runs[0][n]) < 1e-5, (mode, n)
+        grads[mode] = runs[0]
+    for mode in ("1", "2"):
+        worst = max((rel_l2(grads[mode][n], grads["0"][n]), n) for n in grads["0"])
+        print(f"SVIT_WGRAD_OVERLAP={mode} vs 0: worst tensor {worst[1]} {worst[0]:.2e}")
+        assert worst[0] < 1e-5, (mode, worst)
+
+
+def test_side_stream_weight_gradients_mpp(monkeypatch):
+    """The same through the MPP module (svit_mpp_backward: every layer full size, decoder in front of the encoder backward)."""
+    cfg = dict(dim=384, depth=2, heads=6, mlp_dim=1536, num_patches=320, num_vertices=153)
+    torch.manual_seed(12)
+    ref = svit.SiT(**cfg)
+    x = torch.randn(3, 4, cfg["num_patches"], cfg["num_vertices"], device=DEV)
+    K = 4 * cfg["num_vertices"]
+    grads = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("SVIT_WGRAD_OVERLAP", mode)
+        sit = svit.SiT(**cfg)
+        sit.load_state_dict(ref.state_dict())
+        torch.manual_seed(13)
+        ssl = svit.masked_patch_pretraining(transformer=sit, dim_in=cfg["dim"], dim_out=K, device=DEV, mask_prob=0.5,
+                                            replace_prob=0.8, swap_prob=0.02, channels=4,
+                                            num_vertices=cfg["num_vertices"]).to(DEV)
+        torch.manual_seed(14)                      # same masks in both modes (device and CPU generators, Appendix B order)
+        loss, _ = ssl(x)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads[mode] = {n: p.grad.clone() for n, p in ssl.named_parameters() if p.grad is not None}
+    assert grads["0"].keys() == grads["2"].keys()
+    worst = max((rel_l2(grads["2"][n], grads["0"][n]), n) for n in grads["0"])
+    print(f"MPP, SVIT_WGRAD_OVERLAP=2 vs 0: worst tensor {worst[1]} {worst[0]:.2e}")
+    assert worst[0] < 1e-5, worst
+
+
 def test_raw_mesh_ingestion_matches_prepatched():
     """raw ico-6 mesh + on-device gather/z-score == pre-patched input through the same network."""
     cfg = dict(dim=192, depth=2, heads=3, mlp_dim=768, num_patches=320, num_vertices=153)
